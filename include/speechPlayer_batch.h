@@ -1,0 +1,86 @@
+/*
+ * Batched / device-resident entry points of the B200-native Klatt engine.
+ *
+ * A batch is N independent players ("streams") whose frame queues, state blocks and
+ * (optionally) output live in HBM.  It is the same engine as the per-handle API of
+ * speechPlayer.h -- one stream of a batch behaves exactly like one reference player
+ * (reference src/frame.cpp:41-115 frame manager + src/speechWaveGenerator.cpp:197-214
+ * generate loop) -- but all streams advance in ONE kernel launch, and frames can be
+ * handed over in bulk, either from host memory or as device pointers (no copies).
+ *
+ * Plain C: device pointers and the CUDA stream travel as void* (a cudaStream_t is a
+ * pointer; pass NULL for the default stream, or e.g. torch.cuda.current_stream().cuda_stream).
+ * All calls return 0 on success, -1 on failure (speechPlayer_lastError() has the reason).
+ */
+#ifndef NVSP_B200_SPEECHPLAYER_BATCH_H
+#define NVSP_B200_SPEECHPLAYER_BATCH_H
+
+#include "speechPlayer.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct speechPlayer_batch speechPlayer_batch_t;
+
+/* streamIds: HOST array [numStreams] of noise-stream ids (Philox counter words 2,3), or NULL for 0..N-1.
+ * The batch lives on the calling thread's current CUDA device (NVSP_DEVICE / LOCAL_RANK / 0 on first use). */
+speechPlayer_batch_t *speechPlayer_batchCreate(int sampleRate, unsigned int numStreams, int precision,
+                                               int noiseMode, uint64_t seed, const uint64_t *streamIds);
+void speechPlayer_batchDestroy(speechPlayer_batch_t *batch);
+
+/* Put every stream back into the state speechPlayer_initialize leaves it in and rewind the queue cursors
+ * (the queued frames stay).  Asynchronous on cudaStream. */
+int speechPlayer_batchReset(speechPlayer_batch_t *batch, void *cudaStream);
+
+/* Replace the frame queues of all streams.  Stream s owns requests [offsets[s], offsets[s+1]) of the flat
+ * arrays, in queue order (the batch equivalent of calling speechPlayer_queueFrame that many times on a fresh
+ * player; fadeDuration 0 counts as 1).  userIndex / isNull may be NULL.
+ *   ...Host:   all pointers are HOST memory; contents are copied to the device (async on cudaStream when the
+ *              memory is pinned) before the call returns control of them.
+ *   ...Device: all pointers are DEVICE memory that must stay valid and unchanged until the next
+ *              SetFrames / Destroy; nothing is copied.  This is the HBM-resident path of bench.py's `value`. */
+int speechPlayer_batchSetFramesHost(speechPlayer_batch_t *batch, const int64_t *offsets,
+                                    const speechPlayer_frame_t *frames, const unsigned int *minFrameDuration,
+                                    const unsigned int *fadeDuration, const int *userIndex,
+                                    const unsigned char *isNull, void *cudaStream);
+int speechPlayer_batchSetFramesDevice(speechPlayer_batch_t *batch, const void *dOffsets /* int64[N+1] */,
+                                      const void *dFrames /* double[total][47] */, const void *dMinDur /* u32 */,
+                                      const void *dFadeDur /* u32 */, const void *dUserIndex /* i32 or NULL */,
+                                      const void *dIsNull /* u8 or NULL */, void *cudaStream);
+
+/* SPEECHPLAYER_NOISE_REPLAY: device int32 [numStreams][drawsPerStream]; draw d of stream s is at [s][d]. */
+int speechPlayer_batchSetNoiseReplayDevice(speechPlayer_batch_t *batch, const void *dDraws, size_t drawsPerStream);
+
+/* Advance every stream by up to sampleCount ticks (one kernel launch on cudaStream).
+ *   dOut             device int16, row s starts at dOut + s*rowStride (rowStride in samples, >= sampleCount;
+ *                    a multiple of 8 with a 16-byte aligned base enables 16-byte stores)
+ *   dSamplesWritten  device u32 [numStreams] or NULL: per-stream count, < sampleCount iff that queue drained
+ * Returns immediately after enqueueing (asynchronous). */
+int speechPlayer_batchSynthesizeDevice(speechPlayer_batch_t *batch, unsigned int sampleCount, void *dOut,
+                                       size_t rowStride, void *dSamplesWritten, void *cudaStream);
+
+/* Same, into HOST memory [numStreams][sampleCount] (row-major, no padding); blocks until the samples have
+ * landed.  samplesWritten (host u32 [numStreams]) may be NULL.  Returns total samples or -1. */
+long long speechPlayer_batchSynthesizeHost(speechPlayer_batch_t *batch, unsigned int sampleCount, sample *out,
+                                           unsigned int *samplesWritten);
+
+/* getLastIndex of every stream (host int32 [numStreams]); synchronises with the batch's last launch. */
+int speechPlayer_batchGetLastIndices(speechPlayer_batch_t *batch, int *lastIndex);
+
+/* Counters of the launches issued so far by this batch: kernels launched, ticks requested (streams x sampleCount). */
+int speechPlayer_batchGetLaunchStats(speechPlayer_batch_t *batch, unsigned long long *kernelLaunches,
+                                     unsigned long long *ticksRequested);
+
+/* Pure host helper (no device needed): samples a fully pre-queued stream yields,
+ * sum_j max(M_j+1, max(F_j,1)+2)  -- the occupancy law of the reference frame manager (src/frame.cpp:41-80). */
+unsigned long long speechPlayer_timelineSamples(const unsigned int *minFrameDuration,
+                                                const unsigned int *fadeDuration, unsigned int n);
+
+/* Library / build identification: "nvspeechplayer_b200 <ver> sm_100a". */
+const char *speechPlayer_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

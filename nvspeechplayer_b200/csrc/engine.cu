@@ -1,0 +1,783 @@
+// Host side of the B200-native Klatt engine: the C-ABI of include/speechPlayer.h and
+// include/speechPlayer_batch.h, the handle table, per-player request mirrors, device buffers and launches.
+//
+// Mapping to the reference (paths relative to the reference checkout):
+//   speechPlayer_handleInfo_t + the five exports   src/speechPlayer.cpp:19-53   -> Player, speechPlayer_*()
+//   FrameManagerImpl::queueFrame (copy-in, purge)   src/frame.cpp:90-115         -> Player::queue(): the host keeps
+//        the not-yet-consumed requests (a purge drops them here); the state-machine half of purge
+//        (sampleCounter / snapshot of curFrame, :105-111) runs as the prologue of the next launch
+//   LockableObject (queueFrame vs synthesize)        src/lock.h:25-53             -> Player::mu
+//   the per-sample loop                              src/speechWaveGenerator.cpp:197-214 -> klatt_f64.cu / klatt_f32.cu
+//
+// There is no CPU synthesis path in this library: every sample comes out of a CUDA kernel.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/speechPlayer.h"
+#include "../../include/speechPlayer_batch.h"
+#include "glibc_rand.h"
+#include "klatt_common.h"
+
+namespace klatt {
+cudaError_t launchKlattF64(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
+                           int16_t *out, size_t rowStride, uint32_t *samplesWritten, StreamResult *results,
+                           NoiseConfig noise, cudaStream_t stream);
+cudaError_t launchKlattF32(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
+                           int16_t *out, size_t rowStride, uint32_t *samplesWritten, StreamResult *results,
+                           NoiseConfig noise, cudaStream_t stream);
+}  // namespace klatt
+
+using namespace klatt;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_lastError;
+
+static int fail(const std::string &what) {
+	g_lastError = what;
+	if (getenv("NVSP_VERBOSE")) fprintf(stderr, "[nvspeechplayer_b200] %s\n", what.c_str());
+	return -1;
+}
+static bool cudaOk(cudaError_t e, const char *what) {
+	if (e == cudaSuccess) return true;
+	fail(std::string(what) + ": " + cudaGetErrorString(e));
+	return false;
+}
+#define CU(call) do { if (!cudaOk((call), #call)) return -1; } while (0)
+#define CUP(call) do { if (!cudaOk((call), #call)) return nullptr; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device selection: the calling thread's current device, unless NVSP_DEVICE says otherwise (applied once)
+// ------------------------------------------------------------------------------------------------
+static int pickDevice() {
+	static std::once_flag once;
+	static int chosen = -1;
+	std::call_once(once, [] {
+		const char *e = getenv("NVSP_DEVICE");
+		if (e && *e) chosen = atoi(e);
+	});
+	int dev = 0;
+	if (chosen >= 0) {
+		if (cudaSetDevice(chosen) != cudaSuccess) return -1;
+		return chosen;
+	}
+	if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+	return dev;
+}
+
+struct DeviceGuard {
+	int prev = -1;
+	explicit DeviceGuard(int dev) {
+		cudaGetDevice(&prev);
+		if (prev != dev) cudaSetDevice(dev);
+		else prev = -1;
+	}
+	~DeviceGuard() {
+		if (prev >= 0) cudaSetDevice(prev);
+	}
+};
+
+// grow-only device buffer
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	bool reserve(size_t bytes) {
+		if (bytes <= cap) return true;
+		size_t want = std::max(bytes, cap * 2);
+		void *np = nullptr;
+		if (!cudaOk(cudaMalloc(&np, want), "cudaMalloc")) return false;
+		if (p) cudaFree(p);
+		p = np; cap = want;
+		return true;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+	}
+	template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device kernels of the host layer
+// ------------------------------------------------------------------------------------------------
+__global__ void init_states_kernel(StreamState *states, uint32_t n) {
+	// the state speechPlayer_initialize leaves a player in: src/frame.cpp:85-88 (curFrame zeroed, curFrameIsNULL,
+	// sampleCounter 0, lastUserIndex -1, old request = zeroed NULL request), src/speechWaveGenerator.cpp:37,49,
+	// 104-110 (phases, noise memory and resonator histories zero).  The memset before this kernel did the zeros.
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	states[i].fm.lastUserIndex = -1;
+	states[i].fm.curIsNull = 1;
+	states[i].fm.oldIsNull = 1;
+}
+
+__global__ void build_descs_kernel(StreamDesc *descs, StreamState *states, const int64_t *offsets, const double *frames,
+                                   const uint32_t *minDur, const uint32_t *fadeDur, const int32_t *userIndex,
+                                   const uint8_t *isNull, const int32_t *replay, uint64_t drawsPerStream,
+                                   const uint64_t *streamIds, uint32_t n) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	StreamDesc d;
+	int64_t a = offsets ? offsets[i] : 0, b = offsets ? offsets[i + 1] : 0;
+	d.state = states + i;
+	d.frames = frames ? frames + (size_t)a * kNumParams : nullptr;
+	d.minDur = minDur ? minDur + a : nullptr;
+	d.fadeDur = fadeDur ? fadeDur + a : nullptr;
+	d.userIndex = userIndex ? userIndex + a : nullptr;
+	d.isNull = isNull ? isNull + a : nullptr;
+	d.replay = replay ? replay + (size_t)i * drawsPerStream : nullptr;
+	d.replayLen = replay ? drawsPerStream : 0;
+	d.replayBase = 0;
+	d.streamId = streamIds ? streamIds[i] : i;
+	d.qCount = (uint32_t)(b - a);
+	d.qBase = 0;
+	descs[i] = d;
+}
+
+static cudaError_t launchRender(int precision, const StreamDesc *descs, uint32_t n, int sampleRate, uint32_t sampleCount,
+                                int16_t *out, size_t rowStride, uint32_t *written, StreamResult *results,
+                                NoiseConfig noise, cudaStream_t stream) {
+	if (precision == kPrecisionF64)
+		return launchKlattF64(descs, n, sampleRate, sampleCount, out, rowStride, written, results, noise, stream);
+	return launchKlattF32(descs, n, sampleRate, sampleCount, out, rowStride, written, results, noise, stream);
+}
+
+static cudaError_t initStates(StreamState *states, uint32_t n, cudaStream_t stream) {
+	cudaError_t e = cudaMemsetAsync(states, 0, sizeof(StreamState) * (size_t)n, stream);
+	if (e != cudaSuccess) return e;
+	init_states_kernel<<<(n + 255) / 256, 256, 0, stream>>>(states, n);
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chunked render into HOST memory: kernel(chunk c) overlaps the D2H copy of chunk c-1 (two staging buffers,
+// compute stream + copy stream).  hostOut is [n][sampleCount]; rows are gathered with a 2-D copy.
+// ------------------------------------------------------------------------------------------------
+struct HostPipe {
+	cudaStream_t compute = nullptr, copy = nullptr;
+	cudaEvent_t kernelDone[2] = {nullptr, nullptr}, copyDone[2] = {nullptr, nullptr};
+	DevBuf stage[2], res[2];
+	StreamResult *hostRes = nullptr;  // pinned, [2][n]
+	size_t hostResCap = 0;
+	bool ok = false;
+	bool init() {
+		if (ok) return true;
+		if (!cudaOk(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		if (!cudaOk(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		for (int i = 0; i < 2; ++i) {
+			if (!cudaOk(cudaEventCreateWithFlags(&kernelDone[i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+			if (!cudaOk(cudaEventCreateWithFlags(&copyDone[i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+		}
+		ok = true;
+		return true;
+	}
+	void destroy() {
+		if (!ok) return;
+		for (int i = 0; i < 2; ++i) {
+			stage[i].release(); res[i].release();
+			cudaEventDestroy(kernelDone[i]); cudaEventDestroy(copyDone[i]);
+		}
+		if (hostRes) cudaFreeHost(hostRes);
+		cudaStreamDestroy(compute); cudaStreamDestroy(copy);
+		ok = false;
+	}
+};
+
+static size_t stagingBudgetBytes() {
+	const char *e = getenv("NVSP_STAGE_MB");
+	size_t mb = (e && *e) ? (size_t)atoll(e) : 512;
+	return std::max<size_t>(mb, 1) << 20;
+}
+
+// returns total samples written, or -1.  perStream (host, [n]) and lastResults (host, [n]) are optional outputs.
+static long long renderToHost(HostPipe &pipe, int precision, const StreamDesc *dDescs, uint32_t n, int sampleRate,
+                              uint32_t sampleCount, int16_t *hostOut, uint32_t *perStream, StreamResult *lastResults,
+                              NoiseConfig noise, unsigned long long *launchCounter) {
+	if (!pipe.init()) return -1;
+	if (n == 0 || sampleCount == 0) return 0;
+	// chunk length in ticks: whole request if it fits the staging budget, else a multiple of 8
+	size_t budget = stagingBudgetBytes();
+	uint64_t maxTicks = std::max<uint64_t>(budget / ((size_t)n * sizeof(int16_t)), 8);
+	uint32_t chunk = (uint32_t)std::min<uint64_t>(sampleCount, maxTicks);
+	if (chunk < sampleCount) chunk &= ~7u;
+	size_t stride = ((size_t)chunk + 7) & ~(size_t)7;
+	for (int i = 0; i < 2; ++i) {
+		if (!pipe.stage[i].reserve(stride * n * sizeof(int16_t))) return -1;
+		if (!pipe.res[i].reserve((size_t)n * sizeof(StreamResult))) return -1;
+	}
+	if (pipe.hostResCap < (size_t)n * 2) {
+		if (pipe.hostRes) cudaFreeHost(pipe.hostRes);
+		pipe.hostRes = nullptr;
+		if (!cudaOk(cudaMallocHost((void **)&pipe.hostRes, sizeof(StreamResult) * (size_t)n * 2), "cudaMallocHost")) return -1;
+		pipe.hostResCap = (size_t)n * 2;
+	}
+	std::vector<uint32_t> total(n, 0);
+	uint32_t numChunks = (sampleCount + chunk - 1) / chunk;
+	auto harvest = [&](uint32_t c) -> bool {  // wait for chunk c's copies and fold its results
+		int b = c & 1;
+		if (!cudaOk(cudaEventSynchronize(pipe.copyDone[b]), "cudaEventSynchronize")) return false;
+		const StreamResult *r = pipe.hostRes + (size_t)b * n;
+		for (uint32_t s = 0; s < n; ++s) total[s] += r[s].written;
+		if (lastResults && c + 1 == numChunks) memcpy(lastResults, r, sizeof(StreamResult) * (size_t)n);
+		return true;
+	};
+	for (uint32_t c = 0; c < numChunks; ++c) {
+		int b = c & 1;
+		uint32_t t0 = c * chunk, len = std::min(chunk, sampleCount - t0);
+		if (c >= 2 && !harvest(c - 2)) return -1;  // staging buffer b is free again
+		CU(launchRender(precision, dDescs, n, sampleRate, len, pipe.stage[b].as<int16_t>(), stride, nullptr,
+		                pipe.res[b].as<StreamResult>(), noise, pipe.compute));
+		if (launchCounter) ++*launchCounter;
+		CU(cudaEventRecord(pipe.kernelDone[b], pipe.compute));
+		CU(cudaStreamWaitEvent(pipe.copy, pipe.kernelDone[b], 0));
+		CU(cudaMemcpy2DAsync(hostOut + t0, (size_t)sampleCount * sizeof(int16_t), pipe.stage[b].p,
+		                     stride * sizeof(int16_t), (size_t)len * sizeof(int16_t), n, cudaMemcpyDeviceToHost, pipe.copy));
+		CU(cudaMemcpyAsync(pipe.hostRes + (size_t)b * n, pipe.res[b].p, sizeof(StreamResult) * (size_t)n,
+		                   cudaMemcpyDeviceToHost, pipe.copy));
+		CU(cudaEventRecord(pipe.copyDone[b], pipe.copy));
+		// the next kernel that reuses staging buffer b must wait for this copy
+		CU(cudaStreamWaitEvent(pipe.compute, pipe.copyDone[b], 0));
+	}
+	for (uint32_t c = (numChunks >= 2 ? numChunks - 2 : 0); c < numChunks; ++c)
+		if (!harvest(c)) return -1;
+	long long sum = 0;
+	for (uint32_t s = 0; s < n; ++s) {
+		sum += total[s];
+		if (perStream) perStream[s] = total[s];
+	}
+	return sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// process-global glibc-compatible noise (reference: libc rand() shared by every player)
+// ------------------------------------------------------------------------------------------------
+static std::mutex g_noiseMu;
+static GlibcRand g_noise;
+
+// ------------------------------------------------------------------------------------------------
+// Player: one reference "speechPlayer_handleInfo_t"
+// ------------------------------------------------------------------------------------------------
+struct Player {
+	std::mutex mu;
+	int device = 0, sampleRate = 0, precision = kPrecisionF64, noiseMode = kNoiseGlibc;
+	uint64_t seed = 0, streamId = 0;
+	StreamState *dState = nullptr;
+	// host mirror of the requests the device has not consumed yet (src/frame.cpp:33 frameRequestQueue)
+	std::vector<double> frames;
+	std::vector<uint32_t> minDur, fadeDur;
+	std::vector<int32_t> userIndex;
+	std::vector<uint8_t> isNull;
+	uint32_t qBase = 0;       // absolute index of mirror[0] == requests consumed so far
+	bool mirrorDirty = false; // device copy of the mirror is stale
+	bool purgePending = false;
+	DevBuf dFrames, dMin, dFade, dUix, dNull, dReplay, dDesc;
+	std::vector<int32_t> replayHost;  // kNoiseReplay: user-provided draws
+	bool replayDirty = false;
+	uint64_t generated = 0;   // samples generated so far (== draws/2)
+	int lastIndex = -1;
+	HostPipe pipe;
+
+	size_t pending() const { return minDur.size(); }
+
+	void push(const speechPlayer_frame_t *frame, unsigned m, unsigned f, int ux, bool null) {
+		size_t at = frames.size();
+		frames.resize(at + kNumParams, 0.0);
+		if (frame && !null) memcpy(&frames[at], frame, sizeof(double) * kNumParams);
+		minDur.push_back(m);
+		fadeDur.push_back(f);
+		userIndex.push_back(ux);
+		isNull.push_back((null || !frame) ? 1 : 0);
+		mirrorDirty = true;
+	}
+	void clearQueue() {
+		frames.clear(); minDur.clear(); fadeDur.clear(); userIndex.clear(); isNull.clear();
+		mirrorDirty = true;
+	}
+	void dropConsumed(uint32_t newHead) {
+		uint32_t k = newHead - qBase;
+		if (k == 0) return;
+		k = (uint32_t)std::min<size_t>(k, pending());
+		frames.erase(frames.begin(), frames.begin() + (size_t)k * kNumParams);
+		minDur.erase(minDur.begin(), minDur.begin() + k);
+		fadeDur.erase(fadeDur.begin(), fadeDur.begin() + k);
+		userIndex.erase(userIndex.begin(), userIndex.begin() + k);
+		isNull.erase(isNull.begin(), isNull.begin() + k);
+		qBase = newHead;
+		mirrorDirty = true;
+	}
+	// upload what changed and fill the descriptor for the next launch (on `stream`)
+	int prepare(StreamDesc &d, uint32_t sampleCount, cudaStream_t stream) {
+		if (mirrorDirty) {
+			size_t n = pending();
+			if (n) {
+				if (!dFrames.reserve(n * kNumParams * sizeof(double)) || !dMin.reserve(n * 4) || !dFade.reserve(n * 4) ||
+				    !dUix.reserve(n * 4) || !dNull.reserve(n))
+					return -1;
+				CU(cudaMemcpyAsync(dFrames.p, frames.data(), n * kNumParams * sizeof(double), cudaMemcpyHostToDevice, stream));
+				CU(cudaMemcpyAsync(dMin.p, minDur.data(), n * 4, cudaMemcpyHostToDevice, stream));
+				CU(cudaMemcpyAsync(dFade.p, fadeDur.data(), n * 4, cudaMemcpyHostToDevice, stream));
+				CU(cudaMemcpyAsync(dUix.p, userIndex.data(), n * 4, cudaMemcpyHostToDevice, stream));
+				CU(cudaMemcpyAsync(dNull.p, isNull.data(), n, cudaMemcpyHostToDevice, stream));
+			}
+			mirrorDirty = false;
+		}
+		if (purgePending) {
+			static const uint32_t one = 1;
+			CU(cudaMemcpyAsync(&dState->fm.purgePending, &one, 4, cudaMemcpyHostToDevice, stream));
+			purgePending = false;
+		}
+		d.state = dState;
+		d.frames = dFrames.as<double>();
+		d.minDur = dMin.as<uint32_t>();
+		d.fadeDur = dFade.as<uint32_t>();
+		d.userIndex = dUix.as<int32_t>();
+		d.isNull = dNull.as<uint8_t>();
+		d.qCount = (uint32_t)pending();
+		d.qBase = qBase;
+		d.streamId = streamId;
+		d.replay = nullptr; d.replayLen = 0; d.replayBase = 0;
+		if (noiseMode == kNoiseGlibc) {
+			// draws for the worst case (every tick generates); the caller rewinds the generator afterwards
+			size_t n = (size_t)sampleCount * 2;
+			std::vector<int32_t> draws(n);
+			g_noise.fill(draws.data(), n);
+			if (!dReplay.reserve(n * 4)) return -1;
+			CU(cudaMemcpyAsync(dReplay.p, draws.data(), n * 4, cudaMemcpyHostToDevice, stream));
+			CU(cudaStreamSynchronize(stream));  // `draws` dies at scope exit
+			d.replay = dReplay.as<int32_t>(); d.replayLen = n; d.replayBase = generated * 2;
+		} else if (noiseMode == kNoiseReplay) {
+			if (replayDirty) {
+				if (!dReplay.reserve(std::max<size_t>(replayHost.size(), 1) * 4)) return -1;
+				CU(cudaMemcpyAsync(dReplay.p, replayHost.data(), replayHost.size() * 4, cudaMemcpyHostToDevice, stream));
+				replayDirty = false;
+			}
+			d.replay = dReplay.as<int32_t>(); d.replayLen = replayHost.size(); d.replayBase = 0;
+		}
+		return 0;
+	}
+	void absorb(const StreamResult &r, uint32_t written) {
+		generated += written;
+		lastIndex = r.lastUserIndex;
+		dropConsumed(r.qHead);
+	}
+	void destroy() {
+		DeviceGuard g(device);
+		pipe.destroy();
+		dFrames.release(); dMin.release(); dFade.release(); dUix.release(); dNull.release(); dReplay.release(); dDesc.release();
+		if (dState) cudaFree(dState);
+		dState = nullptr;
+	}
+};
+
+// handle table: handles are small integers (index+1) cast to void*, so they survive a round trip through a C int
+static std::mutex g_tableMu;
+static std::vector<Player *> g_players;
+
+static Player *lookup(speechPlayer_handle_t h) {
+	uintptr_t v = reinterpret_cast<uintptr_t>(h);
+	std::lock_guard<std::mutex> lk(g_tableMu);
+	if (v == 0 || v > g_players.size()) return nullptr;
+	return g_players[v - 1];
+}
+
+static int envPrecision() {
+	const char *e = getenv("NVSP_PRECISION");
+	if (e && (!strcmp(e, "fp32") || !strcmp(e, "f32") || !strcmp(e, "FP32"))) return kPrecisionF32;
+	return kPrecisionF64;
+}
+static int envNoise() {
+	const char *e = getenv("NVSP_NOISE");
+	if (e && !strcmp(e, "philox")) return kNoisePhilox;
+	return kNoiseGlibc;
+}
+static uint64_t envSeed() {
+	const char *e = getenv("NVSP_SEED");
+	return (e && *e) ? strtoull(e, nullptr, 0) : 0xB200ull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: per-handle API
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *speechPlayer_lastError(void) { return g_lastError.c_str(); }
+const char *speechPlayer_version(void) { return "nvspeechplayer_b200 0.1 sm_100a"; }
+
+speechPlayer_handle_t speechPlayer_initializeEx(int sampleRate, int precision, int noiseMode, uint64_t seed,
+                                                uint64_t streamId) {
+	g_lastError.clear();
+	if (sampleRate <= 0) { fail("sampleRate must be positive"); return nullptr; }
+	if (precision != kPrecisionF64 && precision != kPrecisionF32) { fail("unknown precision"); return nullptr; }
+	if (noiseMode < kNoisePhilox || noiseMode > kNoiseReplay) { fail("unknown noise mode"); return nullptr; }
+	int dev = pickDevice();
+	if (dev < 0) { fail("no usable CUDA device (this library has no CPU fallback)"); return nullptr; }
+	Player *p = new Player;
+	p->device = dev; p->sampleRate = sampleRate; p->precision = precision; p->noiseMode = noiseMode;
+	p->seed = seed; p->streamId = streamId;
+	DeviceGuard g(dev);
+	if (!cudaOk(cudaMalloc((void **)&p->dState, sizeof(StreamState)), "cudaMalloc(state)") ||
+	    !cudaOk(initStates(p->dState, 1, nullptr), "init state") ||
+	    !cudaOk(cudaStreamSynchronize(nullptr), "init state sync")) {
+		delete p;
+		return nullptr;
+	}
+	std::lock_guard<std::mutex> lk(g_tableMu);
+	for (size_t i = 0; i < g_players.size(); ++i)
+		if (!g_players[i]) {
+			g_players[i] = p;
+			return reinterpret_cast<speechPlayer_handle_t>(i + 1);
+		}
+	g_players.push_back(p);
+	return reinterpret_cast<speechPlayer_handle_t>(g_players.size());
+}
+
+speechPlayer_handle_t speechPlayer_initialize(int sampleRate) {
+	uint64_t sid;
+	{
+		std::lock_guard<std::mutex> lk(g_tableMu);
+		sid = g_players.size();
+	}
+	return speechPlayer_initializeEx(sampleRate, envPrecision(), envNoise(), envSeed(), sid);
+}
+
+void speechPlayer_queueFrame(speechPlayer_handle_t playerHandle, speechPlayer_frame_t *framePtr,
+                             unsigned int minFrameDuration, unsigned int fadeDuration, int userIndex, bool purgeQueue) {
+	Player *p = lookup(playerHandle);
+	if (!p) return;
+	std::lock_guard<std::mutex> lk(p->mu);
+	if (purgeQueue) {  // src/frame.cpp:103-112: drop everything still queued; the rest happens on the device
+		p->clearQueue();
+		p->purgePending = true;
+	}
+	p->push(framePtr, minFrameDuration, fadeDuration, userIndex, framePtr == nullptr);
+}
+
+int speechPlayer_queueFrames(speechPlayer_handle_t playerHandle, const speechPlayer_frame_t *frames,
+                             const unsigned int *minFrameDuration, const unsigned int *fadeDuration,
+                             const int *userIndex, const unsigned char *isNull, unsigned int n) {
+	Player *p = lookup(playerHandle);
+	if (!p) return fail("bad handle");
+	if (n && (!minFrameDuration || !fadeDuration)) return fail("durations missing");
+	std::lock_guard<std::mutex> lk(p->mu);
+	for (unsigned i = 0; i < n; ++i) {
+		bool null = (isNull && isNull[i]) || !frames;
+		p->push(frames ? frames + i : nullptr, minFrameDuration[i], fadeDuration[i], userIndex ? userIndex[i] : -1, null);
+	}
+	return 0;
+}
+
+int speechPlayer_setNoiseReplay(speechPlayer_handle_t playerHandle, const int32_t *draws, size_t numDraws) {
+	Player *p = lookup(playerHandle);
+	if (!p) return fail("bad handle");
+	std::lock_guard<std::mutex> lk(p->mu);
+	if (p->noiseMode != kNoiseReplay) return fail("handle was not created with SPEECHPLAYER_NOISE_REPLAY");
+	p->replayHost.assign(draws, draws + numDraws);
+	p->replayDirty = true;
+	return 0;
+}
+
+void speechPlayer_seedNoise(unsigned int seed) {
+	std::lock_guard<std::mutex> lk(g_noiseMu);
+	g_noise.seed(seed);
+}
+
+long long speechPlayer_synthesizeBatch(speechPlayer_handle_t *handles, unsigned int numHandles, unsigned int sampleCount,
+                                       sample *sampleBuf, unsigned int *samplesWritten) {
+	g_lastError.clear();
+	if (numHandles == 0 || sampleCount == 0) return 0;
+	if (!handles || !sampleBuf) return fail("null argument");
+	std::vector<Player *> ps(numHandles);
+	for (unsigned i = 0; i < numHandles; ++i) {
+		ps[i] = lookup(handles[i]);
+		if (!ps[i]) return fail("bad handle in batch");
+		if (ps[i]->precision != ps[0]->precision || ps[i]->sampleRate != ps[0]->sampleRate ||
+		    ps[i]->device != ps[0]->device || ps[i]->noiseMode != ps[0]->noiseMode || ps[i]->seed != ps[0]->seed)
+			return fail("handles of one batch must share device, sample rate, precision and noise mode");
+	}
+	// lock in address order; a handle may appear only once
+	std::vector<Player *> order(ps);
+	std::sort(order.begin(), order.end());
+	if (std::adjacent_find(order.begin(), order.end()) != order.end()) return fail("duplicate handle in batch");
+	for (Player *p : order) p->mu.lock();
+	struct Unlock {
+		std::vector<Player *> &o;
+		~Unlock() { for (Player *p : o) p->mu.unlock(); }
+	} unlock{order};
+
+	Player *lead = ps[0];
+	DeviceGuard g(lead->device);
+	if (!lead->pipe.init()) return -1;
+	cudaStream_t stream = lead->pipe.compute;
+	std::unique_lock<std::mutex> noiseLock(g_noiseMu, std::defer_lock);
+	GlibcRand checkpoint;
+	if (lead->noiseMode == kNoiseGlibc) {
+		noiseLock.lock();
+		checkpoint = g_noise;
+	}
+	std::vector<StreamDesc> descs(numHandles);
+	for (unsigned i = 0; i < numHandles; ++i)
+		if (ps[i]->prepare(descs[i], sampleCount, stream) != 0) return -1;
+	if (!lead->dDesc.reserve(sizeof(StreamDesc) * (size_t)numHandles)) return -1;
+	CU(cudaMemcpyAsync(lead->dDesc.p, descs.data(), sizeof(StreamDesc) * (size_t)numHandles, cudaMemcpyHostToDevice, stream));
+	CU(cudaStreamSynchronize(stream));
+	std::vector<uint32_t> written(numHandles);
+	std::vector<StreamResult> results(numHandles);
+	NoiseConfig nc{lead->noiseMode, lead->seed};
+	long long total = renderToHost(lead->pipe, lead->precision, lead->dDesc.as<StreamDesc>(), numHandles, lead->sampleRate,
+	                               sampleCount, reinterpret_cast<int16_t *>(sampleBuf), written.data(), results.data(), nc,
+	                               nullptr);
+	if (total < 0) return -1;
+	for (unsigned i = 0; i < numHandles; ++i) {
+		ps[i]->absorb(results[i], written[i]);
+		if (samplesWritten) samplesWritten[i] = written[i];
+	}
+	if (lead->noiseMode == kNoiseGlibc && numHandles == 1) {
+		// the reference consumes exactly two rand() calls per generated sample: rewind to that point
+		g_noise = checkpoint;
+		g_noise.skip((uint64_t)written[0] * 2);
+	}
+	return total;
+}
+
+int speechPlayer_synthesize(speechPlayer_handle_t playerHandle, unsigned int sampleCount, sample *sampleBuf) {
+	unsigned int written = 0;
+	long long r = speechPlayer_synthesizeBatch(&playerHandle, 1, sampleCount, sampleBuf, &written);
+	if (r < 0) return -1;
+	return (int)written;
+}
+
+int speechPlayer_getLastIndex(speechPlayer_handle_t playerHandle) {
+	Player *p = lookup(playerHandle);
+	return p ? p->lastIndex : -1;  // read without the lock, like src/frame.cpp:117-119
+}
+
+void speechPlayer_terminate(speechPlayer_handle_t playerHandle) {
+	uintptr_t v = reinterpret_cast<uintptr_t>(playerHandle);
+	Player *p = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(g_tableMu);
+		if (v == 0 || v > g_players.size()) return;
+		p = g_players[v - 1];
+		g_players[v - 1] = nullptr;
+	}
+	if (!p) return;
+	{ std::lock_guard<std::mutex> lk(p->mu); }
+	p->destroy();
+	delete p;
+}
+
+unsigned long long speechPlayer_timelineSamples(const unsigned int *minFrameDuration, const unsigned int *fadeDuration,
+                                                unsigned int n) {
+	unsigned long long t = 0;
+	for (unsigned i = 0; i < n; ++i) {
+		unsigned long long m = minFrameDuration[i], f = fadeDuration[i] > 1 ? fadeDuration[i] : 1;
+		t += std::max(m + 1, f + 2);
+	}
+	return t;
+}
+
+// test hook: the first n values of the glibc-compatible generator after seed(s)
+void speechPlayer_debugGlibcRand(unsigned int seed, unsigned int n, int32_t *out) {
+	GlibcRand r;
+	r.seed(seed);
+	r.fill(out, n);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: batch API
+// ------------------------------------------------------------------------------------------------
+struct speechPlayer_batch {
+	int device = 0, sampleRate = 0, precision = kPrecisionF32, noiseMode = kNoisePhilox;
+	uint64_t seed = 0;
+	uint32_t n = 0;
+	StreamState *dStates = nullptr;
+	StreamDesc *dDescs = nullptr;
+	uint64_t *dStreamIds = nullptr;
+	// current queue arrays (borrowed device pointers, or the owned copies below)
+	const int64_t *dOffsets = nullptr;
+	const double *dFrames = nullptr;
+	const uint32_t *dMin = nullptr, *dFade = nullptr;
+	const int32_t *dUix = nullptr;
+	const uint8_t *dNull = nullptr;
+	const int32_t *dReplay = nullptr;
+	uint64_t drawsPerStream = 0;
+	DevBuf ownOffsets, ownFrames, ownMin, ownFade, ownUix, ownNull;
+	HostPipe pipe;
+	unsigned long long launches = 0, ticks = 0;
+	std::mutex mu;
+
+	int rebuildDescs(cudaStream_t stream) {
+		build_descs_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dDescs, dStates, dOffsets, dFrames, dMin, dFade, dUix, dNull,
+		                                                        dReplay, drawsPerStream, dStreamIds, n);
+		CU(cudaGetLastError());
+		++launches;
+		return 0;
+	}
+};
+
+extern "C" {
+
+speechPlayer_batch_t *speechPlayer_batchCreate(int sampleRate, unsigned int numStreams, int precision, int noiseMode,
+                                               uint64_t seed, const uint64_t *streamIds) {
+	g_lastError.clear();
+	if (sampleRate <= 0 || numStreams == 0) { fail("bad sampleRate / numStreams"); return nullptr; }
+	if (precision != kPrecisionF64 && precision != kPrecisionF32) { fail("unknown precision"); return nullptr; }
+	if (noiseMode != kNoisePhilox && noiseMode != kNoiseReplay) { fail("batch noise mode must be PHILOX or REPLAY"); return nullptr; }
+	int dev = pickDevice();
+	if (dev < 0) { fail("no usable CUDA device (this library has no CPU fallback)"); return nullptr; }
+	DeviceGuard g(dev);
+	speechPlayer_batch *b = new speechPlayer_batch;
+	b->device = dev; b->sampleRate = sampleRate; b->precision = precision; b->noiseMode = noiseMode; b->seed = seed;
+	b->n = numStreams;
+	bool ok = cudaOk(cudaMalloc((void **)&b->dStates, sizeof(StreamState) * (size_t)numStreams), "cudaMalloc(states)") &&
+	          cudaOk(cudaMalloc((void **)&b->dDescs, sizeof(StreamDesc) * (size_t)numStreams), "cudaMalloc(descs)") &&
+	          cudaOk(cudaMalloc((void **)&b->dStreamIds, sizeof(uint64_t) * (size_t)numStreams), "cudaMalloc(ids)");
+	if (ok) {
+		std::vector<uint64_t> ids(numStreams);
+		for (uint32_t i = 0; i < numStreams; ++i) ids[i] = streamIds ? streamIds[i] : i;
+		ok = cudaOk(cudaMemcpy(b->dStreamIds, ids.data(), sizeof(uint64_t) * (size_t)numStreams, cudaMemcpyHostToDevice), "ids H2D") &&
+		     cudaOk(initStates(b->dStates, numStreams, nullptr), "init states") && b->rebuildDescs(nullptr) == 0 &&
+		     cudaOk(cudaStreamSynchronize(nullptr), "sync");
+	}
+	if (!ok) {
+		speechPlayer_batchDestroy(b);
+		return nullptr;
+	}
+	return b;
+}
+
+void speechPlayer_batchDestroy(speechPlayer_batch_t *b) {
+	if (!b) return;
+	DeviceGuard g(b->device);
+	cudaDeviceSynchronize();
+	b->pipe.destroy();
+	b->ownOffsets.release(); b->ownFrames.release(); b->ownMin.release(); b->ownFade.release(); b->ownUix.release(); b->ownNull.release();
+	if (b->dStates) cudaFree(b->dStates);
+	if (b->dDescs) cudaFree(b->dDescs);
+	if (b->dStreamIds) cudaFree(b->dStreamIds);
+	delete b;
+}
+
+int speechPlayer_batchReset(speechPlayer_batch_t *b, void *cudaStream) {
+	if (!b) return fail("null batch");
+	std::lock_guard<std::mutex> lk(b->mu);
+	DeviceGuard g(b->device);
+	CU(initStates(b->dStates, b->n, static_cast<cudaStream_t>(cudaStream)));
+	b->launches += 1;
+	return 0;
+}
+
+int speechPlayer_batchSetFramesDevice(speechPlayer_batch_t *b, const void *dOffsets, const void *dFrames, const void *dMinDur,
+                                      const void *dFadeDur, const void *dUserIndex, const void *dIsNull, void *cudaStream) {
+	if (!b) return fail("null batch");
+	if (!dOffsets || !dMinDur || !dFadeDur) return fail("offsets and durations are required");
+	std::lock_guard<std::mutex> lk(b->mu);
+	DeviceGuard g(b->device);
+	b->dOffsets = static_cast<const int64_t *>(dOffsets);
+	b->dFrames = static_cast<const double *>(dFrames);
+	b->dMin = static_cast<const uint32_t *>(dMinDur);
+	b->dFade = static_cast<const uint32_t *>(dFadeDur);
+	b->dUix = static_cast<const int32_t *>(dUserIndex);
+	b->dNull = static_cast<const uint8_t *>(dIsNull);
+	return b->rebuildDescs(static_cast<cudaStream_t>(cudaStream));
+}
+
+int speechPlayer_batchSetFramesHost(speechPlayer_batch_t *b, const int64_t *offsets, const speechPlayer_frame_t *frames,
+                                    const unsigned int *minFrameDuration, const unsigned int *fadeDuration,
+                                    const int *userIndex, const unsigned char *isNull, void *cudaStream) {
+	if (!b) return fail("null batch");
+	if (!offsets || !minFrameDuration || !fadeDuration) return fail("offsets and durations are required");
+	cudaStream_t stream = static_cast<cudaStream_t>(cudaStream);
+	size_t total = (size_t)offsets[b->n];
+	{
+		std::lock_guard<std::mutex> lk(b->mu);
+		DeviceGuard g(b->device);
+		if (!b->ownOffsets.reserve(sizeof(int64_t) * ((size_t)b->n + 1)) ||
+		    !b->ownFrames.reserve(std::max<size_t>(total, 1) * sizeof(speechPlayer_frame_t)) ||
+		    !b->ownMin.reserve(std::max<size_t>(total, 1) * 4) || !b->ownFade.reserve(std::max<size_t>(total, 1) * 4) ||
+		    !b->ownUix.reserve(std::max<size_t>(total, 1) * 4) || !b->ownNull.reserve(std::max<size_t>(total, 1)))
+			return -1;
+		CU(cudaMemcpyAsync(b->ownOffsets.p, offsets, sizeof(int64_t) * ((size_t)b->n + 1), cudaMemcpyHostToDevice, stream));
+		if (total) {
+			if (frames) CU(cudaMemcpyAsync(b->ownFrames.p, frames, total * sizeof(speechPlayer_frame_t), cudaMemcpyHostToDevice, stream));
+			CU(cudaMemcpyAsync(b->ownMin.p, minFrameDuration, total * 4, cudaMemcpyHostToDevice, stream));
+			CU(cudaMemcpyAsync(b->ownFade.p, fadeDuration, total * 4, cudaMemcpyHostToDevice, stream));
+			if (userIndex) CU(cudaMemcpyAsync(b->ownUix.p, userIndex, total * 4, cudaMemcpyHostToDevice, stream));
+			if (isNull) CU(cudaMemcpyAsync(b->ownNull.p, isNull, total, cudaMemcpyHostToDevice, stream));
+		}
+	}
+	int r = speechPlayer_batchSetFramesDevice(b, b->ownOffsets.p, frames ? b->ownFrames.p : nullptr, b->ownMin.p, b->ownFade.p,
+	                                          userIndex ? b->ownUix.p : nullptr, isNull ? b->ownNull.p : nullptr, cudaStream);
+	if (r != 0) return r;
+	DeviceGuard g(b->device);
+	CU(cudaStreamSynchronize(stream));  // the caller's host arrays may be reused now
+	return 0;
+}
+
+int speechPlayer_batchSetNoiseReplayDevice(speechPlayer_batch_t *b, const void *dDraws, size_t drawsPerStream) {
+	if (!b) return fail("null batch");
+	if (b->noiseMode != kNoiseReplay) return fail("batch was not created with SPEECHPLAYER_NOISE_REPLAY");
+	std::lock_guard<std::mutex> lk(b->mu);
+	DeviceGuard g(b->device);
+	b->dReplay = static_cast<const int32_t *>(dDraws);
+	b->drawsPerStream = drawsPerStream;
+	return b->rebuildDescs(nullptr);
+}
+
+int speechPlayer_batchSynthesizeDevice(speechPlayer_batch_t *b, unsigned int sampleCount, void *dOut, size_t rowStride,
+                                       void *dSamplesWritten, void *cudaStream) {
+	if (!b) return fail("null batch");
+	if (!dOut) return fail("null output");
+	if (rowStride < sampleCount) return fail("rowStride < sampleCount");
+	std::lock_guard<std::mutex> lk(b->mu);
+	DeviceGuard g(b->device);
+	NoiseConfig nc{b->noiseMode, b->seed};
+	CU(launchRender(b->precision, b->dDescs, b->n, b->sampleRate, sampleCount, static_cast<int16_t *>(dOut), rowStride,
+	                static_cast<uint32_t *>(dSamplesWritten), nullptr, nc, static_cast<cudaStream_t>(cudaStream)));
+	b->launches += 1;
+	b->ticks += (unsigned long long)b->n * sampleCount;
+	return 0;
+}
+
+long long speechPlayer_batchSynthesizeHost(speechPlayer_batch_t *b, unsigned int sampleCount, sample *out,
+                                           unsigned int *samplesWritten) {
+	if (!b) return fail("null batch");
+	if (!out) return fail("null output");
+	std::lock_guard<std::mutex> lk(b->mu);
+	DeviceGuard g(b->device);
+	CU(cudaDeviceSynchronize());  // frames / resets enqueued on other streams must have landed
+	NoiseConfig nc{b->noiseMode, b->seed};
+	long long r = renderToHost(b->pipe, b->precision, b->dDescs, b->n, b->sampleRate, sampleCount,
+	                           reinterpret_cast<int16_t *>(out), samplesWritten, nullptr, nc, &b->launches);
+	if (r >= 0) b->ticks += (unsigned long long)b->n * sampleCount;
+	return r;
+}
+
+int speechPlayer_batchGetLastIndices(speechPlayer_batch_t *b, int *lastIndex) {
+	if (!b || !lastIndex) return fail("null argument");
+	std::lock_guard<std::mutex> lk(b->mu);
+	DeviceGuard g(b->device);
+	CU(cudaDeviceSynchronize());
+	// lastUserIndex is the first word of every state block
+	CU(cudaMemcpy2D(lastIndex, sizeof(int), b->dStates, sizeof(StreamState), sizeof(int), b->n, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+int speechPlayer_batchGetLaunchStats(speechPlayer_batch_t *b, unsigned long long *kernelLaunches,
+                                     unsigned long long *ticksRequested) {
+	if (!b) return fail("null batch");
+	if (kernelLaunches) *kernelLaunches = b->launches;
+	if (ticksRequested) *ticksRequested = b->ticks;
+	return 0;
+}
+
+}  // extern "C"

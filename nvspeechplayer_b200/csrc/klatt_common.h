@@ -1,0 +1,134 @@
+// Shared definitions of the B200-native Klatt engine: parameter slots, per-stream device state,
+// stream descriptors.  Header-only, usable from host C++ and from CUDA.
+//
+// Parameter order is the ABI of speechPlayer_frame_t (reference src/frame.h:20-47).
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define KLATT_HD __host__ __device__ __forceinline__
+#else
+#define KLATT_HD inline
+#endif
+
+namespace klatt {
+
+enum Param : int {
+	kVoicePitch = 0, kVibratoPitchOffset, kVibratoSpeed, kVoiceTurbulenceAmplitude, kGlottalOpenQuotient,
+	kVoiceAmplitude, kAspirationAmplitude,
+	kCf1, kCf2, kCf3, kCf4, kCf5, kCf6, kCfN0, kCfNP,
+	kCb1, kCb2, kCb3, kCb4, kCb5, kCb6, kCbN0, kCbNP,
+	kCaNP, kFricationAmplitude,
+	kPf1, kPf2, kPf3, kPf4, kPf5, kPf6,
+	kPb1, kPb2, kPb3, kPb4, kPb5, kPb6,
+	kPa1, kPa2, kPa3, kPa4, kPa5, kPa6,
+	kParallelBypass, kPreFormantGain, kOutputGain, kEndVoicePitch,
+	kNumParams
+};
+static_assert(kNumParams == 47, "frame ABI is 47 doubles");
+
+// The 14 two-pole sections in the order the engine numbers them:
+//   0 rN0 (anti), 1 rNP, 2..7 cascade r6..r1 (order of use, reference speechWaveGenerator.cpp:149-156),
+//   8..13 parallel r1..r6 (reference :172-177).
+constexpr int kNumResonators = 14;
+constexpr int kResN0 = 0, kResNP = 1, kResCascade = 2, kResParallel = 8;
+
+// frame slot holding the centre frequency / bandwidth of resonator r
+KLATT_HD constexpr int resFreqParam(int r) {
+	return r == kResN0 ? kCfN0 : r == kResNP ? kCfNP : r < kResParallel ? (kCf6 - (r - kResCascade)) : (kPf1 + (r - kResParallel));
+}
+KLATT_HD constexpr int resBwParam(int r) {
+	return r == kResN0 ? kCbN0 : r == kResNP ? kCbNP : r < kResParallel ? (kCb6 - (r - kResCascade)) : (kPb1 + (r - kResParallel));
+}
+
+enum Precision : int { kPrecisionF64 = 0, kPrecisionF32 = 1 };
+enum NoiseMode : int { kNoisePhilox = 0, kNoiseGlibc = 1, kNoiseReplay = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// Frame-manager state of one stream: the members of the reference's FrameManagerImpl
+// (src/frame.cpp:30-39) plus the queue cursor.  Lives in HBM between launches; precision-independent.
+// ---------------------------------------------------------------------------------------------
+struct FrameMgrState {
+	// first 16 bytes are what the host reads back after a launch
+	int32_t lastUserIndex;   // frame.cpp:39
+	uint32_t qHead;          // requests consumed so far (absolute count)
+	uint32_t counter;        // sampleCounter, frame.cpp:38
+	uint8_t hasNew;          // newFrameRequest != NULL
+	uint8_t curIsNull;       // frame.cpp:37
+	uint8_t oldIsNull;       // oldFrameRequest->NULLFrame
+	uint8_t newIsNull;
+	uint32_t oldM;           // oldFrameRequest->minNumSamples
+	uint32_t newM, newF;     // of the request being faded in
+	uint32_t purgePending;   // host-set: a purgeQueue=true request arrived since the last launch (frame.cpp:103-112);
+	                         // the next launch applies the purge prologue and clears it
+	double oldInc, newInc;   // voicePitchInc of old / new
+	double oldFrame[kNumParams];
+	double newFrame[kNumParams];
+	double curFrame[kNumParams];
+};
+
+// Generator state, FP64 parity kernel: members of SpeechWaveGeneratorImpl and its parts
+// (src/speechWaveGenerator.cpp:34,49,93-101,184-192).  Coefficients are a pure function of curFrame and are
+// recomputed on entry, so the reference's setOnce/frequency/bandwidth cache needs no storage.
+struct GenStateF64 {
+	double pitchPos, vibratoPos;   // FrequencyGenerator::lastCyclePos x2
+	double aspLast, fricLast;      // NoiseGenerator::lastValue x2
+	double p1[kNumResonators], p2[kNumResonators];
+	uint64_t samplesGenerated;     // == rand() draws consumed / 2
+};
+
+// Generator state, FP32 production kernel (DESIGN.md "FP32 formulation").
+constexpr int kNumDirect = 17;   // frame params used directly by the DSP each tick (not via coefficients)
+struct GenStateF32 {
+	double pitchPos;               // glottal phase in cycles, FP64 by design
+	uint64_t samplesGenerated;
+	uint32_t vibratoPos;           // vibrato phase, 2^-32 cycles
+	float aspLast, fricLast;
+	uint32_t coefValid;            // 0 until the coefficient state below has been derived from curFrame
+	float y[kNumResonators];       // delta-form state: last output (rN0: last input)
+	float d[kNumResonators];       //                   last output difference (rN0: last input difference)
+	float zre[kNumResonators];     // zeta = 1 - pole, tracked through fades
+	float zim[kNumResonators];
+	float r2[kNumResonators];      // |pole|^2
+	float dir[kNumDirect];         // current value of the directly used params
+};
+
+struct StreamState {
+	FrameMgrState fm;
+	union {
+		GenStateF64 f64;
+		GenStateF32 f32;
+	} gen;
+};
+
+// What a render kernel needs to know about one stream.  Built on the host (per-handle API) or by
+// build_descs_kernel (batch API) and read once per launch.
+struct StreamDesc {
+	StreamState *state;
+	const double *frames;        // [qCount][47], queue order; rows of NULL requests are ignored
+	const uint32_t *minDur;      // [qCount]
+	const uint32_t *fadeDur;     // [qCount]  (0 means 1, reference speechPlayer.cpp:36)
+	const int32_t *userIndex;    // [qCount] or nullptr (-1)
+	const uint8_t *isNull;       // [qCount] or nullptr (all real)
+	const int32_t *replay;       // noise draws for kNoiseGlibc / kNoiseReplay, else nullptr
+	uint64_t replayLen;
+	uint64_t replayBase;         // draw index of replay[0] (draws consumed before this buffer)
+	uint64_t streamId;           // Philox counter words 2,3
+	uint32_t qCount;             // requests available in the arrays (absolute index qBase + i)
+	uint32_t qBase;              // absolute index of frames[0]
+};
+
+// Per-stream outcome of one launch (optional output of the render kernels).
+struct StreamResult {
+	uint32_t written;        // samples produced by this launch (what speechPlayer_synthesize returns)
+	int32_t lastUserIndex;   // getLastIndex() after the launch
+	uint32_t qHead;          // absolute count of requests consumed so far
+	uint32_t pad;
+};
+
+struct NoiseConfig {
+	int mode;
+	uint64_t seed;
+};
+
+}  // namespace klatt
