@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the B200-native Klatt engine.
+
+Metric (BASELINE.json): audio-seconds synthesized per wall-second, batched streams, and the fraction of the FP32
+CUDA-core FMA roofline from counted flops W(phi) = 128 + 270*phi per sample.
+Workload: BASELINE config 3 -- synthetic random-frame batch, 65 536 streams x 10 s at 22 050 Hz PER GPU (weak
+scaling: rank r renders stream ids [r*65536, (r+1)*65536), no data-path collective, streams are independent).
+
+A "step" is one pass of the hot path over one batch: reset every stream to its initial state, then frame manager
++ generator for streams x seconds x rate ticks.
+  value    : inputs (frames, durations) already resident in HBM, output left in HBM (speechPlayer_batch*Device)
+  e2e      : same step through the host-buffer C-ABI: frames H2D from pinned memory, int16 D2H into pinned memory
+  roofline : counted flops / CUDA-event kernel time, against (a) FP32 FMA peak measured on this GPU by an FFMA
+             loop and (b) SMs x 128 x 2 x max clock; plus the output stream's share of the measured HBM peak
+  cpu_baseline : the reference C++ (oracle/_ref) on the host cores, one process per core, bounded sample
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--streams S] [--seconds T]
+N>1 is launched with torch.distributed.run (one rank per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_HOLD, W_FADE_EXTRA = 128.0, 270.0  # flops per sample: hold tick, extra on a fade tick
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--streams", type=int, default=65536, help="streams per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--sample-rate", type=int, default=22050)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--seed", type=lambda s: int(s, 0), default=0xB200)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-streams-per-core", type=int, default=16)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle/_ref when it
+    was compiled, else the plain-C port).  Rank 0 alone runs it."""
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    runs = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_bench.run(streams_per_core=max(args.cpu_streams_per_core // 4, 2), seconds=args.seconds,
+                          sample_rate=args.sample_rate, seed=args.seed, first_stream=0)
+        if i >= args.warmup:
+            runs.append(r)
+    value = sum(r["value"] for r in runs) / len(runs)
+    ms = 1e3 * sum(r["synth_seconds_slowest_core"] for r in runs) / len(runs)
+    last = runs[-1]
+    line = {
+        "impl": "reference", "metric": "audio-seconds synthesized/sec (batched streams)", "value": value,
+        "unit": "audio-seconds/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config3 random-frame batch, bounded sample: " + last["sample"],
+                   "sample_rate": args.sample_rate, "seconds_per_stream": args.seconds},
+        "cpu_baseline": {"value": value, "unit": "audio-seconds/s", "cores": last["cores"], "kind": last["kind"],
+                         "sample": last["sample"], "ns_per_sample_core": last["ns_per_sample_core"]},
+        "e2e": {"value": value, "unit": "audio-seconds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from nvspeechplayer_b200 import player, workloads
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sr, S, secs = args.sample_rate, args.streams, args.seconds
+    count = int(round(secs * sr))
+    prec = player.PRECISION_FP32 if args.precision == "fp32" else player.PRECISION_FP64
+
+    # ---- CPU baseline first (spawns processes; keep it away from the timed GPU region) ----
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import cpu_bench
+        cpu = cpu_bench.run(streams_per_core=args.cpu_streams_per_core, seconds=secs, sample_rate=sr, seed=args.seed)
+
+    # ---- workload: this rank's shard of config 3 ----
+    t_gen = time.time()
+    fb = workloads.random_frames(S, secs, sr, seed=args.seed, first_stream=rank * S)
+    phi = fb.fade_fraction(count) if S <= 4096 else workloads.random_frames(
+        1024, secs, sr, seed=args.seed, first_stream=rank * S).fade_fraction(count)
+    t_gen = time.time() - t_gen
+    flops_per_sample = W_HOLD + W_FADE_EXTRA * phi
+    total_frames = int(fb.offsets[-1])
+
+    lib = player.load_library()
+    lib.speechPlayer_debugFp32PeakTflops.restype = __import__("ctypes").c_double
+    fp32_peak_measured = float(lib.speechPlayer_debugFp32PeakTflops())
+    props = torch.cuda.get_device_properties(dev)
+
+    # ---- HBM-resident inputs ----
+    d_off = torch.from_numpy(fb.offsets.astype(np.int64)).to(dev)
+    d_frames = torch.from_numpy(fb.frames).to(dev)
+    d_min = torch.from_numpy(fb.min_dur.astype(np.int32)).to(dev)   # same bits as uint32
+    d_fade = torch.from_numpy(fb.fade_dur.astype(np.int32)).to(dev)
+    d_uix = torch.from_numpy(fb.user_index).to(dev)
+    d_null = torch.from_numpy(fb.is_null).to(dev)
+    stride = (count + 7) // 8 * 8
+    d_out = torch.empty((S, stride), dtype=torch.int16, device=dev)
+    d_written = torch.zeros(S, dtype=torch.int32, device=dev)
+
+    batch = player.Batch(sr, S, precision=prec, noise=player.NOISE_PHILOX, seed=args.seed, stream_ids=fb.stream_ids)
+    stream = torch.cuda.current_stream().cuda_stream
+    batch.set_frames_device(d_off.data_ptr(), d_frames.data_ptr(), d_min.data_ptr(), d_fade.data_ptr(),
+                            d_uix.data_ptr(), d_null.data_ptr(), stream)
+
+    kev = []  # (before, after) CUDA events around the render kernel alone, on the launching stream
+
+    def step(timed=False):
+        batch.reset(stream)
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        batch.synthesize_device(count, d_out.data_ptr(), stride, d_written.data_ptr(), stream)
+        if timed:
+            b.record()
+            kev.append((a, b))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    assert int(d_written.min()) == count, "a stream drained early: workload shorter than the render"
+    launches0, _ = batch.launch_stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step(timed=True)
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches1, _ = batch.launch_stats()
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * S * secs * args.steps / (elapsed_ms * 1e-3)          # audio-seconds per wall-second, whole job
+    samples_per_s_gpu = S * count * args.steps / (elapsed_ms * 1e-3)      # per GPU
+
+    # ---- e2e: host buffers through the C-ABI (H2D of the frames + D2H of the int16 inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        h_out = torch.empty((S, count), dtype=torch.int16).pin_memory()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_off, h_frames = pin(fb.offsets.astype(np.int64)), pin(fb.frames)
+        h_min, h_fade = pin(fb.min_dur.astype(np.int32)), pin(fb.fade_dur.astype(np.int32))
+        h_uix, h_null = pin(fb.user_index), pin(fb.is_null)
+        h2d = sum(x.numel() * x.element_size() for x in (h_off, h_frames, h_min, h_fade, h_uix, h_null))
+        d2h = S * count * 2 + S * 16
+        eb = player.Batch(sr, S, precision=prec, noise=player.NOISE_PHILOX, seed=args.seed, stream_ids=fb.stream_ids)
+        L = eb._L
+
+        def e2e_step():
+            eb.reset(None)
+            rc = L.speechPlayer_batchSetFramesHost(eb._h, h_off.data_ptr(), h_frames.data_ptr(), h_min.data_ptr(),
+                                                   h_fade.data_ptr(), h_uix.data_ptr(), h_null.data_ptr(), None)
+            assert rc == 0, player.last_error()
+            got = L.speechPlayer_batchSynthesizeHost(eb._h, count, h_out.data_ptr(), None)
+            assert got == S * count, (got, player.last_error())
+
+        e2e_step()  # warm-up (staging buffers, pinned result buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_launches = eb.launch_stats()[0]
+        # the device-resident and the host path must agree bit for bit
+        same = bool(torch.equal(d_out[:64, :count].cpu(), h_out[:64]))
+        e2e = {"value": world * S * secs * args.e2e_steps / float(dt.item()), "unit": "audio-seconds/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
+               "ms_per_step": 1e3 * float(dt.item()) / args.e2e_steps, "matches_device_path": same,
+               "kernel_launches_total": int(e2e_launches)}
+        eb.close()
+
+    if rank == 0:
+        peaks = measured_peaks()
+        achieved_tf = S * count * flops_per_sample / (kernel_ms * 1e-3) / 1e12  # dominant kernel alone
+        sm_max = (clocks or {}).get("sm_max_mhz") or (peaks or {}).get("sm_max_mhz") or 1965.0
+        nominal_tf = props.multi_processor_count * 128 * 2 * sm_max * 1e6 / 1e12
+        peak_tf = fp32_peak_measured if fp32_peak_measured > 0 else nominal_tf
+        out_bytes_per_s = samples_per_s_gpu * 2.0 + total_frames * (47 * 8 + 13) * args.steps / (elapsed_ms * 1e-3)
+        hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
+        line = {
+            "metric": "audio-seconds synthesized/sec (batched streams)", "value": value, "unit": "audio-seconds/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if prec == player.PRECISION_FP32 else "f64", "data": "synthetic",
+            "config": {"workload": "config3: synthetic random-frame batch, %d streams x %.1f s @ %d Hz per GPU, all frame "
+                                   "params randomised (seed 0x%X)" % (S, secs, sr, args.seed),
+                       "streams_per_gpu": S, "seconds_per_stream": secs, "sample_rate": sr, "frames_per_gpu": total_frames,
+                       "fade_fraction_phi": round(phi, 4), "flops_per_sample_W": round(flops_per_sample, 1),
+                       "noise": "philox4x32-10", "precision": args.precision,
+                       "l2": "no flush needed: each step writes %.1f GB of int16 (>> 126 MB L2)" % (S * stride * 2 / 1e9),
+                       "real_time_factor_per_gpu": samples_per_s_gpu / sr},
+            "roofline": {"bound": "fp32_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "peak_source": "FFMA loop measured on this GPU in this run (MEASURED_PEAKS.json has no FP32 entry)"
+                                        if fp32_peak_measured > 0 else "SMs x 128 x 2 x max SM clock",
+                         "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
+                         "kernel": "klatt_batch_f32_kernel" if prec == player.PRECISION_FP32 else "klatt_batch_f64_kernel",
+                         "flops_per_launch": S * count * flops_per_sample, "kernel_ms": kernel_ms,
+                         "kernel_share_of_step": kernel_ms / ms_per_step},
+            "roofline_hbm": {"bound": "hbm", "achieved": out_bytes_per_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": out_bytes_per_s / 1e9 / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                             "algorithmic_bytes_per_sample": 2.0},
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "ns_per_sample_core")} if cpu else None),
+            "e2e": e2e,
+            "gpu_launches": int(launches1 - launches0),
+            "clocks": clocks,
+            "setup": {"workload_generation_s": round(t_gen, 1), "gpu": props.name, "sms": props.multi_processor_count},
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -583,6 +583,48 @@ unsigned long long speechPlayer_timelineSamples(const unsigned int *minFrameDura
 	return t;
 }
 
+// Measured FP32 roofline denominator: a register-resident FFMA loop (16 independent chains per thread, 3-register
+// form) timed with CUDA events on the current device; returns TFLOP/s (2 flops per FMA), <0 on error.  bench.py
+// reports the render kernel's counted flops against this number and against SMs x 128 lanes x 2 x clock.
+__global__ void fp32_peak_kernel(float *out, int iters, float x, float y) {
+	float a[16];
+#pragma unroll
+	for (int j = 0; j < 16; ++j) a[j] = (float)(threadIdx.x + j) * 1e-3f;
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], x, y);
+	}
+	float sum = 0;
+#pragma unroll
+	for (int j = 0; j < 16; ++j) sum += a[j];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+extern "C" double speechPlayer_debugFp32PeakTflops(void) {
+	int dev = 0, sms = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const int threads = 256, blocks = sms * 8, iters = 1 << 15;
+	float *out = nullptr;
+	if (cudaMalloc(&out, sizeof(float) * threads * blocks) != cudaSuccess) return -1;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	double best = -1;
+	for (int rep = 0; rep < 5; ++rep) {
+		cudaEventRecord(e0);
+		fp32_peak_kernel<<<blocks, threads>>>(out, iters, 0.999f, 1e-3f);
+		cudaEventRecord(e1);
+		if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1; break; }
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		double tf = 2.0 * 16.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	cudaFree(out);
+	return best;
+}
+
 // test hook: the first n values of the glibc-compatible generator after seed(s)
 void speechPlayer_debugGlibcRand(unsigned int seed, unsigned int n, int32_t *out) {
 	GlibcRand r;

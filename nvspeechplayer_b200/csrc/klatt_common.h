@@ -78,19 +78,47 @@ struct GenStateF64 {
 };
 
 // Generator state, FP32 production kernel (DESIGN.md "FP32 formulation").
-constexpr int kNumDirect = 17;   // frame params used directly by the DSP each tick (not via coefficients)
+constexpr int kNumDirect = 16;   // frame params used directly by the DSP each tick (not via coefficients / phase increments)
+
+// Everything the FP32 kernel needs to walk one fade (request j faded in from its predecessor) without
+// transcendental functions in the per-tick path.  Computed in double by planFade() -- by the plan kernel for
+// whole queues ahead of time, or inline at the pop tick when the predecessor is only known at run time.
+//   direct params : value at fade start, per-tick increment, value after the fade
+//   resonators    : zeta = 1 - pole (pole = r*exp(i*theta), r = exp(-pi*bw/sr), theta = 2*pi*f/sr) and
+//                   rho = 1 - |pole|^2 at fade start and end, plus the per-tick complex ratio of the pole written as
+//                   1 - omega, and kappa = 1 - |ratio|^2.  A linear fade of (f, bw) makes the pole a complex
+//                   geometric sequence.  Only SMALL quantities are stored (zeta, rho, omega, kappa), never b~2, c~-1.
+//   vibrato       : phase increment per tick as 2^-64-cycle fixed point (start, per-tick change, end)
+constexpr int kCoarseTicks = 64;  // drift control: every 64 samples the per-tick pole recurrence is re-based on a
+                                   // 64-tick recurrence, so rounding bias accumulates over F/64 + 127 steps, not F
+struct FadePlanF32 {
+	float dir0[kNumDirect], dirStep[kNumDirect], dirFinal[kNumDirect];
+	float z0re[kNumResonators], z0im[kNumResonators], rho0[kNumResonators];
+	float wre[kNumResonators], wim[kNumResonators], kap[kNumResonators];
+	float zFre[kNumResonators], zFim[kNumResonators], rhoF[kNumResonators];
+	float Wre[kNumResonators], Wim[kNumResonators], Kap[kNumResonators];  // the same ratio over kCoarseTicks ticks at once
+	int64_t vibInc0, vibIncStep, vibIncFinal;
+	uint32_t n0InvFade, n0InvFinal;  // anti-resonator inverted (cfN0 != 0, reference speechWaveGenerator.cpp:120) during / after the fade
+};
+
 struct GenStateF32 {
 	double pitchPos;               // glottal phase in cycles, FP64 by design
 	uint64_t samplesGenerated;
-	uint32_t vibratoPos;           // vibrato phase, 2^-32 cycles
+	uint64_t vibratoPos;           // vibrato phase, 2^-64 cycles (exact integer accumulation)
+	int64_t vibInc;                // its current per-tick increment (vibratoSpeed/sampleRate)
 	float aspLast, fricLast;
-	uint32_t coefValid;            // 0 until the coefficient state below has been derived from curFrame
 	float y[kNumResonators];       // delta-form state: last output (rN0: last input)
 	float d[kNumResonators];       //                   last output difference (rN0: last input difference)
 	float zre[kNumResonators];     // zeta = 1 - pole, tracked through fades
 	float zim[kNumResonators];
-	float r2[kNumResonators];      // |pole|^2
+	float rho[kNumResonators];     // 1 - |pole|^2
 	float dir[kNumDirect];         // current value of the directly used params
+	uint32_t n0Inv;                // anti-resonator currently inverted
+	uint32_t pad;
+	double pitchStep;              // per-tick voicePitch increment of the fade in progress
+	uint32_t coarseAt, pad1;       // fade tick at which coarse[] was last in sync (0x80000000: not yet)
+	float coarse[3 * kNumResonators];  // coarse-recurrence state (zeta re/im, rho) of the fade in progress
+	FadePlanF32 plan;              // plan of the fade in progress (valid while fm.hasNew)
 };
 
 struct StreamState {

@@ -64,6 +64,7 @@ struct klatt_oracle {
 	int noiseMode; uint64_t seed, stream; const int32_t *replay; size_t nReplay;
 	uint64_t nDraws, nTicks, nFadeTicks;
 	int fadedThisTick;
+	double *dbgPhase; /* optional: pitchPos after every generated sample */
 };
 
 /* ---- noise draw: stands in for rand() (src/speechWaveGenerator.cpp:40) ---- */
@@ -284,12 +285,14 @@ int klatt_oracle_synthesize(klatt_oracle_t *o, unsigned sampleCount, int16_t *ou
 		double lo = (scaled < 32000) ? scaled : 32000;
 		double cl = (lo > -32000) ? lo : -32000;
 		out[i] = (int16_t)(int)cl; /* truncation toward zero */
+		if (o->dbgPhase) o->dbgPhase[o->nTicks] = o->pitchPos;
 		o->nTicks++;
 		o->nFadeTicks += (uint64_t)o->fadedThisTick;
 	}
 	return (int)sampleCount;
 }
 
+void klatt_oracle_debug_phase(klatt_oracle_t *o, double *buf) { o->dbgPhase = buf; }
 int klatt_oracle_get_last_index(const klatt_oracle_t *o) { return o->lastUserIndex; } /* frame.cpp:117-119 */
 uint64_t klatt_oracle_ticks(const klatt_oracle_t *o) { return o->nTicks; }
 uint64_t klatt_oracle_fade_ticks(const klatt_oracle_t *o) { return o->nFadeTicks; }

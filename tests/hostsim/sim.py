@@ -1,0 +1,53 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes access to the host build of the FP32 kernel arithmetic + parity metrics."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libhostsim.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
+        L = ctypes.CDLL(SO)
+        vp = ctypes.c_void_p
+        L.hostsim_render_f32.restype = ctypes.c_int
+        L.hostsim_render_f32.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint64,
+                                         ctypes.c_uint, vp, ctypes.c_uint, vp]
+        _lib = L
+    return _lib
+
+
+def render_f32(sr, frames, min_dur, fade_dur, is_null=None, user_index=None, max_samples=None, seed=0, stream=0, chunk=0):
+    frames = np.ascontiguousarray(frames, dtype=np.float64).reshape(-1, 47)
+    m = np.ascontiguousarray(min_dur, dtype=np.uint32)
+    f = np.ascontiguousarray(fade_dur, dtype=np.uint32)
+    nul = None if is_null is None else np.ascontiguousarray(is_null, dtype=np.uint8)
+    ux = None if user_index is None else np.ascontiguousarray(user_index, dtype=np.int32)
+    if max_samples is None:
+        mm = m.astype(np.int64)
+        ff = np.maximum(f.astype(np.int64), 1)
+        max_samples = int(np.maximum(mm + 1, ff + 2).sum()) + 16
+    out = np.zeros(max_samples, dtype=np.int16)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    li = ctypes.c_int32(0)
+    n = lib().hostsim_render_f32(sr, ptr(frames), ptr(m), ptr(f), ptr(ux), ptr(nul), len(m), seed, stream, max_samples,
+                                 ptr(out), chunk, ctypes.byref(li))
+    return out[:n], li.value
+
+
+def parity(got, want):
+    """(fraction within 1 LSB, fraction exact, SNR dB, max |diff|)"""
+    n = min(len(got), len(want))
+    g = got[:n].astype(np.float64)
+    w = want[:n].astype(np.float64)
+    d = g - w
+    sig = float((w * w).sum())
+    err = float((d * d).sum())
+    snr = float("inf") if err == 0 else 10 * np.log10(max(sig, 1e-30) / err)
+    return float((np.abs(d) <= 1).mean()), float((d == 0).mean()), snr, float(np.abs(d).max())
