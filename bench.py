@@ -202,7 +202,10 @@ def main():
     kev = []  # (before, after) CUDA events around the render kernel alone, on the launching stream
 
     def step(timed=False):
-        batch.reset(stream)
+        # a step = hand the (HBM-resident) queues to fresh players, then plan + render them: SetFrames resets every
+        # stream and invalidates the fade plans, so the plan kernel runs inside the timed synthesize call
+        batch.set_frames_device(d_off.data_ptr(), d_frames.data_ptr(), d_min.data_ptr(), d_fade.data_ptr(),
+                                d_uix.data_ptr(), d_null.data_ptr(), stream)
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()

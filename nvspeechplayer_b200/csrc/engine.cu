@@ -31,6 +31,14 @@ cudaError_t launchKlattF64(const StreamDesc *descs, uint32_t numStreams, int sam
 cudaError_t launchKlattF32(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                            int16_t *out, size_t rowStride, uint32_t *samplesWritten, StreamResult *results,
                            NoiseConfig noise, cudaStream_t stream);
+cudaError_t launchKlattF32Rounds(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
+                                 uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride,
+                                 uint32_t *samplesWritten, StreamResult *results, NoiseConfig noise, uint32_t *listHold,
+                                 uint32_t *listGen, uint32_t *counters, cudaStream_t stream, cudaStream_t side,
+                                 cudaEvent_t fork, cudaEvent_t join, unsigned long long *launchCounter);
+cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_t totalRequests, const double *frames,
+                            const uint32_t *fadeDur, const uint8_t *isNull, int sampleRate, FadePlanF32 *plans,
+                            cudaStream_t stream);
 }  // namespace klatt
 
 using namespace klatt;
@@ -121,31 +129,79 @@ __global__ void init_states_kernel(StreamState *states, uint32_t n) {
 __global__ void build_descs_kernel(StreamDesc *descs, StreamState *states, const int64_t *offsets, const double *frames,
                                    const uint32_t *minDur, const uint32_t *fadeDur, const int32_t *userIndex,
                                    const uint8_t *isNull, const int32_t *replay, uint64_t drawsPerStream,
-                                   const uint64_t *streamIds, uint32_t n) {
+                                   const uint64_t *streamIds, const FadePlanF32 *plans, uint32_t n) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+	if (i > n) return;
 	StreamDesc d;
-	int64_t a = offsets ? offsets[i] : 0, b = offsets ? offsets[i + 1] : 0;
+	// entry n is the dummy stream (fresh state, empty queue) that idle lanes of the paired kernels run
+	int64_t a = (offsets && i < n) ? offsets[i] : 0, b = (offsets && i < n) ? offsets[i + 1] : 0;
 	d.state = states + i;
 	d.frames = frames ? frames + (size_t)a * kNumParams : nullptr;
 	d.minDur = minDur ? minDur + a : nullptr;
 	d.fadeDur = fadeDur ? fadeDur + a : nullptr;
 	d.userIndex = userIndex ? userIndex + a : nullptr;
 	d.isNull = isNull ? isNull + a : nullptr;
-	d.replay = replay ? replay + (size_t)i * drawsPerStream : nullptr;
-	d.replayLen = replay ? drawsPerStream : 0;
+	d.replay = (replay && i < n) ? replay + (size_t)i * drawsPerStream : nullptr;
+	d.replayLen = (replay && i < n) ? drawsPerStream : 0;
 	d.replayBase = 0;
-	d.streamId = streamIds ? streamIds[i] : i;
+	d.streamId = (streamIds && i < n) ? streamIds[i] : i;
 	d.qCount = (uint32_t)(b - a);
 	d.qBase = 0;
+	d.plans = plans ? plans + a : nullptr;
 	descs[i] = d;
 }
 
+// Scratch and second stream for round-based FP32 rendering (klatt_f32.cu "rounds"); owned by a batch or a pipe.
+struct RoundsCtx {
+	DevBuf listHold, listGen, counters;
+	cudaStream_t side = nullptr;
+	cudaEvent_t fork = nullptr, join = nullptr;
+	uint32_t holdTicks = 256, genTicks = 128, minStreams = 2048;
+	bool ok = false;
+	bool init() {
+		if (ok) return true;
+		if (!cudaOk(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+		if (!cudaOk(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "cudaEventCreate")) return false;
+		if (!cudaOk(cudaEventCreateWithFlags(&join, cudaEventDisableTiming), "cudaEventCreate")) return false;
+		auto envU = [](const char *name, uint32_t dflt) {
+			const char *e = getenv(name);
+			return (e && *e) ? (uint32_t)strtoul(e, nullptr, 0) : dflt;
+		};
+		// chunk lengths are multiples of 64: the coarse pole re-basing and the Philox block cadence stay warp-uniform,
+		// and every chunk starts on a 16-byte boundary of its output row
+		genTicks = std::max<uint32_t>(envU("NVSP_GEN_TICKS", 128) & ~63u, 64);
+		holdTicks = std::max<uint32_t>(envU("NVSP_HOLD_TICKS", 256) & ~63u, 64);
+		minStreams = envU("NVSP_ROUNDS_MIN_STREAMS", 2048);
+		ok = true;
+		return true;
+	}
+	void destroy() {
+		listHold.release(); listGen.release(); counters.release();
+		if (!ok) return;
+		cudaEventDestroy(fork); cudaEventDestroy(join); cudaStreamDestroy(side);
+		ok = false;
+	}
+};
+
+// planned: the descriptors carry precomputed fade plans (pre-queued batches) -> FP32 renders may run as rounds
 static cudaError_t launchRender(int precision, const StreamDesc *descs, uint32_t n, int sampleRate, uint32_t sampleCount,
                                 int16_t *out, size_t rowStride, uint32_t *written, StreamResult *results,
-                                NoiseConfig noise, cudaStream_t stream) {
-	if (precision == kPrecisionF64)
+                                NoiseConfig noise, cudaStream_t stream, RoundsCtx *rc = nullptr, bool planned = false,
+                                unsigned long long *launchCounter = nullptr) {
+	if (precision == kPrecisionF64) {
+		if (launchCounter) ++*launchCounter;
 		return launchKlattF64(descs, n, sampleRate, sampleCount, out, rowStride, written, results, noise, stream);
+	}
+	if (rc && planned && rc->init() && n >= rc->minStreams && sampleCount > rc->genTicks) {
+		const uint32_t rounds = (sampleCount + rc->genTicks - 1) / rc->genTicks;
+		if (!rc->listHold.reserve(sizeof(uint32_t) * (size_t)n) || !rc->listGen.reserve(sizeof(uint32_t) * (size_t)n) ||
+		    !rc->counters.reserve(sizeof(uint32_t) * 2 * (size_t)rounds))
+			return cudaErrorMemoryAllocation;
+		return launchKlattF32Rounds(descs, n, sampleRate, sampleCount, rc->holdTicks, rc->genTicks, out, rowStride, written,
+		                            results, noise, rc->listHold.as<uint32_t>(), rc->listGen.as<uint32_t>(),
+		                            rc->counters.as<uint32_t>(), stream, rc->side, rc->fork, rc->join, launchCounter);
+	}
+	if (launchCounter) ++*launchCounter;
 	return launchKlattF32(descs, n, sampleRate, sampleCount, out, rowStride, written, results, noise, stream);
 }
 
@@ -164,6 +220,7 @@ struct HostPipe {
 	cudaStream_t compute = nullptr, copy = nullptr;
 	cudaEvent_t kernelDone[2] = {nullptr, nullptr}, copyDone[2] = {nullptr, nullptr};
 	DevBuf stage[2], res[2];
+	RoundsCtx rounds;
 	StreamResult *hostRes = nullptr;  // pinned, [2][n]
 	size_t hostResCap = 0;
 	bool ok = false;
@@ -184,6 +241,7 @@ struct HostPipe {
 			stage[i].release(); res[i].release();
 			cudaEventDestroy(kernelDone[i]); cudaEventDestroy(copyDone[i]);
 		}
+		rounds.destroy();
 		if (hostRes) cudaFreeHost(hostRes);
 		cudaStreamDestroy(compute); cudaStreamDestroy(copy);
 		ok = false;
@@ -199,14 +257,14 @@ static size_t stagingBudgetBytes() {
 // returns total samples written, or -1.  perStream (host, [n]) and lastResults (host, [n]) are optional outputs.
 static long long renderToHost(HostPipe &pipe, int precision, const StreamDesc *dDescs, uint32_t n, int sampleRate,
                               uint32_t sampleCount, int16_t *hostOut, uint32_t *perStream, StreamResult *lastResults,
-                              NoiseConfig noise, unsigned long long *launchCounter) {
+                              NoiseConfig noise, unsigned long long *launchCounter, bool planned = false) {
 	if (!pipe.init()) return -1;
 	if (n == 0 || sampleCount == 0) return 0;
 	// chunk length in ticks: whole request if it fits the staging budget, else a multiple of 8
 	size_t budget = stagingBudgetBytes();
 	uint64_t maxTicks = std::max<uint64_t>(budget / ((size_t)n * sizeof(int16_t)), 8);
 	uint32_t chunk = (uint32_t)std::min<uint64_t>(sampleCount, maxTicks);
-	if (chunk < sampleCount) chunk &= ~7u;
+	if (chunk < sampleCount) chunk = chunk >= 64 ? (chunk & ~63u) : (chunk & ~7u);
 	size_t stride = ((size_t)chunk + 7) & ~(size_t)7;
 	for (int i = 0; i < 2; ++i) {
 		if (!pipe.stage[i].reserve(stride * n * sizeof(int16_t))) return -1;
@@ -233,8 +291,7 @@ static long long renderToHost(HostPipe &pipe, int precision, const StreamDesc *d
 		uint32_t t0 = c * chunk, len = std::min(chunk, sampleCount - t0);
 		if (c >= 2 && !harvest(c - 2)) return -1;  // staging buffer b is free again
 		CU(launchRender(precision, dDescs, n, sampleRate, len, pipe.stage[b].as<int16_t>(), stride, nullptr,
-		                pipe.res[b].as<StreamResult>(), noise, pipe.compute));
-		if (launchCounter) ++*launchCounter;
+		                pipe.res[b].as<StreamResult>(), noise, pipe.compute, &pipe.rounds, planned, launchCounter));
 		CU(cudaEventRecord(pipe.kernelDone[b], pipe.compute));
 		CU(cudaStreamWaitEvent(pipe.copy, pipe.kernelDone[b], 0));
 		CU(cudaMemcpy2DAsync(hostOut + t0, (size_t)sampleCount * sizeof(int16_t), pipe.stage[b].p,
@@ -342,6 +399,7 @@ struct Player {
 		d.qCount = (uint32_t)pending();
 		d.qBase = qBase;
 		d.streamId = streamId;
+		d.plans = nullptr;  // per-handle queues grow and get purged: fades are planned inline at the pop tick
 		d.replay = nullptr; d.replayLen = 0; d.replayBase = 0;
 		if (noiseMode == kNoiseGlibc) {
 			// draws for the worst case (every tick generates); the caller rewinds the generator afterwards
@@ -653,16 +711,32 @@ struct speechPlayer_batch {
 	const int32_t *dReplay = nullptr;
 	uint64_t drawsPerStream = 0;
 	DevBuf ownOffsets, ownFrames, ownMin, ownFade, ownUix, ownNull;
+	DevBuf plans;              // FadePlanF32 per queued request (FP32 precision)
+	bool plansDirty = false;   // frames changed since the plans were made
+	uint64_t totalRequests = 0;
 	HostPipe pipe;
+	RoundsCtx rounds;
 	unsigned long long launches = 0, ticks = 0;
 	std::mutex mu;
 
-	int rebuildDescs(cudaStream_t stream) {
-		build_descs_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dDescs, dStates, dOffsets, dFrames, dMin, dFade, dUix, dNull,
-		                                                        dReplay, drawsPerStream, dStreamIds, n);
+	int rebuildDescs(cudaStream_t stream, bool withPlans) {
+		build_descs_kernel<<<(n + 256) / 256, 256, 0, stream>>>(dDescs, dStates, dOffsets, dFrames, dMin, dFade, dUix, dNull,
+		                                                        dReplay, drawsPerStream, dStreamIds,
+		                                                        withPlans ? plans.as<FadePlanF32>() : nullptr, n);
 		CU(cudaGetLastError());
 		++launches;
 		return 0;
+	}
+	bool planned() const { return precision == kPrecisionF32 && dOffsets != nullptr && !plansDirty; }
+	// FP32: (re)make the fade plans of every queued request; runs inside the first synthesize after SetFrames, on
+	// the synthesize stream, so the work is part of the rendered step
+	int ensurePlans(cudaStream_t stream) {
+		if (precision != kPrecisionF32 || !dOffsets || !plansDirty) return 0;
+		if (!plans.reserve(std::max<uint64_t>(totalRequests, 1) * sizeof(FadePlanF32))) return -1;
+		CU(launchKlattPlan(dOffsets, n, totalRequests, dFrames, dFade, dNull, sampleRate, plans.as<FadePlanF32>(), stream));
+		++launches;
+		plansDirty = false;
+		return rebuildDescs(stream, true);
 	}
 };
 
@@ -680,14 +754,14 @@ speechPlayer_batch_t *speechPlayer_batchCreate(int sampleRate, unsigned int numS
 	speechPlayer_batch *b = new speechPlayer_batch;
 	b->device = dev; b->sampleRate = sampleRate; b->precision = precision; b->noiseMode = noiseMode; b->seed = seed;
 	b->n = numStreams;
-	bool ok = cudaOk(cudaMalloc((void **)&b->dStates, sizeof(StreamState) * (size_t)numStreams), "cudaMalloc(states)") &&
-	          cudaOk(cudaMalloc((void **)&b->dDescs, sizeof(StreamDesc) * (size_t)numStreams), "cudaMalloc(descs)") &&
+	bool ok = cudaOk(cudaMalloc((void **)&b->dStates, sizeof(StreamState) * ((size_t)numStreams + 1)), "cudaMalloc(states)") &&
+	          cudaOk(cudaMalloc((void **)&b->dDescs, sizeof(StreamDesc) * ((size_t)numStreams + 1)), "cudaMalloc(descs)") &&
 	          cudaOk(cudaMalloc((void **)&b->dStreamIds, sizeof(uint64_t) * (size_t)numStreams), "cudaMalloc(ids)");
 	if (ok) {
 		std::vector<uint64_t> ids(numStreams);
 		for (uint32_t i = 0; i < numStreams; ++i) ids[i] = streamIds ? streamIds[i] : i;
 		ok = cudaOk(cudaMemcpy(b->dStreamIds, ids.data(), sizeof(uint64_t) * (size_t)numStreams, cudaMemcpyHostToDevice), "ids H2D") &&
-		     cudaOk(initStates(b->dStates, numStreams, nullptr), "init states") && b->rebuildDescs(nullptr) == 0 &&
+		     cudaOk(initStates(b->dStates, numStreams + 1, nullptr), "init states") && b->rebuildDescs(nullptr, false) == 0 &&
 		     cudaOk(cudaStreamSynchronize(nullptr), "sync");
 	}
 	if (!ok) {
@@ -702,6 +776,8 @@ void speechPlayer_batchDestroy(speechPlayer_batch_t *b) {
 	DeviceGuard g(b->device);
 	cudaDeviceSynchronize();
 	b->pipe.destroy();
+	b->rounds.destroy();
+	b->plans.release();
 	b->ownOffsets.release(); b->ownFrames.release(); b->ownMin.release(); b->ownFade.release(); b->ownUix.release(); b->ownNull.release();
 	if (b->dStates) cudaFree(b->dStates);
 	if (b->dDescs) cudaFree(b->dDescs);
@@ -713,7 +789,7 @@ int speechPlayer_batchReset(speechPlayer_batch_t *b, void *cudaStream) {
 	if (!b) return fail("null batch");
 	std::lock_guard<std::mutex> lk(b->mu);
 	DeviceGuard g(b->device);
-	CU(initStates(b->dStates, b->n, static_cast<cudaStream_t>(cudaStream)));
+	CU(initStates(b->dStates, b->n + 1, static_cast<cudaStream_t>(cudaStream)));
 	b->launches += 1;
 	return 0;
 }
@@ -724,13 +800,26 @@ int speechPlayer_batchSetFramesDevice(speechPlayer_batch_t *b, const void *dOffs
 	if (!dOffsets || !dMinDur || !dFadeDur) return fail("offsets and durations are required");
 	std::lock_guard<std::mutex> lk(b->mu);
 	DeviceGuard g(b->device);
+	cudaStream_t stream = static_cast<cudaStream_t>(cudaStream);
 	b->dOffsets = static_cast<const int64_t *>(dOffsets);
 	b->dFrames = static_cast<const double *>(dFrames);
 	b->dMin = static_cast<const uint32_t *>(dMinDur);
 	b->dFade = static_cast<const uint32_t *>(dFadeDur);
 	b->dUix = static_cast<const int32_t *>(dUserIndex);
 	b->dNull = static_cast<const uint8_t *>(dIsNull);
-	return b->rebuildDescs(static_cast<cudaStream_t>(cudaStream));
+	// new queues start on fresh players (the batch equivalent of initialize + queueFrame x n)
+	CU(initStates(b->dStates, b->n + 1, stream));
+	b->launches += 1;
+	if (b->precision == kPrecisionF32) {
+		// the plan buffer is sized from the total request count: one 8-byte read-back
+		int64_t total = 0;
+		CU(cudaMemcpyAsync(&total, b->dOffsets + b->n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+		CU(cudaStreamSynchronize(stream));
+		if (total < 0) return fail("offsets[numStreams] is negative");
+		b->totalRequests = (uint64_t)total;
+		b->plansDirty = true;
+	}
+	return b->rebuildDescs(stream, false);
 }
 
 int speechPlayer_batchSetFramesHost(speechPlayer_batch_t *b, const int64_t *offsets, const speechPlayer_frame_t *frames,
@@ -772,7 +861,7 @@ int speechPlayer_batchSetNoiseReplayDevice(speechPlayer_batch_t *b, const void *
 	DeviceGuard g(b->device);
 	b->dReplay = static_cast<const int32_t *>(dDraws);
 	b->drawsPerStream = drawsPerStream;
-	return b->rebuildDescs(nullptr);
+	return b->rebuildDescs(nullptr, b->planned());
 }
 
 int speechPlayer_batchSynthesizeDevice(speechPlayer_batch_t *b, unsigned int sampleCount, void *dOut, size_t rowStride,
@@ -783,9 +872,10 @@ int speechPlayer_batchSynthesizeDevice(speechPlayer_batch_t *b, unsigned int sam
 	std::lock_guard<std::mutex> lk(b->mu);
 	DeviceGuard g(b->device);
 	NoiseConfig nc{b->noiseMode, b->seed};
+	cudaStream_t stream = static_cast<cudaStream_t>(cudaStream);
+	if (b->ensurePlans(stream) != 0) return -1;
 	CU(launchRender(b->precision, b->dDescs, b->n, b->sampleRate, sampleCount, static_cast<int16_t *>(dOut), rowStride,
-	                static_cast<uint32_t *>(dSamplesWritten), nullptr, nc, static_cast<cudaStream_t>(cudaStream)));
-	b->launches += 1;
+	                static_cast<uint32_t *>(dSamplesWritten), nullptr, nc, stream, &b->rounds, b->planned(), &b->launches));
 	b->ticks += (unsigned long long)b->n * sampleCount;
 	return 0;
 }
@@ -798,8 +888,10 @@ long long speechPlayer_batchSynthesizeHost(speechPlayer_batch_t *b, unsigned int
 	DeviceGuard g(b->device);
 	CU(cudaDeviceSynchronize());  // frames / resets enqueued on other streams must have landed
 	NoiseConfig nc{b->noiseMode, b->seed};
+	if (!b->pipe.init()) return -1;
+	if (b->ensurePlans(b->pipe.compute) != 0) return -1;
 	long long r = renderToHost(b->pipe, b->precision, b->dDescs, b->n, b->sampleRate, sampleCount,
-	                           reinterpret_cast<int16_t *>(out), samplesWritten, nullptr, nc, &b->launches);
+	                           reinterpret_cast<int16_t *>(out), samplesWritten, nullptr, nc, &b->launches, b->planned());
 	if (r >= 0) b->ticks += (unsigned long long)b->n * sampleCount;
 	return r;
 }

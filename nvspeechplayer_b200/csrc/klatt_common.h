@@ -77,48 +77,54 @@ struct GenStateF64 {
 	uint64_t samplesGenerated;     // == rand() draws consumed / 2
 };
 
-// Generator state, FP32 production kernel (DESIGN.md "FP32 formulation").
+// Generator state, FP32 production kernels (DESIGN.md "FP32 formulation").
 constexpr int kNumDirect = 16;   // frame params used directly by the DSP each tick (not via coefficients / phase increments)
 
-// Everything the FP32 kernel needs to walk one fade (request j faded in from its predecessor) without
-// transcendental functions in the per-tick path.  Computed in double by planFade() -- by the plan kernel for
-// whole queues ahead of time, or inline at the pop tick when the predecessor is only known at run time.
+// Everything the FP32 kernels need to walk one fade (request j faded in from its predecessor) without
+// transcendental functions in the per-tick path.  Computed in double by planFade() -- by klatt_plan_kernel for
+// whole pre-queued batches, or inline at the pop tick when the predecessor is only known at run time
+// (per-handle API, purge).
 //   direct params : value at fade start, per-tick increment, value after the fade
-//   resonators    : zeta = 1 - pole (pole = r*exp(i*theta), r = exp(-pi*bw/sr), theta = 2*pi*f/sr) and
-//                   rho = 1 - |pole|^2 at fade start and end, plus the per-tick complex ratio of the pole written as
-//                   1 - omega, and kappa = 1 - |ratio|^2.  A linear fade of (f, bw) makes the pole a complex
-//                   geometric sequence.  Only SMALL quantities are stored (zeta, rho, omega, kappa), never b~2, c~-1.
+//   resonators    : zeta = 1 - pole (pole = r*exp(i*theta), r = exp(-pi*bw/sr), theta = 2*pi*f/sr) at fade start
+//                   and end, plus the per-tick complex ratio of the pole written as 1 - omega.  A linear fade of
+//                   (f, bw) makes the pole a complex geometric sequence.  Only SMALL quantities are stored (zeta,
+//                   omega), never b~2, c~-1;  a = |zeta|^2 and rho = 1-|pole|^2 = 2*Re(zeta) - a follow per tick.
 //   vibrato       : phase increment per tick as 2^-64-cycle fixed point (start, per-tick change, end)
 constexpr int kCoarseTicks = 64;  // drift control: every 64 samples the per-tick pole recurrence is re-based on a
                                    // 64-tick recurrence, so rounding bias accumulates over F/64 + 127 steps, not F
-struct FadePlanF32 {
+struct alignas(16) FadePlanF32 {
+	float z0re[kNumResonators], z0im[kNumResonators];
+	float zFre[kNumResonators], zFim[kNumResonators];
+	float wre[kNumResonators], wim[kNumResonators];
+	float Wre[kNumResonators], Wim[kNumResonators];  // the same ratio over kCoarseTicks ticks at once
 	float dir0[kNumDirect], dirStep[kNumDirect], dirFinal[kNumDirect];
-	float z0re[kNumResonators], z0im[kNumResonators], rho0[kNumResonators];
-	float wre[kNumResonators], wim[kNumResonators], kap[kNumResonators];
-	float zFre[kNumResonators], zFim[kNumResonators], rhoF[kNumResonators];
-	float Wre[kNumResonators], Wim[kNumResonators], Kap[kNumResonators];  // the same ratio over kCoarseTicks ticks at once
 	int64_t vibInc0, vibIncStep, vibIncFinal;
 	uint32_t n0InvFade, n0InvFinal;  // anti-resonator inverted (cfN0 != 0, reference speechWaveGenerator.cpp:120) during / after the fade
 };
+static_assert(sizeof(FadePlanF32) % 16 == 0, "plan records are read with 16-byte loads");
 
 struct GenStateF32 {
 	double pitchPos;               // glottal phase in cycles, FP64 by design
+	double pitch;                  // cur.voicePitch
+	double pitchInc;               // its per-tick increment in force: fade step, hold glide, or 0 (pop / swap / landing tick)
+	double pitchOld, pitchNew;     // end points of the fade in progress (the landing tick evaluates old+(new-old)*1.0)
 	uint64_t samplesGenerated;
 	uint64_t vibratoPos;           // vibrato phase, 2^-64 cycles (exact integer accumulation)
 	int64_t vibInc;                // its current per-tick increment (vibratoSpeed/sampleRate)
-	float aspLast, fricLast;
+	float aspLast, fricLast;       // coloured-noise memories, in units of 2^-23
+	uint32_t n0Inv;                // anti-resonator currently inverted
+	uint32_t holdArmed;            // holding with pitchInc == oldInc and nextEvent == oldM+1 (pure-hold chunks allowed)
+	uint32_t nextEvent;            // sampleCounter value at which the frame manager has something to do
+	uint32_t coarseAt;             // fade tick at which zc[] was last in sync (0x80000000: not yet)
+	uint32_t callPos;              // ticks of the current synthesize call already rendered (round-based execution)
+	uint32_t callDrained;          // the queue drained during the current call
 	float y[kNumResonators];       // delta-form state: last output (rN0: last input)
 	float d[kNumResonators];       //                   last output difference (rN0: last input difference)
 	float zre[kNumResonators];     // zeta = 1 - pole, tracked through fades
 	float zim[kNumResonators];
-	float rho[kNumResonators];     // 1 - |pole|^2
 	float dir[kNumDirect];         // current value of the directly used params
-	uint32_t n0Inv;                // anti-resonator currently inverted
-	uint32_t pad;
-	double pitchStep;              // per-tick voicePitch increment of the fade in progress
-	uint32_t coarseAt, pad1;       // fade tick at which coarse[] was last in sync (0x80000000: not yet)
-	float coarse[3 * kNumResonators];  // coarse-recurrence state (zeta re/im, rho) of the fade in progress
-	FadePlanF32 plan;              // plan of the fade in progress (valid while fm.hasNew)
+	float zc[2 * kNumResonators];  // coarse-recurrence state (zeta re/im) of the fade in progress
+	FadePlanF32 plan;              // plan of the fade in progress when it was made inline (no precomputed plans)
 };
 
 struct StreamState {
@@ -144,6 +150,7 @@ struct StreamDesc {
 	uint64_t streamId;           // Philox counter words 2,3
 	uint32_t qCount;             // requests available in the arrays (absolute index qBase + i)
 	uint32_t qBase;              // absolute index of frames[0]
+	const FadePlanF32 *plans;    // [qCount] precomputed fade plans (FP32 kernels), or nullptr: plan inline at the pop tick
 };
 
 // Per-stream outcome of one launch (optional output of the render kernels).

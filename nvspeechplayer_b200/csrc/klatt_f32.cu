@@ -1,7 +1,22 @@
-// klatt_batch_f32: the production kernel.  One stream per thread; the whole per-stream working set (28 filter
-// memories, 56 coefficient-state words, 17 direct parameters, fade increments, FP64 pitch/phase) lives in
-// registers, the frame queue and the per-request fade plans are read from HBM only on pop ticks, and the int16
-// output leaves as 16-byte stores (out_writer.cuh).  The arithmetic is renderStreamF32() in klatt_f32_core.cuh.
+// The FP32 production kernels.  One stream per thread; the per-stream working set lives in registers, the frame
+// queue and the per-request fade plans are read from HBM only on event ticks, and the int16 output leaves as
+// 16-byte stores (out_writer.cuh).  The arithmetic is klatt_f32_core.cuh (compiled with -fmad=false: every fused
+// multiply-add is an explicit fmaf, so the two render kernels round identically on a hold tick).
+//
+//   klatt_plan_kernel        one thread per queued REQUEST: the fade plan (all FP64 transcendentals of the path:
+//                            14 x (exp, cos) per frame of reference src/speechWaveGenerator.cpp:113-125, hoisted out
+//                            of the per-tick loop) for whole pre-queued batches
+//   klatt_partition_kernel   one thread per stream, once per round: which streams have `holdTicks` pure hold ticks
+//                            ahead (-> hold list) and which need the frame manager (-> general list)
+//   klatt_f32_hold_kernel    `holdTicks` ticks of src/frame.cpp:76-79 + src/speechWaveGenerator.cpp:203-208 with
+//                            constant coefficients: no state machine, no coefficient updates
+//   klatt_f32_general_kernel up to `genTicks` ticks through the full frame manager (src/frame.cpp:41-80) with
+//                            per-tick coefficient recurrences
+//   klatt_finalize_kernel    per-stream results of a call made of rounds
+//
+// Why rounds: lanes of a warp that are in different frame-manager phases would make every tick pay for the fade
+// arithmetic (~2x a hold tick).  Re-sorting streams by phase every round keeps warps homogeneous; hold chunks are
+// twice as long as general chunks so that both kernels of a round take about the same time (DESIGN.md "Rounds").
 #include <cuda_runtime.h>
 #include "klatt_common.h"
 #include "klatt_f32_core.cuh"
@@ -9,33 +24,183 @@
 
 namespace klatt {
 
-constexpr int kF32Block = 128;
+constexpr int kF32Block = 64;
 
 namespace {
-struct SmemCoarse {
-	float *base;  // this thread's column of the [kCoarseWords][kF32Block] block
-	__device__ __forceinline__ float &at(int i) { return base[i * kF32Block]; }
-};
+
+__device__ __forceinline__ void zeroRow(int16_t *row, uint32_t from, uint32_t to) {
+	for (uint32_t i = from; i < to; ++i) row[i] = 0;
+}
+
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// plans for pre-queued batches
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+klatt_plan_kernel(const int64_t *__restrict__ offsets, uint32_t numStreams, const double *__restrict__ frames,
+                  const uint32_t *__restrict__ fadeDur, const uint8_t *__restrict__ isNull, int sampleRate,
+                  FadePlanF32 *__restrict__ plans) {
+	const int64_t total = offsets[numStreams];
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= total) return;
+	// the stream that owns request g: last s with offsets[s] <= g
+	uint32_t lo = 0, hi = numStreams;
+	while (hi - lo > 1) {
+		uint32_t mid = (lo + hi) >> 1;
+		if (offsets[mid] <= g) lo = mid; else hi = mid;
+	}
+	const int64_t first = offsets[lo];
+	const bool curNull = isNull ? (isNull[g] != 0) : false;
+	const bool prevNull = (g == first) || (isNull && isNull[g - 1] != 0);
+	int64_t p = g - 1;
+	while (p >= first && isNull && isNull[p] != 0) --p;
+	const double *prevReal = (p >= first && frames) ? frames + (size_t)p * kNumParams : nullptr;
+	double o[kNumParams], n[kNumParams];
+	plannedFrames(prevReal, prevNull, frames ? frames + (size_t)g * kNumParams : nullptr, curNull || !frames, o, n);
+	const uint32_t fd = fadeDur[g];
+	planFade(o, n, fd > 1u ? fd : 1u, sampleRate, plans[g]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rounds
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+klatt_partition_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, uint32_t sampleCount, uint32_t holdTicks,
+                       uint32_t genTicks, int firstRound, uint32_t *__restrict__ listHold, uint32_t *__restrict__ listGen,
+                       uint32_t *__restrict__ counters) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	int cls = 0;  // 0: nothing to do, 1: hold chunk, 2: general chunk
+	if (s < numStreams) {
+		StreamState *st = descs[s].state;
+		GenStateF32 &gs = st->gen.f32;
+		if (firstRound) { gs.callPos = 0; gs.callDrained = 0; }
+		const uint32_t pos = firstRound ? 0u : gs.callPos;
+		const bool drained = firstRound ? false : (gs.callDrained != 0);
+		if (pos < sampleCount && !drained) {
+			const uint32_t left = sampleCount - pos;
+			cls = (left >= holdTicks && canHoldF32(*st, holdTicks)) ? 1 : 2;
+		}
+	}
+	const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+	const unsigned mH = __ballot_sync(0xffffffffu, cls == 1), mG = __ballot_sync(0xffffffffu, cls == 2);
+	uint32_t baseH = 0, baseG = 0;
+	if (lane == 0) {
+		if (mH) baseH = atomicAdd(counters + 0, (uint32_t)__popc(mH));
+		if (mG) baseG = atomicAdd(counters + 1, (uint32_t)__popc(mG));
+	}
+	baseH = __shfl_sync(0xffffffffu, baseH, 0);
+	baseG = __shfl_sync(0xffffffffu, baseG, 0);
+	if (cls == 1) listHold[baseH + __popc(mH & below)] = s;
+	if (cls == 2) listGen[baseG + __popc(mG & below)] = s;
+}
+
+// ---- the two sides of a stream in different warps of one block ------------------------------------------------
+// block = 4 warps: warps 0,1 run the cascade side of streams [64b, 64b+32) and [64b+32, 64b+64) of the list,
+// warps 2,3 the parallel side of the same streams.  Warp w and warp w+2 share one named barrier and a
+// double-buffered shared-memory hand-over of (aspiration noise word, parallel-bank output) x 8 ticks x 32 lanes.
+struct XchgSmem {
+	uint2 *base;  // this lane's column of the pair's [2 buffers][8 ticks][32 lanes]
+	int barId;
+	__device__ __forceinline__ void put(uint32_t t, uint32_t wA, float par) {
+		base[(((t >> 3) & 1u) * kGroupTicks + (t & (kGroupTicks - 1))) * 32] = make_uint2(wA, __float_as_uint(par));
+	}
+	__device__ __forceinline__ void get(uint32_t t, uint32_t &wA, float &par) const {
+		uint2 v = base[(((t >> 3) & 1u) * kGroupTicks + (t & (kGroupTicks - 1))) * 32];
+		wA = v.x;
+		par = __uint_as_float(v.y);
+	}
+	__device__ __forceinline__ void sync() { asm volatile("bar.sync %0, 64;" ::"r"(barId) : "memory"); }
+};
+struct NullOut {
+	__device__ __forceinline__ void push(int) {}
+};
+
+constexpr int kPairBlock = 128;        // threads
+constexpr int kPairStreams = 64;       // streams per block
+
+// descs[numStreams] is a dummy stream (fresh state, empty queue) that the idle lanes of a partially filled warp run
+__global__ void __launch_bounds__(kPairBlock)
+klatt_f32_hold_kernel(const StreamDesc *__restrict__ descs, const uint32_t *__restrict__ list,
+                      const uint32_t *__restrict__ counters, uint32_t numStreams, int sampleRate, uint32_t holdTicks,
+                      int16_t *__restrict__ out, size_t rowStride, NoiseConfig noise) {
+	__shared__ uint2 xbuf[2][2 * kGroupTicks * 32];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, pair = warp & 1u;
+	const uint32_t count = counters[0];
+	if (blockIdx.x * kPairStreams + pair * 32 >= count) return;  // the whole warp pair is idle
+	const uint32_t slot = blockIdx.x * kPairStreams + pair * 32 + lane;
+	const bool valid = slot < count;
+	const uint32_t s = valid ? list[slot] : numStreams;
+	const StreamDesc desc = descs[s];
+	XchgSmem xc{&xbuf[pair][lane], (int)(1 + pair)};
+	if (warp < 2) {
+		int16_t *row = out + (size_t)(valid ? s : 0) * rowStride + desc.state->gen.f32.callPos;
+		OutWriter ow;
+		ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0), valid);
+		renderHoldF32<kRoleCascade>(desc, sampleRate, holdTicks, ow, noise, xc);
+	} else {
+		NullOut no;
+		renderHoldF32<kRoleParallel>(desc, sampleRate, holdTicks, no, noise, xc);
+	}
+}
+
+// a round of the general path: thread pair = stream list[slot], at most genTicks ticks from where the stream stands
+__global__ void __launch_bounds__(kPairBlock)
+klatt_f32_general_pair_kernel(const StreamDesc *__restrict__ descs, const uint32_t *__restrict__ list,
+                              const uint32_t *__restrict__ counters, uint32_t numStreams, int sampleRate,
+                              uint32_t sampleCount, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,
+                              NoiseConfig noise) {
+	__shared__ uint2 xbuf[2][2 * kGroupTicks * 32];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, pair = warp & 1u;
+	const uint32_t count = counters[1];
+	if (blockIdx.x * kPairStreams + pair * 32 >= count) return;
+	const uint32_t slot = blockIdx.x * kPairStreams + pair * 32 + lane;
+	const bool valid = slot < count;
+	const uint32_t s = valid ? list[slot] : numStreams;
+	const StreamDesc desc = descs[s];
+	const uint32_t pos = desc.state->gen.f32.callPos;
+	uint32_t ticks = 0;
+	if (valid) {
+		ticks = sampleCount - pos;
+		if (ticks > genTicks) ticks = genTicks;
+	}
+	XchgSmem xc{&xbuf[pair][lane], (int)(1 + pair)};
+	int32_t lastUserIndex;
+	uint32_t qHead;
+	if (warp < 2) {
+		int16_t *row = out + (size_t)(valid ? s : 0) * rowStride;
+		OutWriter ow;
+		ow.init(row + pos, ((reinterpret_cast<uintptr_t>(row + pos) & 15u) == 0), valid);
+		const uint32_t produced = renderGeneralF32<kRoleCascade>(desc, sampleRate, ticks, genTicks, ow, noise, xc, &lastUserIndex, &qHead);
+		ow.flush();
+		if (produced < ticks) zeroRow(row, pos + produced, sampleCount);  // drained: the rest of the row is silence
+	} else {
+		NullOut no;
+		renderGeneralF32<kRoleParallel>(desc, sampleRate, ticks, genTicks, no, noise, xc, &lastUserIndex, &qHead);
+	}
+}
+
+// One launch renders the whole call, both sides of a stream in one thread (thread i = stream i; call state reset
+// and results written here).  Per-handle API and small batches; plans inline unless the descriptors carry them.
 __global__ void __launch_bounds__(kF32Block)
-klatt_batch_f32_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
-                       int16_t *__restrict__ out, size_t rowStride, uint32_t *__restrict__ samplesWritten,
-                       StreamResult *__restrict__ results, NoiseConfig noise) {
+klatt_f32_general_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
+                         int16_t *__restrict__ out, size_t rowStride, uint32_t *__restrict__ samplesWritten,
+                         StreamResult *__restrict__ results, NoiseConfig noise) {
 	const uint32_t s = blockIdx.x * kF32Block + threadIdx.x;
 	if (s >= numStreams) return;
 	const StreamDesc desc = descs[s];
-	__shared__ float coarse[kCoarseWords * kF32Block];
-	SmemCoarse cs;
-	cs.base = coarse + threadIdx.x;
-	OutWriter ow;
+	GenStateF32 &gs = desc.state->gen.f32;
+	gs.callPos = 0;
+	gs.callDrained = 0;
 	int16_t *row = out + (size_t)s * rowStride;
+	OutWriter ow;
 	ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0));
 	int32_t lastUserIndex;
 	uint32_t qHead;
-	uint32_t produced = renderStreamF32(desc, sampleRate, sampleCount, ow, cs, noise, &lastUserIndex, &qHead);
+	XchgSelf xc;
+	const uint32_t produced = renderGeneralF32<kRoleBoth>(desc, sampleRate, sampleCount, sampleCount, ow, noise, xc, &lastUserIndex, &qHead);
 	ow.flush();
-	for (uint32_t i = produced; i < sampleCount; ++i) row[i] = 0;  // drained: the rest of the row is silence
+	if (produced < sampleCount) zeroRow(row, produced, sampleCount);  // drained: the rest of the row is silence
 	if (samplesWritten) samplesWritten[s] = produced;
 	if (results) {
 		StreamResult res;
@@ -44,13 +209,73 @@ klatt_batch_f32_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams
 	}
 }
 
+__global__ void __launch_bounds__(256)
+klatt_finalize_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, uint32_t *__restrict__ samplesWritten,
+                      StreamResult *__restrict__ results) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= numStreams) return;
+	const StreamState *st = descs[s].state;
+	const uint32_t w = st->gen.f32.callPos;
+	if (samplesWritten) samplesWritten[s] = w;
+	if (results) {
+		StreamResult res;
+		res.written = w; res.lastUserIndex = st->fm.lastUserIndex; res.qHead = st->fm.qHead; res.pad = 0;
+		results[s] = res;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_t totalRequests, const double *frames,
+                            const uint32_t *fadeDur, const uint8_t *isNull, int sampleRate, FadePlanF32 *plans,
+                            cudaStream_t stream) {
+	if (totalRequests == 0) return cudaSuccess;
+	const unsigned grid = (unsigned)((totalRequests + 127) / 128);
+	klatt_plan_kernel<<<grid, 128, 0, stream>>>(offsets, numStreams, frames, fadeDur, isNull, sampleRate, plans);
+	return cudaGetLastError();
+}
+
 cudaError_t launchKlattF32(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                            int16_t *out, size_t rowStride, uint32_t *samplesWritten, StreamResult *results,
                            NoiseConfig noise, cudaStream_t stream) {
 	if (numStreams == 0 || sampleCount == 0) return cudaSuccess;
 	dim3 grid((numStreams + kF32Block - 1) / kF32Block);
-	klatt_batch_f32_kernel<<<grid, kF32Block, 0, stream>>>(descs, numStreams, sampleRate, sampleCount, out, rowStride,
-	                                                       samplesWritten, results, noise);
+	klatt_f32_general_kernel<<<grid, kF32Block, 0, stream>>>(descs, numStreams, sampleRate, sampleCount, out, rowStride,
+	                                                         samplesWritten, results, noise);
+	return cudaGetLastError();
+}
+
+// One call as rounds of (partition, hold || general).  `side` is a second stream of the same device on which the
+// general kernel of each round runs next to the hold kernel; `fork` / `join` are two events owned by the caller.
+// scratch: listHold[numStreams], listGen[numStreams], counters[2 * rounds] (zeroed here).  descs holds numStreams + 1
+// entries: the last one is the dummy stream idle lanes run.
+cudaError_t launchKlattF32Rounds(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
+                                 uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride,
+                                 uint32_t *samplesWritten, StreamResult *results, NoiseConfig noise, uint32_t *listHold,
+                                 uint32_t *listGen, uint32_t *counters, cudaStream_t stream, cudaStream_t side,
+                                 cudaEvent_t fork, cudaEvent_t join, unsigned long long *launchCounter) {
+	if (numStreams == 0 || sampleCount == 0) return cudaSuccess;
+	const uint32_t rounds = (sampleCount + genTicks - 1) / genTicks;
+	cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 2 * (size_t)rounds, stream);
+	if (e != cudaSuccess) return e;
+	const dim3 gridP((numStreams + 255) / 256), gridR((numStreams + kPairStreams - 1) / kPairStreams);
+	for (uint32_t r = 0; r < rounds; ++r) {
+		uint32_t *cnt = counters + 2 * (size_t)r;
+		klatt_partition_kernel<<<gridP, 256, 0, stream>>>(descs, numStreams, sampleCount, holdTicks, genTicks, r == 0, listHold,
+		                                                  listGen, cnt);
+		if ((e = cudaEventRecord(fork, stream)) != cudaSuccess) return e;
+		if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return e;
+		klatt_f32_general_pair_kernel<<<gridR, kPairBlock, 0, side>>>(descs, listGen, cnt, numStreams, sampleRate, sampleCount,
+		                                                              genTicks, out, rowStride, noise);
+		klatt_f32_hold_kernel<<<gridR, kPairBlock, 0, stream>>>(descs, listHold, cnt, numStreams, sampleRate, holdTicks, out,
+		                                                        rowStride, noise);
+		if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
+		if ((e = cudaStreamWaitEvent(stream, join, 0)) != cudaSuccess) return e;
+		if (launchCounter) *launchCounter += 3;
+	}
+	klatt_finalize_kernel<<<gridP, 256, 0, stream>>>(descs, numStreams, samplesWritten, results);
+	if (launchCounter) *launchCounter += 1;
 	return cudaGetLastError();
 }
 

@@ -1,15 +1,21 @@
 // FP32 production formulation of the Klatt hot path (one stream, serial in time).
 //
-// The function renderStreamF32() below IS the body of the batch kernel (klatt_f32.cu calls it once per
-// thread); it is written against plain pointers so that the very same arithmetic can also be compiled for the
-// host by the numerics study under tests/hostsim/ (test infrastructure; the product never runs it on a CPU).
+// renderGeneralF32() and renderHoldF32() below ARE the bodies of the two batch kernels (klatt_f32.cu calls them
+// once per thread); they are written against plain pointers so that the very same arithmetic can also be compiled
+// for the host by the numerics study under tests/hostsim/ (test infrastructure; the product never runs it on a CPU).
+// Every multiply-add that is meant to be fused is an explicit fmaf(); the translation unit is compiled with
+// -fmad=false (host: -ffp-contract=off), so both functions round identically on a hold tick and a stream may
+// switch between them at any chunk boundary without changing a single output bit.
 //
-// What it computes is the reference's per-sample loop (reference src/speechWaveGenerator.cpp:197-214 driven by
+// What they compute is the reference's per-sample loop (reference src/speechWaveGenerator.cpp:197-214 driven by
 // the frame manager of src/frame.cpp:41-80), reformulated so that FP32 is accurate enough (DESIGN.md
 // "FP32 formulation" has the derivations and the measured SNR):
 //
 //  * frame manager: same tick state machine (pop / fade / swap / hold, NULL-frame rewrites, userIndex, drain),
-//    but a fade is walked with per-tick INCREMENTS prepared once per request by planFade() in double.
+//    run as EVENTS: a stream only enters the state machine on the ticks where something changes (first fade
+//    tick, landing tick, swap tick, first hold tick, pop tick); every other tick is the same straight-line
+//    update with per-tick INCREMENTS that are zero outside fades.  The increments of a fade are prepared once
+//    per request by planFade() in double.
 //  * pitch and glottal phase stay FP64 (src/speechWaveGenerator.cpp:55,74): the sawtooth turns phase error into
 //    full-scale error (a wrap that lands one sample early rings through every resonator), FP32 phase gives
 //    ~11 dB SNR.  Vibrato phase and its increment are 64-bit fixed point: exact accumulation, no drift.
@@ -18,12 +24,13 @@
 //    c = rho - 1; src :116-131) but only the SMALL quantities a, rho, d are represented, instead of cancelling
 //    b ~ 2 against c ~ -1.
 //  * coefficients during a fade: a linear fade of (f, bw) moves the pole along a complex geometric sequence,
-//    so zeta = 1 - pole is advanced by  zeta' = zeta + omega - zeta*omega  (6 FMAs) and
-//    rho' = rho + kappa*(1 - rho), instead of 14 x (exp + cos) per tick (src :113-125).
+//    so zeta = 1 - pole is advanced by  zeta' = zeta + omega - zeta*omega  (6 flops) and a = |zeta|^2,
+//    rho = 2*Re(zeta) - a follow (3 flops), instead of 14 x (exp + cos) per tick (src :113-125).
 //  * noise, source shaping, mixes, gain, clamp and truncation follow src :40, :72-86, :150, :172-179, :207-208.
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include "klatt_common.h"
 #include "philox.cuh"
 
@@ -49,9 +56,10 @@ KLATT_HD constexpr int directParam(int i) {
 // ---------------------------------------------------------------------------------------------------
 // planFade: everything a fade from frame `o` to frame `n` over F ticks needs (double precision, once per request).
 // `o`/`n` are what the reference holds in oldFrameRequest->frame / newFrameRequest->frame after the pop-tick
-// rewrites (src/frame.cpp:59-71).  NaN in a target keeps the old value (src/utils.h:21).
+// rewrites (src/frame.cpp:59-71).  NaN in a target keeps the old value (src/utils.h:21).  voicePitch is not
+// part of the plan (it is tracked in FP64 by the render kernels).
 // ---------------------------------------------------------------------------------------------------
-KLATT_HD void poleTerms(double f, double bw, double srInv, float &zre, float &zim, float &rho) {
+KLATT_HD void poleTerms(double f, double bw, double srInv, float &zre, float &zim) {
 	const double PI = 3.14159265358979323846;
 	double x = -PI * bw * srInv;        // log of the pole radius
 	double th = 2.0 * PI * f * srInv;   // pole angle
@@ -60,7 +68,6 @@ KLATT_HD void poleTerms(double f, double bw, double srInv, float &zre, float &zi
 	double sh = sin(0.5 * th);
 	zre = (float)(-em1 + 2.0 * r * sh * sh);  // 1 - r*cos(th), cancellation-free
 	zim = (float)(-r * sin(th));
-	rho = (float)(-expm1(2.0 * x));  // 1 - r^2
 }
 
 // vibratoSpeed (Hz) -> phase increment per tick in 2^-64 cycles
@@ -95,9 +102,9 @@ KLATT_HD void planFade(const double *o, const double *n, uint32_t F, int sampleR
 		double b0 = o[resBwParam(r)], b1 = n[resBwParam(r)];
 		if (f1 != f1) f1 = f0;
 		if (b1 != b1) b1 = b0;
-		poleTerms(f0, b0, srInv, p.z0re[r], p.z0im[r], p.rho0[r]);
-		poleTerms(f0 + ((f1 - f0) * 1.0), b0 + ((b1 - b0) * 1.0), srInv, p.zFre[r], p.zFim[r], p.rhoF[r]);
-		// per-tick ratio of the pole: q*exp(i*dth) = 1 - omega ; |ratio|^2 = 1 - kappa
+		poleTerms(f0, b0, srInv, p.z0re[r], p.z0im[r]);
+		poleTerms(f0 + ((f1 - f0) * 1.0), b0 + ((b1 - b0) * 1.0), srInv, p.zFre[r], p.zFim[r]);
+		// per-tick ratio of the pole: q*exp(i*dth) = 1 - omega
 		const double PI = 3.14159265358979323846;
 		double xs = -PI * (b1 - b0) * invF * srInv;
 		double dth = 2.0 * PI * (f1 - f0) * invF * srInv;
@@ -106,13 +113,11 @@ KLATT_HD void planFade(const double *o, const double *n, uint32_t F, int sampleR
 		double sh = sin(0.5 * dth);
 		p.wre[r] = (float)(-qm1 + 2.0 * q * sh * sh);
 		p.wim[r] = (float)(-q * sin(dth));
-		p.kap[r] = (float)(-expm1(2.0 * xs));
 		{  // the same pole ratio over kCoarseTicks ticks
 			double xsA = xs * kCoarseTicks, dthA = dth * kCoarseTicks;
 			double QAm1 = expm1(xsA), QA = 1.0 + QAm1, shA = sin(0.5 * dthA);
 			p.Wre[r] = (float)(-QAm1 + 2.0 * QA * shA * shA);
 			p.Wim[r] = (float)(-QA * sin(dthA));
-			p.Kap[r] = (float)(-expm1(2.0 * xsA));
 		}
 		if (r == kResN0) {
 			p.n0InvFade = !(f0 == 0 && f1 == 0);
@@ -121,22 +126,84 @@ KLATT_HD void planFade(const double *o, const double *n, uint32_t F, int sampleR
 	}
 }
 
+// The frames a pre-queued request fades between, without running the stream (klatt_plan_kernel): request j of a
+// queue whose predecessors are all known.  prevReal = the last non-NULL request before j (nullptr: none, the
+// zero-initialised oldFrameRequest of src/frame.cpp:86), prevIsNull = request j-1 was a NULL request (or j is
+// the first request of a fresh player: the initial old request is NULL, src/frame.cpp:87).
+//   NULL request : new = old with preFormantGain 0                          (src/frame.cpp:59-63)
+//   real after NULL : old = new with preFormantGain 0                       (src/frame.cpp:64-67)
+KLATT_HD void plannedFrames(const double *prevReal, bool prevIsNull, const double *cur, bool curIsNull, double *o, double *n) {
+	for (int i = 0; i < kNumParams; ++i) o[i] = prevReal ? prevReal[i] : 0.0;
+	if (prevIsNull) o[kPreFormantGain] = 0;
+	if (curIsNull) {
+		for (int i = 0; i < kNumParams; ++i) n[i] = o[i];
+		n[kPreFormantGain] = 0;
+	} else {
+		for (int i = 0; i < kNumParams; ++i) n[i] = cur[i];
+		if (prevIsNull) {
+			for (int i = 0; i < kNumParams; ++i) o[i] = n[i];
+			o[kPreFormantGain] = 0;
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------------
-// per-stream working set (registers on the device)
+// Roles.  A stream's tick splits into two halves that only meet in the final mix (reference
+// src/speechWaveGenerator.cpp:203-207):
+//   cascade side  : vibrato, glottal phase, aspiration, rN0, rNP, r6..r1  (resonators 0..7)  -> x, and the sample
+//   parallel side : noise draws, frication, the six parallel sections      (resonators 8..13) -> par
+// kRoleBoth runs both in one thread (per-handle API, host numerics build).  The batch kernels give each side its
+// own thread in a different warp of the block (half the registers per thread, twice the warps per SM); the
+// parallel side hands (aspiration noise word, par) over through shared memory 8 ticks at a time.  Every role
+// executes the same operations on the same values, so all of them produce the same bits.
 // ---------------------------------------------------------------------------------------------------
-struct LiveF32 {
-	float y[kNumResonators], d[kNumResonators];             // filter memories
-	float zre[kNumResonators], zim[kNumResonators];         // zeta = 1 - pole
-	float rho[kNumResonators], a[kNumResonators];           // 1-|pole|^2, |zeta|^2
-	float dir[kNumDirect];
-	float wre[kNumResonators], wim[kNumResonators], kap[kNumResonators];  // fade increments (resonators)
-	float dir0[kNumDirect], dstep[kNumDirect];  // direct params during a fade: dir = dir0 + k*dstep (stateless: an
-	                                            // accumulated "+= dstep" rounds the same way every tick and drifts)
-	float invA0;     // 1/a of the anti-resonator
+enum Role : int { kRoleBoth = 0, kRoleCascade = 1, kRoleParallel = 2 };
+constexpr int kGroupTicks = 8;  // hand-over granularity, and one 16-byte output store
+
+template <int ROLE> struct RoleTraits {
+	static constexpr bool hasC = ROLE != kRoleParallel;
+	static constexpr bool hasP = ROLE != kRoleCascade;
+	static constexpr int R0 = hasC ? 0 : kResParallel;
+	static constexpr int R1 = hasP ? kNumResonators : kResParallel;
+};
+// direct params each side reads
+KLATT_HD constexpr bool directOfCascade(int i) {
+	return i == dVibratoPitchOffset || i == dVoiceTurbulenceAmplitude || i == dGlottalOpenQuotient || i == dVoiceAmplitude ||
+	       i == dAspirationAmplitude || i == dCaNP || i == dPreFormantGain || i == dOutputGain;
+}
+KLATT_HD constexpr bool directOfParallel(int i) {
+	return i == dFricationAmplitude || (i >= dPa1 && i <= dPa6) || i == dParallelBypass || i == dPreFormantGain;
+}
+template <int ROLE> KLATT_HD constexpr bool roleUsesDirect(int i) {
+	return (RoleTraits<ROLE>::hasC && directOfCascade(i)) || (RoleTraits<ROLE>::hasP && directOfParallel(i));
+}
+
+// hand-over between the two sides when they share a thread: plain members
+struct XchgSelf {
+	uint32_t wA_;
+	float par_;
+	KLATT_HD void put(uint32_t, uint32_t wA, float par) { wA_ = wA; par_ = par; }
+	KLATT_HD void get(uint32_t, uint32_t &wA, float &par) const { wA = wA_; par = par_; }
+	KLATT_HD void sync() {}
+};
+
+// ---------------------------------------------------------------------------------------------------
+// per-stream working set (registers on the device).  Arrays are indexed with compile-time constants only
+// (every loop below is fully unrolled), so a role never materialises the elements it does not touch.
+// ---------------------------------------------------------------------------------------------------
+struct DspState {  // what every tick reads AND writes
+	float y[kNumResonators], d[kNumResonators];
 	float aspLast, fricLast;
 	uint64_t vibratoPos;
-	int64_t vibInc, vibIncStep;
-	double pitchPos, pitch, pitchStep;
+	int64_t vibInc;
+	double pitchPos, pitch, pitchInc;
+};
+
+struct CoefF32 {  // what a tick only reads: a pure function of (zeta, direct params)
+	float a[kNumResonators], rho[kNumResonators];
+	float invA0;  // 1/a of the anti-resonator
+	float vpo, vta, goq, va, aa, caNP, pa[6], bypass;
+	float halfGain, fricGain, og4000;
 	bool n0Inv;
 };
 
@@ -148,106 +215,57 @@ KLATT_HD float fastRcp(float x) {
 #endif
 }
 
-KLATT_HD void refreshA(LiveF32 &L) {
+constexpr float kDrawScale = 1.0f / 8388608.0f;  // noise draws enter as 23-bit integers
+
+template <int ROLE>
+KLATT_HD void buildCoef(CoefF32 &C, const float *zre, const float *zim, const float *dir, bool n0Inv) {
+	using T = RoleTraits<ROLE>;
 #pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) L.a[r] = fmaf(L.zre[r], L.zre[r], L.zim[r] * L.zim[r]);
-	L.invA0 = fastRcp(L.a[kResN0]);
+	for (int r = T::R0; r < T::R1; ++r) {
+		float a = fmaf(zre[r], zre[r], zim[r] * zim[r]);  // |1 - pole|^2
+		C.a[r] = a;
+		C.rho[r] = fmaf(2.0f, zre[r], -a);                // 1 - |pole|^2
+	}
+	C.halfGain = dir[dPreFormantGain] * 0.5f;
+	if (T::hasC) {
+		C.invA0 = fastRcp(C.a[kResN0]);
+		C.vpo = dir[dVibratoPitchOffset]; C.vta = dir[dVoiceTurbulenceAmplitude]; C.goq = dir[dGlottalOpenQuotient];
+		C.va = dir[dVoiceAmplitude]; C.aa = dir[dAspirationAmplitude]; C.caNP = dir[dCaNP];
+		C.og4000 = dir[dOutputGain] * 4000.0f;
+		C.n0Inv = n0Inv;
+	}
+	if (T::hasP) {
+#pragma unroll
+		for (int k = 0; k < 6; ++k) C.pa[k] = dir[dPa1 + k];
+		C.bypass = dir[dParallelBypass];
+		C.fricGain = ((0.3f * kDrawScale) * dir[dFricationAmplitude]) * C.halfGain;
+	}
 }
 
-// one fade tick of every interpolated quantity (reference: 47 lerps + 14 setParams per tick, src/frame.cpp:50-52,
-// src/speechWaveGenerator.cpp:113-125)
-KLATT_HD void stepFade(LiveF32 &L, float k) {
+// one tick of the pole recurrences: zeta' = zeta + omega - zeta*omega (a no-op when omega == 0)
+template <int ROLE>
+KLATT_HD void stepPoles(float *zre, float *zim, const float *wre, const float *wim) {
+	using T = RoleTraits<ROLE>;
 #pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) {
-		float zr = L.zre[r], zi = L.zim[r], wr = L.wre[r], wi = L.wim[r];
+	for (int r = T::R0; r < T::R1; ++r) {
+		float zr = zre[r], zi = zim[r], wr = wre[r], wi = wim[r];
 		float tr = fmaf(-zr, wr, wr);   // omega - zeta*omega, real
 		tr = fmaf(zi, wi, tr);
 		float ti = fmaf(-zr, wi, wi);   // imaginary
 		ti = fmaf(-zi, wr, ti);
-		L.zre[r] = zr + tr;
-		L.zim[r] = zi + ti;
-		L.rho[r] = fmaf(L.kap[r], 1.0f - L.rho[r], L.rho[r]);
+		zre[r] = zr + tr;
+		zim[r] = zi + ti;
 	}
-#pragma unroll
-	for (int i = 0; i < kNumDirect; ++i) L.dir[i] = fmaf(k, L.dstep[i], L.dir0[i]);
-	refreshA(L);
-	L.pitch += L.pitchStep;
-	L.vibInc += L.vibIncStep;
-}
-
-KLATT_HD void loadFadeStart(LiveF32 &L, const FadePlanF32 &p) {
-#pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) { L.zre[r] = p.z0re[r]; L.zim[r] = p.z0im[r]; L.rho[r] = p.rho0[r]; }
-#pragma unroll
-	for (int i = 0; i < kNumDirect; ++i) L.dir[i] = p.dir0[i];
-	L.vibInc = p.vibInc0;
-}
-KLATT_HD void loadFadeFinal(LiveF32 &L, const FadePlanF32 &p) {
-#pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) { L.zre[r] = p.zFre[r]; L.zim[r] = p.zFim[r]; L.rho[r] = p.rhoF[r]; }
-#pragma unroll
-	for (int i = 0; i < kNumDirect; ++i) L.dir[i] = p.dirFinal[i];
-	L.vibInc = p.vibIncFinal;
-	refreshA(L);
-}
-KLATT_HD void loadFadeSteps(LiveF32 &L, const FadePlanF32 &p) {
-#pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) { L.wre[r] = p.wre[r]; L.wim[r] = p.wim[r]; L.kap[r] = p.kap[r]; }
-#pragma unroll
-	for (int i = 0; i < kNumDirect; ++i) { L.dstep[i] = p.dirStep[i]; L.dir0[i] = p.dir0[i]; }
-	L.vibIncStep = p.vibIncStep;
-}
-
-// Coarse (kCoarseTicks-tick) pole recurrence: 6 words per resonator that are touched once every kCoarseTicks
-// samples, so they live outside the register file (shared memory on the device, [word][thread]).
-//   Store::at(i) -> float&   i in [0, kCoarseWords)
-constexpr int kCoarseWords = 6 * kNumResonators;  // zc_re, zc_im, rhoc, W_re, W_im, Kap
-
-template <class Store>
-KLATT_HD void coarseLoadSteps(Store &cs, const FadePlanF32 &p) {
-#pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) {
-		cs.at(3 * kNumResonators + r) = p.Wre[r];
-		cs.at(4 * kNumResonators + r) = p.Wim[r];
-		cs.at(5 * kNumResonators + r) = p.Kap[r];
-	}
-}
-template <class Store>
-KLATT_HD void coarseCapture(Store &cs, const LiveF32 &L) {
-#pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) {
-		cs.at(r) = L.zre[r];
-		cs.at(kNumResonators + r) = L.zim[r];
-		cs.at(2 * kNumResonators + r) = L.rho[r];
-	}
-}
-template <class Store>
-KLATT_HD void coarseAdvance(Store &cs, LiveF32 &L) {
-#pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) {
-		float zr = cs.at(r), zi = cs.at(kNumResonators + r), rh = cs.at(2 * kNumResonators + r);
-		float wr = cs.at(3 * kNumResonators + r), wi = cs.at(4 * kNumResonators + r), kp = cs.at(5 * kNumResonators + r);
-		float tr = fmaf(-zr, wr, wr);
-		tr = fmaf(zi, wi, tr);
-		float ti = fmaf(-zr, wi, wi);
-		ti = fmaf(-zi, wr, ti);
-		zr += tr;
-		zi += ti;
-		rh = fmaf(kp, 1.0f - rh, rh);
-		cs.at(r) = zr; cs.at(kNumResonators + r) = zi; cs.at(2 * kNumResonators + r) = rh;
-		L.zre[r] = zr; L.zim[r] = zi; L.rho[r] = rh;
-	}
-	refreshA(L);
 }
 
 // delta-form two-pole section; returns the new output
-KLATT_HD float resonate(LiveF32 &L, int r, float x) {
-	float w = fmaf(-L.rho[r], L.d[r], L.d[r]);  // (1-rho)*d
-	w = fmaf(-L.a[r], L.y[r], w);
-	float dn = fmaf(L.a[r], x, w);
-	L.d[r] = dn;
-	L.y[r] += dn;
-	return L.y[r];
+KLATT_HD float resonate(DspState &S, const CoefF32 &C, int r, float x) {
+	float w = fmaf(-C.rho[r], S.d[r], S.d[r]);  // (1-rho)*d
+	w = fmaf(-C.a[r], S.y[r], w);
+	float dn = fmaf(C.a[r], x, w);
+	S.d[r] = dn;
+	S.y[r] += dn;
+	return S.y[r];
 }
 
 KLATT_HD float sinTurns(float t) {  // sin(2*pi*t), |t| <= 0.5
@@ -258,92 +276,241 @@ KLATT_HD float sinTurns(float t) {  // sin(2*pi*t), |t| <= 0.5
 #endif
 }
 
-// one generated sample (reference src/speechWaveGenerator.cpp:203-208); uA/uF are the two uniform draws in [0,1]
-KLATT_HD int dspTick(LiveF32 &L, float uA, float uF, double srInv) {
-	// ---- vibrato (:73) and glottal phase (:74, :55) ----
-	L.vibratoPos += (uint64_t)L.vibInc;
-	float vph = (float)(int32_t)(uint32_t)(L.vibratoPos >> 32) * 2.3283064365386963e-10f;  // cycles in [-0.5, 0.5)
-	float vib = sinTurns(vph) * 0.06f * L.dir[dVibratoPitchOffset];
-	double base = L.pitch * srInv;
-#ifdef KLATT_EXPERIMENT_VIB64
-	double vibd = sin((double)(int64_t)L.vibratoPos * (6.283185307179586 / 18446744073709551616.0)) * 0.06 * (double)L.dir[dVibratoPitchOffset];
-	double pos = L.pitchPos + fma(base, vibd, base);
+KLATT_HD float bitsToFloat(uint32_t u) {
+#ifdef __CUDA_ARCH__
+	return __uint_as_float(u);
 #else
-	double pos = L.pitchPos + fma(base, (double)vib, base);
+	float f;
+	memcpy(&f, &u, 4);
+	return f;
 #endif
-	if (pos >= 1.0) pos -= 1.0;
-	if (!(pos >= 0.0 && pos < 1.0)) pos = fmod(pos, 1.0);  // negative or absurd pitch: the reference's fmod semantics
-	L.pitchPos = pos;
-	float voice = (float)pos;
-	// ---- aspiration noise + turbulence (:40, :75-80) ----
-	L.aspLast = fmaf(0.75f, L.aspLast, uA);
-	float asp = L.aspLast * 0.2f;
-	float turb = asp * L.dir[dVoiceTurbulenceAmplitude];
-	if (voice < L.dir[dGlottalOpenQuotient]) turb *= 0.01f;
-	float v = (fmaf(voice, 2.0f, -1.0f) + turb) * L.dir[dVoiceAmplitude];
-	float src = fmaf(asp, L.dir[dAspirationAmplitude], v);
-	const float halfGain = L.dir[dPreFormantGain] * 0.5f;
-	// ---- cascade (:147-158) ----
-	float ci = src * halfGain;
-	float dx = ci - L.y[kResN0];  // anti-resonator: memories hold INPUTS (:133)
-	float dx1 = fmaf(-L.rho[kResN0], L.d[kResN0], L.d[kResN0]);  // (1-rho) * previous input difference
-	float n0 = L.n0Inv ? fmaf(dx - dx1, L.invA0, L.y[kResN0])
-	                   : fmaf(L.a[kResN0], dx, dx1 + L.y[kResN0]);
-	L.d[kResN0] = dx;
-	L.y[kResN0] = ci;
-	float np = resonate(L, kResNP, n0);
-	float x = fmaf(np - ci, L.dir[dCaNP], ci);
-#pragma unroll
-	for (int r = kResCascade; r < kResParallel; ++r) x = resonate(L, r, x);
-	// ---- frication noise + parallel bank (:205-206, :170-180) ----
-	L.fricLast = fmaf(0.75f, L.fricLast, uF);
-	float pin = (L.fricLast * 0.3f) * L.dir[dFricationAmplitude] * halfGain;
+}
+
+// x - trunc(x): the reference's fmod(x, 1) (src/speechWaveGenerator.cpp:55) without a branch; exact for |x| < 2^31
+KLATT_HD double fracRef(double x) {
+#ifdef __CUDA_ARCH__
+	return x - (double)__double2int_rz(x);
+#else
+	double t = (x != x) ? 0.0 : (x >= 2147483647.0 ? 2147483647.0 : (x <= -2147483648.0 ? -2147483648.0 : (double)(int32_t)x));
+	return x - t;
+#endif
+}
+
+// parallel side of one generated sample (reference src/speechWaveGenerator.cpp:205-206, :170-180): wF is the
+// frication noise word (the reference's rand() value is word>>1; the top 23 bits are used)
+KLATT_HD float parallelSide(DspState &S, const CoefF32 &C, uint32_t wF) {
+	float uF = bitsToFloat(0x4B000000u | (wF >> 9)) - 8388608.0f;  // exact integer 0..2^23-1
+	S.fricLast = fmaf(0.75f, S.fricLast, uF);
+	float pin = S.fricLast * C.fricGain;
 	float par = 0.0f;
 #pragma unroll
-	for (int k = 0; k < 6; ++k) par = fmaf(resonate(L, kResParallel + k, pin) - pin, L.dir[dPa1 + k], par);
-	par = fmaf(pin - par, L.dir[dParallelBypass], par);
+	for (int k = 0; k < 6; ++k) par = fmaf(resonate(S, C, kResParallel + k, pin) - pin, C.pa[k], par);
+	return fmaf(pin - par, C.bypass, par);
+}
+
+// cascade side (reference src/speechWaveGenerator.cpp:203-204, :72-86, :147-158) and the final mix (:207-208)
+KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, double srInv) {
+	// ---- vibrato (:73) and glottal phase (:74, :55) ----
+	S.vibratoPos += (uint64_t)S.vibInc;
+	// cycles in [-0.5, 0.5), rounded to nearest: a truncated phase is a systematic pitch error while a slow vibrato
+	// sits inside one quantisation step
+	float vph = (float)(int32_t)(uint32_t)(S.vibratoPos >> 32) * 2.3283064365386963e-10f;
+	float vib = (sinTurns(vph) * 0.06f) * C.vpo;
+	S.pitch += S.pitchInc;
+	double base = S.pitch * srInv;
+	double pos = fracRef(S.pitchPos + fma(base, (double)vib, base));
+	S.pitchPos = pos;
+	float voice = (float)pos;
+	// ---- aspiration noise + turbulence (:40, :75-80) ----
+	float uA = bitsToFloat(0x4B000000u | (wA >> 9)) - 8388608.0f;
+	S.aspLast = fmaf(0.75f, S.aspLast, uA);
+	float asp = S.aspLast * (0.2f * kDrawScale);
+	float turb = asp * C.vta;
+	if (voice < C.goq) turb *= 0.01f;
+	float v = (fmaf(voice, 2.0f, -1.0f) + turb) * C.va;
+	float src = fmaf(asp, C.aa, v);
+	// ---- cascade (:147-158) ----
+	float ci = src * C.halfGain;
+	float dx = ci - S.y[kResN0];  // anti-resonator: memories hold INPUTS (:133)
+	float dx1 = fmaf(-C.rho[kResN0], S.d[kResN0], S.d[kResN0]);  // (1-rho) * previous input difference
+	float n0 = C.n0Inv ? fmaf(dx - dx1, C.invA0, S.y[kResN0])
+	                   : fmaf(C.a[kResN0], dx, dx1 + S.y[kResN0]);
+	S.d[kResN0] = dx;
+	S.y[kResN0] = ci;
+	float np = resonate(S, C, kResNP, n0);
+	float x = fmaf(np - ci, C.caNP, ci);
+#pragma unroll
+	for (int r = kResCascade; r < kResParallel; ++r) x = resonate(S, C, r, x);
 	// ---- mix, gain, clamp with the Win32 macro NaN behaviour (NaN -> +32000), truncate (:207-208) ----
-	float s = (x + par) * L.dir[dOutputGain] * 4000.0f;
+	float s = (x + par) * C.og4000;
 	s = fminf(s, 32000.0f);  // fminf(NaN, 32000) == 32000
 	s = fmaxf(s, -32000.0f);
 	return (int)s;
 }
 
+// the two noise words of generated sample `gen` (Philox mode caches the 4-word block of samples 2b, 2b+1)
+struct NoiseSource {
+	Philox4 blk;
+	uint64_t blkIndex;
+	KLATT_HD void init() { blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0; blkIndex = ~0ull; }
+	KLATT_HD void draw(const NoiseConfig &noise, const StreamDesc &desc, uint64_t gen, uint32_t &wA, uint32_t &wF) {
+		if (noise.mode == kNoisePhilox) {
+			uint64_t b = gen >> 1;
+			if (b != blkIndex) { blk = noiseBlock(noise.seed, desc.streamId, b); blkIndex = b; }
+			bool odd = (gen & 1ull) != 0;
+			wA = odd ? blk.w[2] : blk.w[0];
+			wF = odd ? blk.w[3] : blk.w[1];
+		} else {  // replayed rand() values (31 bits): shift into word position
+			uint64_t d0 = 2 * gen - desc.replayBase;
+			wA = (d0 < desc.replayLen) ? ((uint32_t)desc.replay[d0] << 1) : 0u;
+			wF = (d0 + 1 < desc.replayLen) ? ((uint32_t)desc.replay[d0 + 1] << 1) : 0u;
+		}
+	}
+};
+
+template <int ROLE>
+KLATT_HD void loadDspState(DspState &S, const GenStateF32 &gs) {
+	using T = RoleTraits<ROLE>;
+#pragma unroll
+	for (int r = T::R0; r < T::R1; ++r) { S.y[r] = gs.y[r]; S.d[r] = gs.d[r]; }
+	if (T::hasC) {
+		S.aspLast = gs.aspLast; S.vibratoPos = gs.vibratoPos; S.vibInc = gs.vibInc;
+		S.pitchPos = gs.pitchPos; S.pitch = gs.pitch; S.pitchInc = gs.pitchInc;
+	}
+	if (T::hasP) S.fricLast = gs.fricLast;
+}
+template <int ROLE>
+KLATT_HD void storeDspState(GenStateF32 &gs, const DspState &S) {
+	using T = RoleTraits<ROLE>;
+#pragma unroll
+	for (int r = T::R0; r < T::R1; ++r) { gs.y[r] = S.y[r]; gs.d[r] = S.d[r]; }
+	if (T::hasC) {
+		gs.aspLast = S.aspLast; gs.vibratoPos = S.vibratoPos; gs.vibInc = S.vibInc;
+		gs.pitchPos = S.pitchPos; gs.pitch = S.pitch; gs.pitchInc = S.pitchInc;
+	}
+	if (T::hasP) gs.fricLast = S.fricLast;
+}
+
 // ---------------------------------------------------------------------------------------------------
-// renderStreamF32: advance one stream by up to sampleCount ticks.  Returns the number of samples produced.
-// `plans` (may be null) holds precomputed FadePlanF32 for requests [qBase, qBase+qCount) whose predecessor was
-// known at plan time; planValidFrom is the first absolute request index for which they may be used.
+// renderHoldF32: `ticks` PURE HOLD ticks of one stream (reference src/frame.cpp:76-79: only the pitch glides).
+// The caller guarantees (canHoldF32) that no frame-manager event falls inside: coefficients are built once.
+// `ticks` is a multiple of kGroupTicks.  Only the cascade side owns the frame-manager counters.
 // ---------------------------------------------------------------------------------------------------
-template <class Out, class Store>
-KLATT_HD uint32_t renderStreamF32(const StreamDesc &desc, int sampleRate, uint32_t sampleCount, Out &out, Store &cs,
-                                  const NoiseConfig &noise, int32_t *lastUserIndexOut, uint32_t *qHeadOut) {
+KLATT_HD bool canHoldF32(const StreamState &st, uint32_t ticks) {
+	const FrameMgrState &fm = st.fm;
+	return !fm.hasNew && !fm.curIsNull && !fm.purgePending && st.gen.f32.holdArmed &&
+	       (uint64_t)fm.counter + ticks <= (uint64_t)fm.oldM;
+}
+
+template <int ROLE, class Out, class Xchg>
+KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t ticks, Out &out, const NoiseConfig &noise,
+                            Xchg &xc) {
+	using T = RoleTraits<ROLE>;
+	StreamState *st = desc.state;
+	GenStateF32 &gs = st->gen.f32;
+	const double srInv = 1.0 / (double)sampleRate;
+	DspState S;
+	loadDspState<ROLE>(S, gs);
+	CoefF32 C;
+	{
+		float zre[kNumResonators], zim[kNumResonators], dir[kNumDirect];
+#pragma unroll
+		for (int r = T::R0; r < T::R1; ++r) { zre[r] = gs.zre[r]; zim[r] = gs.zim[r]; }
+#pragma unroll
+		for (int i = 0; i < kNumDirect; ++i)
+			if (roleUsesDirect<ROLE>(i)) dir[i] = gs.dir[i];
+		buildCoef<ROLE>(C, zre, zim, dir, gs.n0Inv != 0);
+	}
+	uint64_t gen = gs.samplesGenerated;
+	NoiseSource ns;
+	ns.init();
+	const bool evenPhilox = noise.mode == kNoisePhilox && (gen & 1ull) == 0;
+	for (uint32_t t = 0; t < ticks; t += kGroupTicks) {
+		if (T::hasC && !T::hasP) xc.sync();  // the parallel side has finished this group
+		if (!T::hasP || evenPhilox) {  // straight-line group: one Philox block per two ticks
+#pragma unroll
+			for (int k = 0; k < kGroupTicks; k += 2) {
+				Philox4 blk;
+				if (T::hasP) blk = noiseBlock(noise.seed, desc.streamId, (gen + k) >> 1);
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					uint32_t wA = 0;
+					float par = 0.0f;
+					if (T::hasP) {
+						wA = blk.w[2 * h];
+						par = parallelSide(S, C, blk.w[2 * h + 1]);
+						if (!T::hasC) xc.put(t + k + h, wA, par);
+					}
+					if (T::hasC) {
+						if (!T::hasP) xc.get(t + k + h, wA, par);
+						out.push(cascadeSide(S, C, wA, par, srInv));
+					}
+				}
+			}
+		} else {
+			for (int k = 0; k < kGroupTicks; ++k) {
+				uint32_t wA, wF;
+				ns.draw(noise, desc, gen + k, wA, wF);
+				float par = parallelSide(S, C, wF);
+				if (!T::hasC) xc.put(t + k, wA, par);
+				if (T::hasC) out.push(cascadeSide(S, C, wA, par, srInv));
+			}
+		}
+		gen += kGroupTicks;
+		if (T::hasP && !T::hasC) xc.sync();  // hand the group over
+	}
+	storeDspState<ROLE>(gs, S);
+	if (T::hasC) {
+		gs.samplesGenerated = gen;
+		st->fm.counter += ticks;
+		gs.callPos += ticks;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// renderGeneralF32: advance one stream by up to myTicks ticks through the full frame manager.
+// Returns the number of samples produced (< myTicks iff the queue drained).  loopTicks >= myTicks is the trip
+// count every thread of a cascade/parallel warp pair shares (hand-over barriers are warp-wide).
+// desc.plans (may be null, kRoleBoth only) holds precomputed FadePlanF32 for requests [qBase, qBase+qCount);
+// without it the plan is made inline at the pop tick from the frame manager's own frames (per-handle API, purge).
+// ---------------------------------------------------------------------------------------------------
+template <int ROLE, class Out, class Xchg>
+KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint32_t myTicks, uint32_t loopTicks, Out &out,
+                                   const NoiseConfig &noise, Xchg &xc, int32_t *lastUserIndexOut, uint32_t *qHeadOut) {
+	using T = RoleTraits<ROLE>;
 	StreamState *st = desc.state;
 	FrameMgrState &fm = st->fm;
 	GenStateF32 &gs = st->gen.f32;
 	const double srInv = 1.0 / (double)sampleRate;
+	const bool planned = desc.plans != nullptr;  // always true for the split roles
 
 	uint32_t counter = fm.counter, qHead = fm.qHead;
 	uint32_t oldM = fm.oldM, newM = fm.newM, newF = fm.newF;
 	int32_t lastUserIndex = fm.lastUserIndex;
 	bool hasNew = fm.hasNew, curIsNull = fm.curIsNull, oldIsNull = fm.oldIsNull, newIsNull = fm.newIsNull;
 	double oldInc = fm.oldInc, newInc = fm.newInc;
+	double pitchOld = gs.pitchOld, pitchNew = gs.pitchNew;
+	uint32_t nextEvent = gs.nextEvent;
+	bool holdArmed = gs.holdArmed != 0;
+	bool n0Inv = gs.n0Inv != 0;
 
-	LiveF32 L;
+	DspState S;
+	loadDspState<ROLE>(S, gs);
+	float zre[kNumResonators], zim[kNumResonators], wre[kNumResonators], wim[kNumResonators];
+	float dir0[kNumDirect], dstep[kNumDirect];
+	float kf = 0.0f, kfStep = 0.0f;
+	int64_t vibIncStep = 0;
 #pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) {
-		L.y[r] = gs.y[r]; L.d[r] = gs.d[r]; L.zre[r] = gs.zre[r]; L.zim[r] = gs.zim[r]; L.rho[r] = gs.rho[r];
-	}
+	for (int r = T::R0; r < T::R1; ++r) { zre[r] = gs.zre[r]; zim[r] = gs.zim[r]; wre[r] = 0.0f; wim[r] = 0.0f; }
 #pragma unroll
-	for (int i = 0; i < kNumDirect; ++i) L.dir[i] = gs.dir[i];
-	L.aspLast = gs.aspLast; L.fricLast = gs.fricLast; L.vibratoPos = gs.vibratoPos; L.vibInc = gs.vibInc; L.vibIncStep = 0;
-	L.pitchPos = gs.pitchPos; L.pitch = fm.curFrame[kVoicePitch]; L.pitchStep = gs.pitchStep;
-	L.n0Inv = gs.n0Inv != 0;
-	refreshA(L);
+	for (int i = 0; i < kNumDirect; ++i)
+		if (roleUsesDirect<ROLE>(i)) { dir0[i] = gs.dir[i]; dstep[i] = 0.0f; }
 	uint64_t gen = gs.samplesGenerated;
 
 	// purge prologue, src/frame.cpp:103-112 (the dropped requests were removed on the host).  fm.curFrame is kept
-	// current at every exit, so the snapshot is available here.
-	if (fm.purgePending) {
+	// current at every exit in inline mode, so the snapshot is available here; the working set simply stays where
+	// the interrupted fade left it.
+	if (ROLE == kRoleBoth && fm.purgePending) {
 		fm.purgePending = 0;
 		counter = oldM;
 		if (hasNew) {
@@ -351,163 +518,231 @@ KLATT_HD uint32_t renderStreamF32(const StreamDesc &desc, int sampleRate, uint32
 			for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.curFrame[i];
 			hasNew = false;
 		}
+		S.pitchInc = 0.0;
+		holdArmed = false;
+		nextEvent = oldM + 1;
 	}
-	const FadePlanF32 *plan = &gs.plan;
+	const FadePlanF32 *plan = nullptr;
 	if (hasNew) {
-		loadFadeSteps(L, *plan);
-		coarseLoadSteps(cs, *plan);
-		for (int i = 0; i < 3 * kNumResonators; ++i) cs.at(i) = gs.coarse[i];
+		plan = planned ? desc.plans + (qHead - 1 - desc.qBase) : &gs.plan;
+		if (counter >= 1 && counter < newF) {  // resuming in the middle of a fade: the increments are in force
+#pragma unroll
+			for (int r = T::R0; r < T::R1; ++r) { wre[r] = plan->wre[r]; wim[r] = plan->wim[r]; }
+#pragma unroll
+			for (int i = 0; i < kNumDirect; ++i)
+				if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dir0[i]; dstep[i] = plan->dirStep[i]; }
+			kf = (float)counter;
+			kfStep = 1.0f;
+			vibIncStep = plan->vibIncStep;
+		}
 	}
-	uint32_t coarseAt = hasNew ? gs.coarseAt : 0x80000000u;  // fade tick of the last coarse sync (0x80000000: none)
+	uint32_t coarseAt = hasNew ? gs.coarseAt : 0x80000000u;
 
-	Philox4 blk;
-	blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
-	uint64_t blkIndex = ~0ull;
-	const float kInvRandMax = 1.0f / 2147483647.0f;
+	NoiseSource ns;
+	ns.init();
 
 	uint32_t produced = 0;
-	for (; produced < sampleCount; ++produced) {
-		// ================= frame manager tick, src/frame.cpp:41-80 =================
-		counter++;
+	bool active = myTicks > 0;
+	for (uint32_t t = 0; t < loopTicks; ++t) {
+		if (T::hasC && !T::hasP && (t & (kGroupTicks - 1)) == 0) xc.sync();  // the parallel side has finished this group
+		if (active) {
+			// ================= frame manager, src/frame.cpp:41-80, entered only on event ticks =================
+			counter++;
+			if (counter >= nextEvent) {
+				if (hasNew) {
+					if (counter > newF) {  // :44-47 the fade is over: new becomes old; cur keeps its ratio-1 value
+						if (ROLE == kRoleBoth && !planned)
+							for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
+						oldM = newM; oldInc = newInc; oldIsNull = newIsNull;
+						hasNew = false;
+						S.pitchInc = 0.0;
+						nextEvent = counter + 1;  // next tick: first hold tick, or the next pop
+					} else if (counter == 1 && newF > 1) {  // :49-52 first fade tick: start from the (possibly rewritten) old frame
+#pragma unroll
+						for (int r = T::R0; r < T::R1; ++r) {
+							zre[r] = plan->z0re[r]; zim[r] = plan->z0im[r]; wre[r] = plan->wre[r]; wim[r] = plan->wim[r];
+						}
+#pragma unroll
+						for (int i = 0; i < kNumDirect; ++i)
+							if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dir0[i]; dstep[i] = plan->dirStep[i]; }
+						kf = 0.0f; kfStep = 1.0f;
+						if (T::hasC) {
+							S.vibInc = plan->vibInc0; vibIncStep = plan->vibIncStep;
+							S.pitch = pitchOld;
+							S.pitchInc = (pitchNew != pitchNew) ? 0.0 : (pitchNew - pitchOld) / (double)newF;
+							n0Inv = plan->n0InvFade != 0;
+						}
+						coarseAt = 0x80000000u;
+						nextEvent = newF;
+					} else {  // counter == newF, ratio == 1: land exactly on the planned end values
+#pragma unroll
+						for (int r = T::R0; r < T::R1; ++r) {
+							zre[r] = plan->zFre[r]; zim[r] = plan->zFim[r]; wre[r] = 0.0f; wim[r] = 0.0f;
+						}
+#pragma unroll
+						for (int i = 0; i < kNumDirect; ++i)
+							if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dirFinal[i]; dstep[i] = 0.0f; }
+						kf = 0.0f; kfStep = 0.0f;
+						S.pitch = (pitchNew != pitchNew) ? pitchOld : pitchOld + ((pitchNew - pitchOld) * 1.0);
+						S.pitchInc = 0.0;
+						if (T::hasC) {
+							S.vibInc = plan->vibIncFinal; vibIncStep = 0;
+							n0Inv = plan->n0InvFinal != 0;
+						}
+						nextEvent = newF + 1;
+					}
+				} else if (counter > oldM) {  // :54
+					uint32_t rel = qHead - desc.qBase;
+					if (rel < desc.qCount) {  // :55-72
+						curIsNull = false;
+						// the working set is where the previous request left it and stays frozen for this tick (cur is
+						// untouched on the pop tick, so this tick still renders with the stale values)
+						newM = desc.minDur[rel];
+						uint32_t fd = desc.fadeDur[rel];
+						newF = fd > 1u ? fd : 1u;  // src/speechPlayer.cpp:36
+						newIsNull = desc.isNull ? (desc.isNull[rel] != 0) : false;
+						int32_t ux = desc.userIndex ? desc.userIndex[rel] : -1;
+						qHead++;
+						hasNew = true;
+						pitchOld = S.pitch;  // old.frame.voicePitch follows the glide (:78)
+						if (ROLE == kRoleBoth && !planned) {
+							fm.oldFrame[kVoicePitch] = S.pitch;
+							for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
+						}
+						if (newIsNull) {  // :59-63
+							if (ROLE == kRoleBoth && !planned) {
+								for (int i = 0; i < kNumParams; ++i) fm.newFrame[i] = fm.oldFrame[i];
+								fm.newFrame[kPreFormantGain] = 0;
+							}
+							pitchNew = S.pitch;
+							newInc = 0;
+						} else {
+							const double *fr = desc.frames + (size_t)rel * kNumParams;
+							pitchNew = fr[kVoicePitch];
+							newInc = (fr[kEndVoicePitch] - fr[kVoicePitch]) / (double)newM;  // src/frame.cpp:98
+							if (ROLE == kRoleBoth && !planned)
+								for (int i = 0; i < kNumParams; ++i) fm.newFrame[i] = fr[i];
+							if (oldIsNull) {  // :64-67
+								pitchOld = pitchNew;
+								if (ROLE == kRoleBoth && !planned) {
+									for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
+									fm.oldFrame[kPreFormantGain] = 0;
+								}
+							}
+						}
+						if (ux != -1) lastUserIndex = ux;  // :69
+						counter = 0;                       // :70
+						pitchNew += (newInc * (double)newF);  // :71
+						if (planned) {
+							plan = desc.plans + rel;
+						} else if (ROLE == kRoleBoth) {  // plan the fade here (double precision, once per request)
+							fm.newFrame[kVoicePitch] = pitchNew;
+							fm.oldFrame[kVoicePitch] = pitchOld;
+							planFade(fm.oldFrame, fm.newFrame, newF, sampleRate, gs.plan);
+							plan = &gs.plan;
+						}
+						S.pitchInc = 0.0;
+						holdArmed = false;
+						nextEvent = 1;
+					} else {
+						curIsNull = true;  // :73-75
+					}
+				} else {  // :76-79 first hold tick: only the pitch glides from here on
+					S.pitchInc = oldInc;
+					holdArmed = true;
+					nextEvent = oldM + 1;
+				}
+				if (curIsNull) active = false;  // src/speechWaveGenerator.cpp:210
+			}
+		}
+		if (active) {
+			// ================= the straight-line per-tick update (all increments are zero outside fades) ===========
+			kf += kfStep;
+			stepPoles<ROLE>(zre, zim, wre, wim);
+			if (T::hasC) S.vibInc += vibIncStep;  // (the pitch advances inside cascadeSide)
+			if ((gen & (uint64_t)(kCoarseTicks - 1)) == 0 && kfStep != 0.0f) {
+				// drift control, on a grid of ABSOLUTE sample indices (identical for every chunking of the render, and
+				// the same loop iteration for every lane of a batch that started together)
+				if (counter - coarseAt == (uint32_t)kCoarseTicks) {
+#pragma unroll
+					for (int r = T::R0; r < T::R1; ++r) {
+						float zr = gs.zc[r], zi = gs.zc[kNumResonators + r], wr = plan->Wre[r], wi = plan->Wim[r];
+						float tr = fmaf(-zr, wr, wr);
+						tr = fmaf(zi, wi, tr);
+						float ti = fmaf(-zr, wi, wi);
+						ti = fmaf(-zi, wr, ti);
+						zre[r] = zr + tr;
+						zim[r] = zi + ti;
+					}
+				}
+#pragma unroll
+				for (int r = T::R0; r < T::R1; ++r) { gs.zc[r] = zre[r]; gs.zc[kNumResonators + r] = zim[r]; }
+				coarseAt = counter;
+			}
+			CoefF32 C;
+			{
+				float dir[kNumDirect];
+#pragma unroll
+				for (int i = 0; i < kNumDirect; ++i)
+					if (roleUsesDirect<ROLE>(i)) dir[i] = fmaf(kf, dstep[i], dir0[i]);
+				buildCoef<ROLE>(C, zre, zim, dir, n0Inv);
+			}
+			// ================= noise draws (two per generated sample) and the DSP =================
+			uint32_t wA = 0;
+			float par = 0.0f;
+			if (T::hasP) {
+				uint32_t wF;
+				ns.draw(noise, desc, gen, wA, wF);
+				par = parallelSide(S, C, wF);
+				if (!T::hasC) xc.put(t, wA, par);
+			}
+			gen++;
+			if (T::hasC) {
+				if (!T::hasP) xc.get(t, wA, par);
+				out.push(cascadeSide(S, C, wA, par, srInv));
+			}
+			produced++;
+			if (produced == myTicks) active = false;
+		}
+		if (T::hasP && !T::hasC && ((t & (kGroupTicks - 1)) == kGroupTicks - 1 || t + 1 == loopTicks)) xc.sync();  // hand over
+	}
+
+	// ---- store the stream back ----
+	if (ROLE == kRoleBoth && !planned) {  // keep fm.curFrame / fm.oldFrame meaningful for purge and for the next inline plan
 		if (hasNew) {
-			if (counter > newF) {  // :44-47 the fade is over: new becomes old; cur keeps its ratio-1 value
-				for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
-				oldM = newM; oldInc = newInc; oldIsNull = newIsNull;
-				hasNew = false;
-			} else {  // :49-52
-				if (counter == 1) {  // the fade starts from the (possibly rewritten) old frame, not from the stale cur
-					loadFadeStart(L, *plan);
-					L.pitch = fm.oldFrame[kVoicePitch];
-				}
-				stepFade(L, (float)counter);
-#ifdef KLATT_EXPERIMENT_EXACT_COEF
-				{
-					double ratio = (double)counter / (double)newF;
-					for (int r = 0; r < kNumResonators; ++r) {
-						double f0 = fm.oldFrame[resFreqParam(r)], f1 = fm.newFrame[resFreqParam(r)];
-						double b0 = fm.oldFrame[resBwParam(r)], b1 = fm.newFrame[resBwParam(r)];
-						poleTerms(f0 + (f1 - f0) * ratio, b0 + (b1 - b0) * ratio, srInv, L.zre[r], L.zim[r], L.rho[r]);
-					}
-					for (int i = 0; i < kNumDirect; ++i) {
-						double a = fm.oldFrame[directParam(i)], b = fm.newFrame[directParam(i)];
-						L.dir[i] = (float)(a + (b - a) * ratio);
-					}
-					refreshA(L);
-				}
-#endif
-				if (counter < newF && (gen & (uint64_t)(kCoarseTicks - 1)) == 0) {
-					// drift control, on a grid of ABSOLUTE sample indices (identical for every chunking of the
-					// render, and the same loop iteration for every lane of a batch that started together)
-					if (counter - coarseAt == (uint32_t)kCoarseTicks) coarseAdvance(cs, L);
-					else coarseCapture(cs, L);
-					coarseAt = counter;
-				}
-				if (counter == newF) {  // ratio == 1: land exactly on the planned end values
-					loadFadeFinal(L, *plan);
-					L.pitch = fm.oldFrame[kVoicePitch] + ((fm.newFrame[kVoicePitch] - fm.oldFrame[kVoicePitch]) * 1.0);
-					L.n0Inv = plan->n0InvFinal != 0;
-				} else {
-					L.n0Inv = plan->n0InvFade != 0;
+			if (counter >= 1) {
+				double ratio = (double)counter / (double)newF;
+				for (int i = 0; i < kNumParams; ++i) {
+					double o = fm.oldFrame[i], n = fm.newFrame[i];
+					fm.curFrame[i] = (n != n) ? o : o + ((n - o) * ratio);
 				}
 			}
-		} else if (counter > oldM) {  // :54
-			uint32_t rel = qHead - desc.qBase;
-			if (rel < desc.qCount) {  // :55-72
-				curIsNull = false;
-				// keep the snapshot invariants: cur == what the hold rendered with, old pitch follows the glide (:78)
-				fm.oldFrame[kVoicePitch] = L.pitch;
-				for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
-				newM = desc.minDur[rel];
-				uint32_t fd = desc.fadeDur[rel];
-				newF = fd > 1u ? fd : 1u;  // src/speechPlayer.cpp:36
-				newIsNull = desc.isNull ? (desc.isNull[rel] != 0) : false;
-				int32_t ux = desc.userIndex ? desc.userIndex[rel] : -1;
-				qHead++;
-				hasNew = true;
-				if (newIsNull) {  // :59-63
-					for (int i = 0; i < kNumParams; ++i) fm.newFrame[i] = fm.oldFrame[i];
-					fm.newFrame[kPreFormantGain] = 0;
-					fm.newFrame[kVoicePitch] = L.pitch;
-					newInc = 0;
-				} else {
-					const double *fr = desc.frames + (size_t)rel * kNumParams;
-					for (int i = 0; i < kNumParams; ++i) fm.newFrame[i] = fr[i];
-					newInc = (fr[kEndVoicePitch] - fr[kVoicePitch]) / (double)newM;  // src/frame.cpp:98
-					if (oldIsNull) {  // :64-67
-						for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
-						fm.oldFrame[kPreFormantGain] = 0;
-					}
-				}
-				if (ux != -1) lastUserIndex = ux;  // :69
-				counter = 0;                       // :70
-				fm.newFrame[kVoicePitch] += (newInc * (double)newF);  // :71
-				// plan the fade (double precision, once per request)
-				planFade(fm.oldFrame, fm.newFrame, newF, sampleRate, gs.plan);
-				plan = &gs.plan;
-				loadFadeSteps(L, *plan);
-				coarseLoadSteps(cs, *plan);
-				coarseAt = 0x80000000u;
-				double tgt = fm.newFrame[kVoicePitch], from = fm.oldFrame[kVoicePitch];
-				L.pitchStep = (tgt != tgt) ? 0.0 : (tgt - from) / (double)newF;
-				// NOTE: this tick still renders with the stale working set (cur is untouched on the pop tick)
-			} else {
-				curIsNull = true;  // :73-75
-			}
-		} else {  // :76-79 hold: only the pitch glides
-			L.pitch += oldInc;
-		}
-		if (curIsNull) break;  // src/speechWaveGenerator.cpp:210
-
-		// ================= noise draws (two per generated sample) =================
-		uint32_t drawA, drawF;
-		if (noise.mode == kNoisePhilox) {
-			uint64_t b = gen >> 1;
-			if (b != blkIndex) { blk = noiseBlock(noise.seed, desc.streamId, b); blkIndex = b; }
-			bool odd = (gen & 1ull) != 0;
-			drawA = (odd ? blk.w[2] : blk.w[0]) >> 1;
-			drawF = (odd ? blk.w[3] : blk.w[1]) >> 1;
 		} else {
-			uint64_t d0 = 2 * gen - desc.replayBase;
-			drawA = (d0 < desc.replayLen) ? (uint32_t)desc.replay[d0] : 0u;
-			drawF = (d0 + 1 < desc.replayLen) ? (uint32_t)desc.replay[d0 + 1] : 0u;
+			for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
+			fm.oldFrame[kVoicePitch] = S.pitch;
 		}
-		gen++;
-#ifdef KLATT_HOSTSIM_DEBUG
-		if (g_dbgPhase) g_dbgPhase[gen - 1] = L.pitchPos;
-#endif
-		out.push(dspTick(L, (float)drawA * kInvRandMax, (float)drawF * kInvRandMax, srInv));
+		fm.curFrame[kVoicePitch] = S.pitch;
 	}
-
-	// ---- store the stream back; keep fm.curFrame / fm.oldFrame meaningful for purge and for the next plan ----
-	if (hasNew) {
-		if (counter >= 1) {
-			double ratio = (double)counter / (double)newF;
-			for (int i = 0; i < kNumParams; ++i) {
-				double o = fm.oldFrame[i], n = fm.newFrame[i];
-				fm.curFrame[i] = (n != n) ? o : o + ((n - o) * ratio);
-			}
-		}
-	} else {
-		for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
-		fm.oldFrame[kVoicePitch] = L.pitch;
-	}
-	fm.curFrame[kVoicePitch] = L.pitch;
-	fm.counter = counter; fm.qHead = qHead; fm.oldM = oldM; fm.newM = newM; fm.newF = newF;
-	fm.lastUserIndex = lastUserIndex;
-	fm.hasNew = hasNew; fm.curIsNull = curIsNull; fm.oldIsNull = oldIsNull; fm.newIsNull = newIsNull;
-	fm.oldInc = oldInc; fm.newInc = newInc;
+	storeDspState<ROLE>(gs, S);
 #pragma unroll
-	for (int r = 0; r < kNumResonators; ++r) {
-		gs.y[r] = L.y[r]; gs.d[r] = L.d[r]; gs.zre[r] = L.zre[r]; gs.zim[r] = L.zim[r]; gs.rho[r] = L.rho[r];
-	}
+	for (int r = T::R0; r < T::R1; ++r) { gs.zre[r] = zre[r]; gs.zim[r] = zim[r]; }
 #pragma unroll
-	for (int i = 0; i < kNumDirect; ++i) gs.dir[i] = L.dir[i];
-	gs.aspLast = L.aspLast; gs.fricLast = L.fricLast; gs.vibratoPos = L.vibratoPos; gs.vibInc = L.vibInc;
-	gs.pitchPos = L.pitchPos; gs.pitchStep = L.pitchStep; gs.n0Inv = L.n0Inv ? 1u : 0u;
-	gs.samplesGenerated = gen;
-	gs.coarseAt = coarseAt;
-	if (hasNew)
-		for (int i = 0; i < 3 * kNumResonators; ++i) gs.coarse[i] = cs.at(i);
+	for (int i = 0; i < kNumDirect; ++i)
+		if (roleUsesDirect<ROLE>(i) && (T::hasC || i != dPreFormantGain)) gs.dir[i] = fmaf(kf, dstep[i], dir0[i]);
+	if (T::hasC) {
+		fm.counter = counter; fm.qHead = qHead; fm.oldM = oldM; fm.newM = newM; fm.newF = newF;
+		fm.lastUserIndex = lastUserIndex;
+		fm.hasNew = hasNew; fm.curIsNull = curIsNull; fm.oldIsNull = oldIsNull; fm.newIsNull = newIsNull;
+		fm.oldInc = oldInc; fm.newInc = newInc;
+		gs.pitchOld = pitchOld; gs.pitchNew = pitchNew;
+		gs.n0Inv = n0Inv ? 1u : 0u;
+		gs.holdArmed = holdArmed ? 1u : 0u;
+		gs.nextEvent = nextEvent;
+		gs.samplesGenerated = gen;
+		gs.coarseAt = coarseAt;
+		gs.callPos += produced;
+		if (produced < myTicks) gs.callDrained = 1;
+	}
 	*lastUserIndexOut = lastUserIndex;
 	*qHeadOut = qHead;
 	return produced;

@@ -18,12 +18,15 @@ def lib():
         vp = ctypes.c_void_p
         L.hostsim_render_f32.restype = ctypes.c_int
         L.hostsim_render_f32.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint64,
-                                         ctypes.c_uint, vp, ctypes.c_uint, vp]
+                                         ctypes.c_uint, vp, ctypes.c_uint, vp, ctypes.c_int, ctypes.c_uint, ctypes.c_uint, vp]
         _lib = L
     return _lib
 
 
-def render_f32(sr, frames, min_dur, fade_dur, is_null=None, user_index=None, max_samples=None, seed=0, stream=0, chunk=0):
+def render_f32(sr, frames, min_dur, fade_dur, is_null=None, user_index=None, max_samples=None, seed=0, stream=0, chunk=0,
+               planned=False, hold_ticks=0, gen_ticks=0, return_hold=False):
+    """planned=False: inline plans, one general pass per `chunk` ticks.  planned=True: precomputed plans and rounds of
+    hold_ticks pure-hold / gen_ticks general chunks, as the batch engine schedules them."""
     frames = np.ascontiguousarray(frames, dtype=np.float64).reshape(-1, 47)
     m = np.ascontiguousarray(min_dur, dtype=np.uint32)
     f = np.ascontiguousarray(fade_dur, dtype=np.uint32)
@@ -36,8 +39,12 @@ def render_f32(sr, frames, min_dur, fade_dur, is_null=None, user_index=None, max
     out = np.zeros(max_samples, dtype=np.int16)
     ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
     li = ctypes.c_int32(0)
+    hold = ctypes.c_uint32(0)
     n = lib().hostsim_render_f32(sr, ptr(frames), ptr(m), ptr(f), ptr(ux), ptr(nul), len(m), seed, stream, max_samples,
-                                 ptr(out), chunk, ctypes.byref(li))
+                                 ptr(out), chunk, ctypes.byref(li), int(bool(planned)), hold_ticks, gen_ticks,
+                                 ctypes.byref(hold))
+    if return_hold:
+        return out[:n], li.value, hold.value
     return out[:n], li.value
 
 
