@@ -200,6 +200,7 @@ def main():
                             d_uix.data_ptr(), d_null.data_ptr(), stream)
 
     kev = []  # (before, after) CUDA events around the render kernel alone, on the launching stream
+    enqueue_s = []  # host time spent enqueueing one synthesize call (asynchronous launches)
 
     def step(timed=False):
         # a step = hand the (HBM-resident) queues to fresh players, then plan + render them: SetFrames resets every
@@ -209,8 +210,10 @@ def main():
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
+        t_host = time.perf_counter()
         batch.synthesize_device(count, d_out.data_ptr(), stride, d_written.data_ptr(), stream)
         if timed:
+            enqueue_s.append(time.perf_counter() - t_host)
             b.record()
             kev.append((a, b))
 
@@ -299,7 +302,8 @@ def main():
                        "fade_fraction_phi": round(phi, 4), "flops_per_sample_W": round(flops_per_sample, 1),
                        "noise": "philox4x32-10", "precision": args.precision,
                        "l2": "no flush needed: each step writes %.1f GB of int16 (>> 126 MB L2)" % (S * stride * 2 / 1e9),
-                       "real_time_factor_per_gpu": samples_per_s_gpu / sr},
+                       "real_time_factor_per_gpu": samples_per_s_gpu / sr,
+                       "host_enqueue_ms_per_step": round(1e3 * sum(enqueue_s) / max(len(enqueue_s), 1), 2)},
             "roofline": {"bound": "fp32_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None,
                          "peak_source": "FFMA loop measured on this GPU in this run (MEASURED_PEAKS.json has no FP32 entry)"

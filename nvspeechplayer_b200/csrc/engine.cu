@@ -34,8 +34,9 @@ cudaError_t launchKlattF32(const StreamDesc *descs, uint32_t numStreams, int sam
 cudaError_t launchKlattF32Rounds(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                                  uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride,
                                  uint32_t *samplesWritten, StreamResult *results, NoiseConfig noise, uint32_t *listHold,
-                                 uint32_t *listGen, uint32_t *counters, cudaStream_t stream, cudaStream_t side,
-                                 cudaEvent_t fork, cudaEvent_t join, unsigned long long *launchCounter);
+                                 uint32_t *listGen, uint32_t *counters, int16_t *scratchRow, cudaStream_t stream, uint32_t numGroups,
+                                 cudaStream_t *lanes, cudaEvent_t evStart, cudaEvent_t *evFork, cudaEvent_t *evJoin,
+                                 unsigned long long *launchCounter);
 cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_t totalRequests, const double *frames,
                             const uint32_t *fadeDur, const uint8_t *isNull, int sampleRate, FadePlanF32 *plans,
                             cudaStream_t stream);
@@ -153,16 +154,14 @@ __global__ void build_descs_kernel(StreamDesc *descs, StreamState *states, const
 
 // Scratch and second stream for round-based FP32 rendering (klatt_f32.cu "rounds"); owned by a batch or a pipe.
 struct RoundsCtx {
-	DevBuf listHold, listGen, counters;
-	cudaStream_t side = nullptr;
-	cudaEvent_t fork = nullptr, join = nullptr;
-	uint32_t holdTicks = 256, genTicks = 128, minStreams = 2048;
+	static constexpr uint32_t kMaxGroups = 8;
+	DevBuf listHold, listGen, counters, scratchRow;
+	cudaStream_t lanes[2 * kMaxGroups] = {};
+	cudaEvent_t evStart = nullptr, evFork[kMaxGroups] = {}, evJoin[kMaxGroups] = {};
+	uint32_t holdTicks = 256, genTicks = 128, minStreams = 2048, groups = 4;
 	bool ok = false;
 	bool init() {
 		if (ok) return true;
-		if (!cudaOk(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
-		if (!cudaOk(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "cudaEventCreate")) return false;
-		if (!cudaOk(cudaEventCreateWithFlags(&join, cudaEventDisableTiming), "cudaEventCreate")) return false;
 		auto envU = [](const char *name, uint32_t dflt) {
 			const char *e = getenv(name);
 			return (e && *e) ? (uint32_t)strtoul(e, nullptr, 0) : dflt;
@@ -172,13 +171,29 @@ struct RoundsCtx {
 		genTicks = std::max<uint32_t>(envU("NVSP_GEN_TICKS", 128) & ~63u, 64);
 		holdTicks = std::max<uint32_t>(envU("NVSP_HOLD_TICKS", 256) & ~63u, 64);
 		minStreams = envU("NVSP_ROUNDS_MIN_STREAMS", 2048);
+		groups = std::min<uint32_t>(std::max<uint32_t>(envU("NVSP_GROUPS", 4), 1), kMaxGroups);
+		if (!cudaOk(cudaEventCreateWithFlags(&evStart, cudaEventDisableTiming), "cudaEventCreate")) return false;
+		for (uint32_t g = 0; g < groups; ++g) {
+			if (!cudaOk(cudaStreamCreateWithFlags(&lanes[2 * g], cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+			if (!cudaOk(cudaStreamCreateWithFlags(&lanes[2 * g + 1], cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+			if (!cudaOk(cudaEventCreateWithFlags(&evFork[g], cudaEventDisableTiming), "cudaEventCreate")) return false;
+			if (!cudaOk(cudaEventCreateWithFlags(&evJoin[g], cudaEventDisableTiming), "cudaEventCreate")) return false;
+		}
 		ok = true;
 		return true;
 	}
 	void destroy() {
-		listHold.release(); listGen.release(); counters.release();
-		if (!ok) return;
-		cudaEventDestroy(fork); cudaEventDestroy(join); cudaStreamDestroy(side);
+		listHold.release(); listGen.release(); counters.release(); scratchRow.release();
+		if (evStart) cudaEventDestroy(evStart);
+		for (uint32_t g = 0; g < kMaxGroups; ++g) {
+			if (evFork[g]) cudaEventDestroy(evFork[g]);
+			if (evJoin[g]) cudaEventDestroy(evJoin[g]);
+			if (lanes[2 * g]) cudaStreamDestroy(lanes[2 * g]);
+			if (lanes[2 * g + 1]) cudaStreamDestroy(lanes[2 * g + 1]);
+			evFork[g] = evJoin[g] = nullptr;
+			lanes[2 * g] = lanes[2 * g + 1] = nullptr;
+		}
+		evStart = nullptr;
 		ok = false;
 	}
 };
@@ -195,11 +210,13 @@ static cudaError_t launchRender(int precision, const StreamDesc *descs, uint32_t
 	if (rc && planned && rc->init() && n >= rc->minStreams && sampleCount > rc->genTicks) {
 		const uint32_t rounds = (sampleCount + rc->genTicks - 1) / rc->genTicks;
 		if (!rc->listHold.reserve(sizeof(uint32_t) * (size_t)n) || !rc->listGen.reserve(sizeof(uint32_t) * (size_t)n) ||
-		    !rc->counters.reserve(sizeof(uint32_t) * 2 * (size_t)rounds))
+		    !rc->counters.reserve(sizeof(uint32_t) * 2 * (size_t)rounds * rc->groups) ||
+		    !rc->scratchRow.reserve(sizeof(int16_t) * (size_t)rc->holdTicks))
 			return cudaErrorMemoryAllocation;
 		return launchKlattF32Rounds(descs, n, sampleRate, sampleCount, rc->holdTicks, rc->genTicks, out, rowStride, written,
 		                            results, noise, rc->listHold.as<uint32_t>(), rc->listGen.as<uint32_t>(),
-		                            rc->counters.as<uint32_t>(), stream, rc->side, rc->fork, rc->join, launchCounter);
+		                            rc->counters.as<uint32_t>(), rc->scratchRow.as<int16_t>(), stream, rc->groups, rc->lanes, rc->evStart, rc->evFork,
+		                            rc->evJoin, launchCounter);
 	}
 	if (launchCounter) ++*launchCounter;
 	return launchKlattF32(descs, n, sampleRate, sampleCount, out, rowStride, written, results, noise, stream);

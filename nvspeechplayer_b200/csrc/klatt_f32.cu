@@ -66,12 +66,12 @@ klatt_plan_kernel(const int64_t *__restrict__ offsets, uint32_t numStreams, cons
 // rounds
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-klatt_partition_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, uint32_t sampleCount, uint32_t holdTicks,
-                       uint32_t genTicks, int firstRound, uint32_t *__restrict__ listHold, uint32_t *__restrict__ listGen,
-                       uint32_t *__restrict__ counters) {
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+klatt_partition_kernel(const StreamDesc *__restrict__ descs, uint32_t firstStream, uint32_t numStreams, uint32_t sampleCount,
+                       uint32_t holdTicks, uint32_t genTicks, int firstRound, uint32_t *__restrict__ listHold,
+                       uint32_t *__restrict__ listGen, uint32_t *__restrict__ counters) {
+	const uint32_t s = firstStream + blockIdx.x * blockDim.x + threadIdx.x;
 	int cls = 0;  // 0: nothing to do, 1: hold chunk, 2: general chunk
-	if (s < numStreams) {
+	if (s < firstStream + numStreams) {
 		StreamState *st = descs[s].state;
 		GenStateF32 &gs = st->gen.f32;
 		if (firstRound) { gs.callPos = 0; gs.callDrained = 0; }
@@ -98,17 +98,19 @@ klatt_partition_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams
 // ---- the two sides of a stream in different warps of one block ------------------------------------------------
 // block = 4 warps: warps 0,1 run the cascade side of streams [64b, 64b+32) and [64b+32, 64b+64) of the list,
 // warps 2,3 the parallel side of the same streams.  Warp w and warp w+2 share one named barrier and a
-// double-buffered shared-memory hand-over of (aspiration noise word, parallel-bank output) x 8 ticks x 32 lanes.
+// double-buffered shared-memory hand-over of (aspiration noise word, parallel-bank output, vibrato) x 8 ticks x 32 lanes.
 struct XchgSmem {
-	uint2 *base;  // this lane's column of the pair's [2 buffers][8 ticks][32 lanes]
-	int barId;
-	__device__ __forceinline__ void put(uint32_t t, uint32_t wA, float par) {
-		base[(((t >> 3) & 1u) * kGroupTicks + (t & (kGroupTicks - 1))) * 32] = make_uint2(wA, __float_as_uint(par));
+	uint32_t base;  // shared-space address of this lane's column of the pair's [2 buffers][8 ticks][32 lanes] x 16 bytes
+	uint32_t barId;
+	__device__ __forceinline__ void put(uint32_t t, uint32_t wA, float par, float vib) {
+		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(base + (t & 15u) * 512u), "r"(wA), "r"(__float_as_uint(par)),
+		             "r"(__float_as_uint(vib)) : "memory");
 	}
-	__device__ __forceinline__ void get(uint32_t t, uint32_t &wA, float &par) const {
-		uint2 v = base[(((t >> 3) & 1u) * kGroupTicks + (t & (kGroupTicks - 1))) * 32];
-		wA = v.x;
-		par = __uint_as_float(v.y);
+	__device__ __forceinline__ void get(uint32_t t, uint32_t &wA, float &par, float &vib) const {
+		uint32_t p, v, pad;
+		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wA), "=r"(p), "=r"(v), "=r"(pad) : "r"(base + (t & 15u) * 512u) : "memory");
+		par = __uint_as_float(p);
+		vib = __uint_as_float(v);
 	}
 	__device__ __forceinline__ void sync() { asm volatile("bar.sync %0, 64;" ::"r"(barId) : "memory"); }
 };
@@ -120,23 +122,24 @@ constexpr int kPairBlock = 128;        // threads
 constexpr int kPairStreams = 64;       // streams per block
 
 // descs[numStreams] is a dummy stream (fresh state, empty queue) that the idle lanes of a partially filled warp run
-__global__ void __launch_bounds__(kPairBlock)
+__global__ void __launch_bounds__(kPairBlock, 6)
 klatt_f32_hold_kernel(const StreamDesc *__restrict__ descs, const uint32_t *__restrict__ list,
                       const uint32_t *__restrict__ counters, uint32_t numStreams, int sampleRate, uint32_t holdTicks,
-                      int16_t *__restrict__ out, size_t rowStride, NoiseConfig noise) {
-	__shared__ uint2 xbuf[2][2 * kGroupTicks * 32];
+                      int16_t *__restrict__ out, size_t rowStride, int16_t *__restrict__ scratchRow, NoiseConfig noise) {
+	__shared__ uint4 xbuf[2][2 * kGroupTicks * 32];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, pair = warp & 1u;
 	const uint32_t count = counters[0];
 	if (blockIdx.x * kPairStreams + pair * 32 >= count) return;  // the whole warp pair is idle
 	const uint32_t slot = blockIdx.x * kPairStreams + pair * 32 + lane;
 	const bool valid = slot < count;
 	const uint32_t s = valid ? list[slot] : numStreams;
-	const StreamDesc desc = descs[s];
-	XchgSmem xc{&xbuf[pair][lane], (int)(1 + pair)};
+	const StreamDesc &desc = descs[s];
+	XchgSmem xc{(uint32_t)__cvta_generic_to_shared(&xbuf[pair][lane]), 1u + pair};
 	if (warp < 2) {
-		int16_t *row = out + (size_t)(valid ? s : 0) * rowStride + desc.state->gen.f32.callPos;
+		// idle lanes render the dummy stream into a scratch row of holdTicks samples
+		int16_t *row = valid ? out + (size_t)s * rowStride + desc.state->gen.f32.callPos : scratchRow;
 		OutWriter ow;
-		ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0), valid);
+		ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0));
 		renderHoldF32<kRoleCascade>(desc, sampleRate, holdTicks, ow, noise, xc);
 	} else {
 		NullOut no;
@@ -145,32 +148,32 @@ klatt_f32_hold_kernel(const StreamDesc *__restrict__ descs, const uint32_t *__re
 }
 
 // a round of the general path: thread pair = stream list[slot], at most genTicks ticks from where the stream stands
-__global__ void __launch_bounds__(kPairBlock)
+__global__ void __launch_bounds__(kPairBlock, 4)
 klatt_f32_general_pair_kernel(const StreamDesc *__restrict__ descs, const uint32_t *__restrict__ list,
                               const uint32_t *__restrict__ counters, uint32_t numStreams, int sampleRate,
                               uint32_t sampleCount, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,
                               NoiseConfig noise) {
-	__shared__ uint2 xbuf[2][2 * kGroupTicks * 32];
+	__shared__ uint4 xbuf[2][2 * kGroupTicks * 32];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, pair = warp & 1u;
 	const uint32_t count = counters[1];
 	if (blockIdx.x * kPairStreams + pair * 32 >= count) return;
 	const uint32_t slot = blockIdx.x * kPairStreams + pair * 32 + lane;
 	const bool valid = slot < count;
 	const uint32_t s = valid ? list[slot] : numStreams;
-	const StreamDesc desc = descs[s];
+	const StreamDesc &desc = descs[s];
 	const uint32_t pos = desc.state->gen.f32.callPos;
 	uint32_t ticks = 0;
 	if (valid) {
 		ticks = sampleCount - pos;
 		if (ticks > genTicks) ticks = genTicks;
 	}
-	XchgSmem xc{&xbuf[pair][lane], (int)(1 + pair)};
+	XchgSmem xc{(uint32_t)__cvta_generic_to_shared(&xbuf[pair][lane]), 1u + pair};
 	int32_t lastUserIndex;
 	uint32_t qHead;
 	if (warp < 2) {
 		int16_t *row = out + (size_t)(valid ? s : 0) * rowStride;
 		OutWriter ow;
-		ow.init(row + pos, ((reinterpret_cast<uintptr_t>(row + pos) & 15u) == 0), valid);
+		ow.init(row + pos, ((reinterpret_cast<uintptr_t>(row + pos) & 15u) == 0));  // idle lanes have no ticks: they never store
 		const uint32_t produced = renderGeneralF32<kRoleCascade>(desc, sampleRate, ticks, genTicks, ow, noise, xc, &lastUserIndex, &qHead);
 		ow.flush();
 		if (produced < ticks) zeroRow(row, pos + produced, sampleCount);  // drained: the rest of the row is silence
@@ -246,35 +249,53 @@ cudaError_t launchKlattF32(const StreamDesc *descs, uint32_t numStreams, int sam
 	return cudaGetLastError();
 }
 
-// One call as rounds of (partition, hold || general).  `side` is a second stream of the same device on which the
-// general kernel of each round runs next to the hold kernel; `fork` / `join` are two events owned by the caller.
-// scratch: listHold[numStreams], listGen[numStreams], counters[2 * rounds] (zeroed here).  descs holds numStreams + 1
-// entries: the last one is the dummy stream idle lanes run.
+// One call as rounds of (partition, hold || general).  The streams are split into `numGroups` contiguous groups that
+// run their rounds independently, each on its own pair of CUDA streams, so that the tail of one group's round (few
+// blocks left, SMs draining) overlaps the other groups' kernels.  lanes[2*g] / lanes[2*g+1] are the two streams of
+// group g, evFork / evJoin[g] events owned by the caller.  Everything is ordered after what `stream` holds at the
+// time of the call, and `stream` waits for all groups before the results kernel.
+// scratch: listHold[numStreams], listGen[numStreams], counters[2 * rounds * numGroups] (zeroed here).  descs holds
+// numStreams + 1 entries: the last one is the dummy stream idle lanes run.
 cudaError_t launchKlattF32Rounds(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                                  uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride,
                                  uint32_t *samplesWritten, StreamResult *results, NoiseConfig noise, uint32_t *listHold,
-                                 uint32_t *listGen, uint32_t *counters, cudaStream_t stream, cudaStream_t side,
-                                 cudaEvent_t fork, cudaEvent_t join, unsigned long long *launchCounter) {
+                                 uint32_t *listGen, uint32_t *counters, int16_t *scratchRow, cudaStream_t stream, uint32_t numGroups,
+                                 cudaStream_t *lanes, cudaEvent_t evStart, cudaEvent_t *evFork, cudaEvent_t *evJoin,
+                                 unsigned long long *launchCounter) {
 	if (numStreams == 0 || sampleCount == 0) return cudaSuccess;
 	const uint32_t rounds = (sampleCount + genTicks - 1) / genTicks;
-	cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 2 * (size_t)rounds, stream);
+	cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 2 * (size_t)rounds * numGroups, stream);
 	if (e != cudaSuccess) return e;
-	const dim3 gridP((numStreams + 255) / 256), gridR((numStreams + kPairStreams - 1) / kPairStreams);
+	if ((e = cudaEventRecord(evStart, stream)) != cudaSuccess) return e;
+	const uint32_t perGroup = ((numStreams + numGroups - 1) / numGroups + kPairStreams - 1) / kPairStreams * kPairStreams;
+	for (uint32_t g = 0; g < numGroups; ++g)
+		if ((e = cudaStreamWaitEvent(lanes[2 * g], evStart, 0)) != cudaSuccess) return e;
 	for (uint32_t r = 0; r < rounds; ++r) {
-		uint32_t *cnt = counters + 2 * (size_t)r;
-		klatt_partition_kernel<<<gridP, 256, 0, stream>>>(descs, numStreams, sampleCount, holdTicks, genTicks, r == 0, listHold,
-		                                                  listGen, cnt);
-		if ((e = cudaEventRecord(fork, stream)) != cudaSuccess) return e;
-		if ((e = cudaStreamWaitEvent(side, fork, 0)) != cudaSuccess) return e;
-		klatt_f32_general_pair_kernel<<<gridR, kPairBlock, 0, side>>>(descs, listGen, cnt, numStreams, sampleRate, sampleCount,
-		                                                              genTicks, out, rowStride, noise);
-		klatt_f32_hold_kernel<<<gridR, kPairBlock, 0, stream>>>(descs, listHold, cnt, numStreams, sampleRate, holdTicks, out,
-		                                                        rowStride, noise);
-		if ((e = cudaEventRecord(join, side)) != cudaSuccess) return e;
-		if ((e = cudaStreamWaitEvent(stream, join, 0)) != cudaSuccess) return e;
-		if (launchCounter) *launchCounter += 3;
+		for (uint32_t g = 0; g < numGroups; ++g) {
+			const uint32_t first = g * perGroup;
+			if (first >= numStreams) break;
+			const uint32_t n = numStreams - first < perGroup ? numStreams - first : perGroup;
+			cudaStream_t main = lanes[2 * g], side = lanes[2 * g + 1];
+			uint32_t *cnt = counters + 2 * ((size_t)g * rounds + r);
+			const dim3 gridP((n + 255) / 256), gridR((n + kPairStreams - 1) / kPairStreams);
+			klatt_partition_kernel<<<gridP, 256, 0, main>>>(descs, first, n, sampleCount, holdTicks, genTicks, r == 0,
+			                                                listHold + first, listGen + first, cnt);
+			if ((e = cudaEventRecord(evFork[g], main)) != cudaSuccess) return e;
+			if ((e = cudaStreamWaitEvent(side, evFork[g], 0)) != cudaSuccess) return e;
+			klatt_f32_general_pair_kernel<<<gridR, kPairBlock, 0, side>>>(descs, listGen + first, cnt, numStreams, sampleRate,
+			                                                              sampleCount, genTicks, out, rowStride, noise);
+			klatt_f32_hold_kernel<<<gridR, kPairBlock, 0, main>>>(descs, listHold + first, cnt, numStreams, sampleRate, holdTicks,
+			                                                      out, rowStride, scratchRow, noise);
+			if ((e = cudaEventRecord(evJoin[g], side)) != cudaSuccess) return e;
+			if ((e = cudaStreamWaitEvent(main, evJoin[g], 0)) != cudaSuccess) return e;
+			if (launchCounter) *launchCounter += 3;
+		}
 	}
-	klatt_finalize_kernel<<<gridP, 256, 0, stream>>>(descs, numStreams, samplesWritten, results);
+	for (uint32_t g = 0; g < numGroups; ++g) {
+		if ((e = cudaEventRecord(evJoin[g], lanes[2 * g])) != cudaSuccess) return e;
+		if ((e = cudaStreamWaitEvent(stream, evJoin[g], 0)) != cudaSuccess) return e;
+	}
+	klatt_finalize_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, numStreams, samplesWritten, results);
 	if (launchCounter) *launchCounter += 1;
 	return cudaGetLastError();
 }

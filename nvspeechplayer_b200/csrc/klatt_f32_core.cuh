@@ -150,11 +150,13 @@ KLATT_HD void plannedFrames(const double *prevReal, bool prevIsNull, const doubl
 // ---------------------------------------------------------------------------------------------------
 // Roles.  A stream's tick splits into two halves that only meet in the final mix (reference
 // src/speechWaveGenerator.cpp:203-207):
-//   cascade side  : vibrato, glottal phase, aspiration, rN0, rNP, r6..r1  (resonators 0..7)  -> x, and the sample
-//   parallel side : noise draws, frication, the six parallel sections      (resonators 8..13) -> par
+//   cascade side  : glottal phase, aspiration, rN0, rNP, r6..r1            (resonators 0..7)  -> x, and the sample
+//   parallel side : noise draws, frication, the six parallel sections      (resonators 8..13) -> par,
+//                   and the vibrato oscillator (it feeds the cascade side's phase increment, but depends on nothing
+//                   the cascade side computes, and moving it here balances the two halves)
 // kRoleBoth runs both in one thread (per-handle API, host numerics build).  The batch kernels give each side its
 // own thread in a different warp of the block (half the registers per thread, twice the warps per SM); the
-// parallel side hands (aspiration noise word, par) over through shared memory 8 ticks at a time.  Every role
+// parallel side hands (aspiration noise word, par, vibrato) over through shared memory 8 ticks at a time.  Every role
 // executes the same operations on the same values, so all of them produce the same bits.
 // ---------------------------------------------------------------------------------------------------
 enum Role : int { kRoleBoth = 0, kRoleCascade = 1, kRoleParallel = 2 };
@@ -168,11 +170,12 @@ template <int ROLE> struct RoleTraits {
 };
 // direct params each side reads
 KLATT_HD constexpr bool directOfCascade(int i) {
-	return i == dVibratoPitchOffset || i == dVoiceTurbulenceAmplitude || i == dGlottalOpenQuotient || i == dVoiceAmplitude ||
+	return i == dVoiceTurbulenceAmplitude || i == dGlottalOpenQuotient || i == dVoiceAmplitude ||
 	       i == dAspirationAmplitude || i == dCaNP || i == dPreFormantGain || i == dOutputGain;
 }
 KLATT_HD constexpr bool directOfParallel(int i) {
-	return i == dFricationAmplitude || (i >= dPa1 && i <= dPa6) || i == dParallelBypass || i == dPreFormantGain;
+	return i == dVibratoPitchOffset || i == dFricationAmplitude || (i >= dPa1 && i <= dPa6) || i == dParallelBypass ||
+	       i == dPreFormantGain;
 }
 template <int ROLE> KLATT_HD constexpr bool roleUsesDirect(int i) {
 	return (RoleTraits<ROLE>::hasC && directOfCascade(i)) || (RoleTraits<ROLE>::hasP && directOfParallel(i));
@@ -181,9 +184,9 @@ template <int ROLE> KLATT_HD constexpr bool roleUsesDirect(int i) {
 // hand-over between the two sides when they share a thread: plain members
 struct XchgSelf {
 	uint32_t wA_;
-	float par_;
-	KLATT_HD void put(uint32_t, uint32_t wA, float par) { wA_ = wA; par_ = par; }
-	KLATT_HD void get(uint32_t, uint32_t &wA, float &par) const { wA = wA_; par = par_; }
+	float par_, vib_;
+	KLATT_HD void put(uint32_t, uint32_t wA, float par, float vib) { wA_ = wA; par_ = par; vib_ = vib; }
+	KLATT_HD void get(uint32_t, uint32_t &wA, float &par, float &vib) const { wA = wA_; par = par_; vib = vib_; }
 	KLATT_HD void sync() {}
 };
 
@@ -209,7 +212,9 @@ struct CoefF32 {  // what a tick only reads: a pure function of (zeta, direct pa
 
 KLATT_HD float fastRcp(float x) {
 #ifdef __CUDA_ARCH__
-	return __fdividef(1.0f, x);
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.RCP
+	return r;
 #else
 	return 1.0f / x;
 #endif
@@ -229,7 +234,7 @@ KLATT_HD void buildCoef(CoefF32 &C, const float *zre, const float *zim, const fl
 	C.halfGain = dir[dPreFormantGain] * 0.5f;
 	if (T::hasC) {
 		C.invA0 = fastRcp(C.a[kResN0]);
-		C.vpo = dir[dVibratoPitchOffset]; C.vta = dir[dVoiceTurbulenceAmplitude]; C.goq = dir[dGlottalOpenQuotient];
+		C.vta = dir[dVoiceTurbulenceAmplitude]; C.goq = dir[dGlottalOpenQuotient];
 		C.va = dir[dVoiceAmplitude]; C.aa = dir[dAspirationAmplitude]; C.caNP = dir[dCaNP];
 		C.og4000 = dir[dOutputGain] * 4000.0f;
 		C.n0Inv = n0Inv;
@@ -238,6 +243,7 @@ KLATT_HD void buildCoef(CoefF32 &C, const float *zre, const float *zim, const fl
 #pragma unroll
 		for (int k = 0; k < 6; ++k) C.pa[k] = dir[dPa1 + k];
 		C.bypass = dir[dParallelBypass];
+		C.vpo = dir[dVibratoPitchOffset];
 		C.fricGain = ((0.3f * kDrawScale) * dir[dFricationAmplitude]) * C.halfGain;
 	}
 }
@@ -268,12 +274,18 @@ KLATT_HD float resonate(DspState &S, const CoefF32 &C, int r, float x) {
 	return S.y[r];
 }
 
-KLATT_HD float sinTurns(float t) {  // sin(2*pi*t), |t| <= 0.5
-#ifdef __CUDA_ARCH__
-	return sinpif(2.0f * t);
-#else
-	return sinf(6.283185307179586f * t);
-#endif
+// sin(2*pi*t) for |t| <= 0.5: fold to |t| <= 0.25, then t*(c0 + u*Q(u)), u = t^2 (odd degree-11 least-squares fit on
+// Chebyshev nodes; the fit is good to 1.3e-11, the FP32 evaluation to ~1 ulp).  Same code on host and device, so the
+// CPU numerics tests see the kernel's vibrato bit for bit.
+KLATT_HD float sinTurns(float t) {
+	if (t > 0.25f) t = 0.5f - t;
+	if (t < -0.25f) t = -0.5f - t;
+	const float u = t * t;
+	float q = fmaf(u, -14.3368558883667f, 41.999961853027344f);
+	q = fmaf(u, q, -76.70366668701172f);
+	q = fmaf(u, q, 81.60520935058594f);
+	q = fmaf(u, q, -41.34170150756836f);
+	return fmaf(t * u, q, t * 6.2831854820251465f);
 }
 
 KLATT_HD float bitsToFloat(uint32_t u) {
@@ -308,14 +320,18 @@ KLATT_HD float parallelSide(DspState &S, const CoefF32 &C, uint32_t wF) {
 	return fmaf(pin - par, C.bypass, par);
 }
 
-// cascade side (reference src/speechWaveGenerator.cpp:203-204, :72-86, :147-158) and the final mix (:207-208)
-KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, double srInv) {
-	// ---- vibrato (:73) and glottal phase (:74, :55) ----
+// vibrato oscillator (reference src/speechWaveGenerator.cpp:73): the relative pitch offset of this tick
+KLATT_HD float vibratoSide(DspState &S, const CoefF32 &C) {
 	S.vibratoPos += (uint64_t)S.vibInc;
 	// cycles in [-0.5, 0.5), rounded to nearest: a truncated phase is a systematic pitch error while a slow vibrato
 	// sits inside one quantisation step
 	float vph = (float)(int32_t)(uint32_t)(S.vibratoPos >> 32) * 2.3283064365386963e-10f;
-	float vib = (sinTurns(vph) * 0.06f) * C.vpo;
+	return (sinTurns(vph) * 0.06f) * C.vpo;
+}
+
+// cascade side (reference src/speechWaveGenerator.cpp:203-204, :72-86, :147-158) and the final mix (:207-208)
+KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, float vib, double srInv) {
+	// ---- glottal phase (:74, :55) ----
 	S.pitch += S.pitchInc;
 	double base = S.pitch * srInv;
 	double pos = fracRef(S.pitchPos + fma(base, (double)vib, base));
@@ -353,10 +369,10 @@ struct NoiseSource {
 	Philox4 blk;
 	uint64_t blkIndex;
 	KLATT_HD void init() { blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0; blkIndex = ~0ull; }
-	KLATT_HD void draw(const NoiseConfig &noise, const StreamDesc &desc, uint64_t gen, uint32_t &wA, uint32_t &wF) {
+	KLATT_HD void draw(const NoiseConfig &noise, const StreamDesc &desc, uint64_t streamId, uint64_t gen, uint32_t &wA, uint32_t &wF) {
 		if (noise.mode == kNoisePhilox) {
 			uint64_t b = gen >> 1;
-			if (b != blkIndex) { blk = noiseBlock(noise.seed, desc.streamId, b); blkIndex = b; }
+			if (b != blkIndex) { blk = noiseBlock(noise.seed, streamId, b); blkIndex = b; }
 			bool odd = (gen & 1ull) != 0;
 			wA = odd ? blk.w[2] : blk.w[0];
 			wF = odd ? blk.w[3] : blk.w[1];
@@ -374,10 +390,10 @@ KLATT_HD void loadDspState(DspState &S, const GenStateF32 &gs) {
 #pragma unroll
 	for (int r = T::R0; r < T::R1; ++r) { S.y[r] = gs.y[r]; S.d[r] = gs.d[r]; }
 	if (T::hasC) {
-		S.aspLast = gs.aspLast; S.vibratoPos = gs.vibratoPos; S.vibInc = gs.vibInc;
+		S.aspLast = gs.aspLast;
 		S.pitchPos = gs.pitchPos; S.pitch = gs.pitch; S.pitchInc = gs.pitchInc;
 	}
-	if (T::hasP) S.fricLast = gs.fricLast;
+	if (T::hasP) { S.fricLast = gs.fricLast; S.vibratoPos = gs.vibratoPos; S.vibInc = gs.vibInc; }
 }
 template <int ROLE>
 KLATT_HD void storeDspState(GenStateF32 &gs, const DspState &S) {
@@ -385,10 +401,10 @@ KLATT_HD void storeDspState(GenStateF32 &gs, const DspState &S) {
 #pragma unroll
 	for (int r = T::R0; r < T::R1; ++r) { gs.y[r] = S.y[r]; gs.d[r] = S.d[r]; }
 	if (T::hasC) {
-		gs.aspLast = S.aspLast; gs.vibratoPos = S.vibratoPos; gs.vibInc = S.vibInc;
+		gs.aspLast = S.aspLast;
 		gs.pitchPos = S.pitchPos; gs.pitch = S.pitch; gs.pitchInc = S.pitchInc;
 	}
-	if (T::hasP) gs.fricLast = S.fricLast;
+	if (T::hasP) { gs.fricLast = S.fricLast; gs.vibratoPos = S.vibratoPos; gs.vibInc = S.vibInc; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -422,6 +438,7 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 		buildCoef<ROLE>(C, zre, zim, dir, gs.n0Inv != 0);
 	}
 	uint64_t gen = gs.samplesGenerated;
+	const uint64_t streamId = desc.streamId;
 	NoiseSource ns;
 	ns.init();
 	const bool evenPhilox = noise.mode == kNoisePhilox && (gen & 1ull) == 0;
@@ -431,29 +448,31 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 #pragma unroll
 			for (int k = 0; k < kGroupTicks; k += 2) {
 				Philox4 blk;
-				if (T::hasP) blk = noiseBlock(noise.seed, desc.streamId, (gen + k) >> 1);
+				if (T::hasP) blk = noiseBlock(noise.seed, streamId, (gen + k) >> 1);
 #pragma unroll
 				for (int h = 0; h < 2; ++h) {
 					uint32_t wA = 0;
-					float par = 0.0f;
+					float par = 0.0f, vib = 0.0f;
 					if (T::hasP) {
 						wA = blk.w[2 * h];
 						par = parallelSide(S, C, blk.w[2 * h + 1]);
-						if (!T::hasC) xc.put(t + k + h, wA, par);
+						vib = vibratoSide(S, C);
+						if (!T::hasC) xc.put(t + k + h, wA, par, vib);
 					}
 					if (T::hasC) {
-						if (!T::hasP) xc.get(t + k + h, wA, par);
-						out.push(cascadeSide(S, C, wA, par, srInv));
+						if (!T::hasP) xc.get(t + k + h, wA, par, vib);
+						out.push(cascadeSide(S, C, wA, par, vib, srInv));
 					}
 				}
 			}
 		} else {
 			for (int k = 0; k < kGroupTicks; ++k) {
 				uint32_t wA, wF;
-				ns.draw(noise, desc, gen + k, wA, wF);
+				ns.draw(noise, desc, streamId, gen + k, wA, wF);
 				float par = parallelSide(S, C, wF);
-				if (!T::hasC) xc.put(t + k, wA, par);
-				if (T::hasC) out.push(cascadeSide(S, C, wA, par, srInv));
+				float vib = vibratoSide(S, C);
+				if (!T::hasC) xc.put(t + k, wA, par, vib);
+				if (T::hasC) out.push(cascadeSide(S, C, wA, par, vib, srInv));
 			}
 		}
 		gen += kGroupTicks;
@@ -488,8 +507,8 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 	uint32_t oldM = fm.oldM, newM = fm.newM, newF = fm.newF;
 	int32_t lastUserIndex = fm.lastUserIndex;
 	bool hasNew = fm.hasNew, curIsNull = fm.curIsNull, oldIsNull = fm.oldIsNull, newIsNull = fm.newIsNull;
-	double oldInc = fm.oldInc, newInc = fm.newInc;
-	double pitchOld = gs.pitchOld, pitchNew = gs.pitchNew;
+	// (fm.oldInc / fm.newInc / gs.pitchOld / gs.pitchNew are only touched on event ticks, by the cascade side: they stay
+	// in memory instead of occupying eight registers)
 	uint32_t nextEvent = gs.nextEvent;
 	bool holdArmed = gs.holdArmed != 0;
 	bool n0Inv = gs.n0Inv != 0;
@@ -506,6 +525,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 	for (int i = 0; i < kNumDirect; ++i)
 		if (roleUsesDirect<ROLE>(i)) { dir0[i] = gs.dir[i]; dstep[i] = 0.0f; }
 	uint64_t gen = gs.samplesGenerated;
+	const uint64_t streamId = desc.streamId;
 
 	// purge prologue, src/frame.cpp:103-112 (the dropped requests were removed on the host).  fm.curFrame is kept
 	// current at every exit in inline mode, so the snapshot is available here; the working set simply stays where
@@ -543,8 +563,9 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 
 	uint32_t produced = 0;
 	bool active = myTicks > 0;
-	for (uint32_t t = 0; t < loopTicks; ++t) {
-		if (T::hasC && !T::hasP && (t & (kGroupTicks - 1)) == 0) xc.sync();  // the parallel side has finished this group
+	for (uint32_t tg = 0; tg < loopTicks; tg += kGroupTicks) {
+	if (T::hasC && !T::hasP) xc.sync();  // the parallel side has finished this group
+	for (uint32_t t = tg; t < tg + kGroupTicks && t < loopTicks; ++t) {
 		if (active) {
 			// ================= frame manager, src/frame.cpp:41-80, entered only on event ticks =================
 			counter++;
@@ -553,7 +574,8 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 					if (counter > newF) {  // :44-47 the fade is over: new becomes old; cur keeps its ratio-1 value
 						if (ROLE == kRoleBoth && !planned)
 							for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
-						oldM = newM; oldInc = newInc; oldIsNull = newIsNull;
+						oldM = newM; oldIsNull = newIsNull;
+						if (T::hasC) fm.oldInc = fm.newInc;
 						hasNew = false;
 						S.pitchInc = 0.0;
 						nextEvent = counter + 1;  // next tick: first hold tick, or the next pop
@@ -566,8 +588,9 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						for (int i = 0; i < kNumDirect; ++i)
 							if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dir0[i]; dstep[i] = plan->dirStep[i]; }
 						kf = 0.0f; kfStep = 1.0f;
+						if (T::hasP) { S.vibInc = plan->vibInc0; vibIncStep = plan->vibIncStep; }
 						if (T::hasC) {
-							S.vibInc = plan->vibInc0; vibIncStep = plan->vibIncStep;
+							const double pitchOld = gs.pitchOld, pitchNew = gs.pitchNew;
 							S.pitch = pitchOld;
 							S.pitchInc = (pitchNew != pitchNew) ? 0.0 : (pitchNew - pitchOld) / (double)newF;
 							n0Inv = plan->n0InvFade != 0;
@@ -583,12 +606,13 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						for (int i = 0; i < kNumDirect; ++i)
 							if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dirFinal[i]; dstep[i] = 0.0f; }
 						kf = 0.0f; kfStep = 0.0f;
-						S.pitch = (pitchNew != pitchNew) ? pitchOld : pitchOld + ((pitchNew - pitchOld) * 1.0);
-						S.pitchInc = 0.0;
 						if (T::hasC) {
-							S.vibInc = plan->vibIncFinal; vibIncStep = 0;
+							const double pitchOld = gs.pitchOld, pitchNew = gs.pitchNew;
+							S.pitch = (pitchNew != pitchNew) ? pitchOld : pitchOld + ((pitchNew - pitchOld) * 1.0);
+							S.pitchInc = 0.0;
 							n0Inv = plan->n0InvFinal != 0;
 						}
+						if (T::hasP) { S.vibInc = plan->vibIncFinal; vibIncStep = 0; }
 						nextEvent = newF + 1;
 					}
 				} else if (counter > oldM) {  // :54
@@ -604,7 +628,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						int32_t ux = desc.userIndex ? desc.userIndex[rel] : -1;
 						qHead++;
 						hasNew = true;
-						pitchOld = S.pitch;  // old.frame.voicePitch follows the glide (:78)
+						double pitchOld = S.pitch, pitchNew, newInc;  // old.frame.voicePitch follows the glide (:78)
 						if (ROLE == kRoleBoth && !planned) {
 							fm.oldFrame[kVoicePitch] = S.pitch;
 							for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
@@ -633,6 +657,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						if (ux != -1) lastUserIndex = ux;  // :69
 						counter = 0;                       // :70
 						pitchNew += (newInc * (double)newF);  // :71
+						if (T::hasC) { gs.pitchOld = pitchOld; gs.pitchNew = pitchNew; fm.newInc = newInc; }
 						if (planned) {
 							plan = desc.plans + rel;
 						} else if (ROLE == kRoleBoth) {  // plan the fade here (double precision, once per request)
@@ -648,7 +673,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						curIsNull = true;  // :73-75
 					}
 				} else {  // :76-79 first hold tick: only the pitch glides from here on
-					S.pitchInc = oldInc;
+					if (T::hasC) S.pitchInc = fm.oldInc;
 					holdArmed = true;
 					nextEvent = oldM + 1;
 				}
@@ -659,7 +684,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 			// ================= the straight-line per-tick update (all increments are zero outside fades) ===========
 			kf += kfStep;
 			stepPoles<ROLE>(zre, zim, wre, wim);
-			if (T::hasC) S.vibInc += vibIncStep;  // (the pitch advances inside cascadeSide)
+			if (T::hasP) S.vibInc += vibIncStep;
 			if ((gen & (uint64_t)(kCoarseTicks - 1)) == 0 && kfStep != 0.0f) {
 				// drift control, on a grid of ABSOLUTE sample indices (identical for every chunking of the render, and
 				// the same loop iteration for every lane of a batch that started together)
@@ -689,22 +714,24 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 			}
 			// ================= noise draws (two per generated sample) and the DSP =================
 			uint32_t wA = 0;
-			float par = 0.0f;
+			float par = 0.0f, vib = 0.0f;
 			if (T::hasP) {
 				uint32_t wF;
-				ns.draw(noise, desc, gen, wA, wF);
+				ns.draw(noise, desc, streamId, gen, wA, wF);
 				par = parallelSide(S, C, wF);
-				if (!T::hasC) xc.put(t, wA, par);
+				vib = vibratoSide(S, C);
+				if (!T::hasC) xc.put(t, wA, par, vib);
 			}
 			gen++;
 			if (T::hasC) {
-				if (!T::hasP) xc.get(t, wA, par);
-				out.push(cascadeSide(S, C, wA, par, srInv));
+				if (!T::hasP) xc.get(t, wA, par, vib);
+				out.push(cascadeSide(S, C, wA, par, vib, srInv));
 			}
 			produced++;
 			if (produced == myTicks) active = false;
 		}
-		if (T::hasP && !T::hasC && ((t & (kGroupTicks - 1)) == kGroupTicks - 1 || t + 1 == loopTicks)) xc.sync();  // hand over
+	}
+	if (T::hasP && !T::hasC) xc.sync();  // hand the group over
 	}
 
 	// ---- store the stream back ----
@@ -733,8 +760,6 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 		fm.counter = counter; fm.qHead = qHead; fm.oldM = oldM; fm.newM = newM; fm.newF = newF;
 		fm.lastUserIndex = lastUserIndex;
 		fm.hasNew = hasNew; fm.curIsNull = curIsNull; fm.oldIsNull = oldIsNull; fm.newIsNull = newIsNull;
-		fm.oldInc = oldInc; fm.newInc = newInc;
-		gs.pitchOld = pitchOld; gs.pitchNew = pitchNew;
 		gs.n0Inv = n0Inv ? 1u : 0u;
 		gs.holdArmed = holdArmed ? 1u : 0u;
 		gs.nextEvent = nextEvent;

@@ -13,10 +13,9 @@ struct OutWriter {
 	uint32_t w0, w1, w2, w3;
 	uint32_t count;    // samples pushed so far
 	bool vec;          // 16-byte stores allowed (row is 16-byte aligned)
-	bool enabled;      // false: count but never store (lanes of a partially filled warp)
 
-	__device__ __forceinline__ void init(int16_t *rowPtr, bool vecOk, bool on = true) {
-		row = rowPtr; w0 = w1 = w2 = w3 = 0; count = 0; vec = vecOk; enabled = on;
+	__device__ __forceinline__ void init(int16_t *rowPtr, bool vecOk) {
+		row = rowPtr; w0 = w1 = w2 = w3 = 0; count = 0; vec = vecOk;
 	}
 	__device__ __forceinline__ void push(int s) {
 		// shift the 128-bit window right by one sample and insert the new one at the top
@@ -25,7 +24,7 @@ struct OutWriter {
 		w2 = __funnelshift_r(w2, w3, 16);
 		w3 = (w3 >> 16) | ((uint32_t)s << 16);
 		++count;
-		if ((count & 7u) == 0 && enabled) {
+		if ((count & 7u) == 0) {
 			int16_t *p = row + (count - 8);
 			if (vec) {
 				*reinterpret_cast<uint4 *>(p) = make_uint4(w0, w1, w2, w3);
@@ -37,7 +36,7 @@ struct OutWriter {
 	// write the 1..7 samples of an incomplete last group
 	__device__ __forceinline__ void flush() {
 		uint32_t rem = count & 7u;
-		if (rem == 0 || !enabled) return;
+		if (rem == 0) return;
 		// the window holds the last 8 pushes; the rem newest sit at the top: align them to the bottom
 		for (uint32_t i = rem; i < 8; ++i) {
 			w0 = __funnelshift_r(w0, w1, 16);

@@ -131,3 +131,39 @@ def test_philox_noise_statistics():
     for a in range(7):
         for c in range(a + 1, 7):
             assert abs(np.corrcoef(x[a], x[c])[0, 1]) < 0.02
+
+
+def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
+    """The batch engine's round-based execution (phase-sorted hold / general chunks, the two sides of a stream in
+    paired warps, several stream groups in flight) renders the same bits as the one-thread-per-stream kernel,
+    including streams that drain mid-call, partially filled warps and calls that end inside a chunk."""
+    sr, n = 22050, 203
+    streams = [workloads.random_stream(500 + s, 0.35 if s % 7 == 3 else 1.0, sr) for s in range(n)]
+    fb = workloads._concat(sr, streams, np.arange(500, 500 + n, dtype=np.uint64))
+    count = int(1.0 * sr)
+    res = {}
+    for mode, min_streams in (("single", "100000000"), ("rounds", "1")):
+        monkeypatch.setenv("NVSP_ROUNDS_MIN_STREAMS", min_streams)
+        monkeypatch.setenv("NVSP_GROUPS", "3")
+        b = player.Batch(sr, n, precision=player.PRECISION_FP32, seed=77, stream_ids=fb.stream_ids)
+        b.set_frames_host(fb)
+        parts, written = [], np.zeros(n, dtype=np.int64)
+        for c in (9000, 777, count - 9777):
+            o, w = b.synthesize_host(c)
+            parts.append(o)
+            written += w
+        res[mode] = (np.concatenate(parts, axis=1), written, b.last_indices(), b.launch_stats()[0])
+        b.close()
+    assert res["rounds"][3] > res["single"][3] + 50, "the rounds path did not run"
+    np.testing.assert_array_equal(res["single"][1], res["rounds"][1])
+    np.testing.assert_array_equal(res["single"][2], res["rounds"][2])
+    np.testing.assert_array_equal(res["single"][0], res["rounds"][0])
+    expect = np.minimum(fb.timeline_samples(), count)
+    np.testing.assert_array_equal(res["rounds"][1], expect)
+    # and both are the reference's audio
+    s = 3
+    fr, m, f, nul, ux = fb.stream(s)
+    want = port.render(sr, fr, m, f, nul, ux, max_samples=count, noise=("philox", 77, int(fb.stream_ids[s])))
+    got = res["rounds"][0][s][:len(want)]
+    parity.assert_f32_parity(got, want, "drained stream")
+    assert not res["rounds"][0][s][len(want):].any()
