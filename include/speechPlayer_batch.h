@@ -36,6 +36,8 @@ int speechPlayer_batchReset(speechPlayer_batch_t *batch, void *cudaStream);
 /* Replace the frame queues of all streams.  Stream s owns requests [offsets[s], offsets[s+1]) of the flat
  * arrays, in queue order (the batch equivalent of calling speechPlayer_queueFrame that many times on a fresh
  * player; fadeDuration 0 counts as 1).  userIndex / isNull may be NULL.
+ * Setting new queues also puts every stream back into the freshly initialised state, and (FP32) makes the next
+ * synthesize call re-plan every fade (klatt_plan_kernel) before it renders.
  *   ...Host:   all pointers are HOST memory; contents are copied to the device (async on cudaStream when the
  *              memory is pinned) before the call returns control of them.
  *   ...Device: all pointers are DEVICE memory that must stay valid and unchanged until the next
@@ -71,6 +73,23 @@ int speechPlayer_batchGetLastIndices(speechPlayer_batch_t *batch, int *lastIndex
 /* Counters of the launches issued so far by this batch: kernels launched, ticks requested (streams x sampleCount). */
 int speechPlayer_batchGetLaunchStats(speechPlayer_batch_t *batch, unsigned long long *kernelLaunches,
                                      unsigned long long *ticksRequested);
+
+/* Long-utterance path: ONE pre-queued stream rendered with parallelism in TIME (nvspeechplayer_b200/csrc/klatt_long.cu):
+ * the stream is cut into chunks of chunkTicks ticks (0 = default 1024) that are rendered concurrently; the glottal
+ * phase each chunk starts from comes from a scan of per-chunk phase advances, the state each two-pole section starts
+ * from comes from a parallel scan (warp shuffles) over the per-chunk 2x2 affine maps of that section.  FP32
+ * arithmetic, Philox noise keyed (seed, streamId); same audio as a fresh FP32 player fed the same queue, within the
+ * FP32 tolerance (not bit for bit: the scan re-associates).
+ *   frames / minFrameDuration / fadeDuration / isNull : HOST arrays, the stream's queueFrame calls in order
+ *   out          : int16 [maxSamples], HOST memory, or DEVICE memory when outOnDevice != 0
+ *   renderMs     : (optional) device time from the first to the last kernel of the call, in milliseconds
+ * Returns the number of samples written = min(maxSamples, sum max(M+1, F+2)), or -1 on error. */
+long long speechPlayer_synthesizeLong(int sampleRate, const speechPlayer_frame_t *frames,
+                                      const unsigned int *minFrameDuration, const unsigned int *fadeDuration,
+                                      const unsigned char *isNull, unsigned int numFrames, uint64_t seed,
+                                      uint64_t streamId, unsigned int chunkTicks, sample *out,
+                                      unsigned long long maxSamples, int outOnDevice, double *renderMs,
+                                      unsigned long long *kernelLaunches);
 
 /* Pure host helper (no device needed): samples a fully pre-queued stream yields,
  * sum_j max(M_j+1, max(F_j,1)+2)  -- the occupancy law of the reference frame manager (src/frame.cpp:41-80). */

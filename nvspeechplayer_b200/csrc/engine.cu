@@ -40,6 +40,27 @@ cudaError_t launchKlattF32Rounds(const StreamDesc *descs, uint32_t numStreams, i
 cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_t totalRequests, const double *frames,
                             const uint32_t *fadeDur, const uint8_t *isNull, int sampleRate, FadePlanF32 *plans,
                             cudaStream_t stream);
+struct LongStream {  // klatt_long.cu
+	const double *frames;
+	const uint32_t *minDur, *fadeDur;
+	const uint8_t *isNull;
+	const FadePlanF32 *plans;
+	uint32_t nReq;
+	int sampleRate;
+	uint64_t seed, streamId;
+	uint64_t *start;
+	int32_t *prevReal;
+	double *pitchPop;
+	double *pitchOld, *pitchNew, *pitchInc;
+	uint64_t *vibPosStart;
+};
+struct Affine {
+	float p00, p01, p10, p11, zy, zd;
+};
+cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream);
+cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, double *advance,
+                                  double *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
+                                  float2 *startState, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream);
 }  // namespace klatt
 
 using namespace klatt;
@@ -158,7 +179,7 @@ struct RoundsCtx {
 	DevBuf listHold, listGen, counters, scratchRow;
 	cudaStream_t lanes[2 * kMaxGroups] = {};
 	cudaEvent_t evStart = nullptr, evFork[kMaxGroups] = {}, evJoin[kMaxGroups] = {};
-	uint32_t holdTicks = 256, genTicks = 128, minStreams = 2048, groups = 4;
+	uint32_t holdTicks = 512, genTicks = 256, minStreams = 2048, groups = 4;
 	bool ok = false;
 	bool init() {
 		if (ok) return true;
@@ -168,8 +189,8 @@ struct RoundsCtx {
 		};
 		// chunk lengths are multiples of 64: the coarse pole re-basing and the Philox block cadence stay warp-uniform,
 		// and every chunk starts on a 16-byte boundary of its output row
-		genTicks = std::max<uint32_t>(envU("NVSP_GEN_TICKS", 128) & ~63u, 64);
-		holdTicks = std::max<uint32_t>(envU("NVSP_HOLD_TICKS", 256) & ~63u, 64);
+		genTicks = std::max<uint32_t>(envU("NVSP_GEN_TICKS", 256) & ~63u, 64);
+		holdTicks = std::max<uint32_t>(envU("NVSP_HOLD_TICKS", 512) & ~63u, 64);
 		minStreams = envU("NVSP_ROUNDS_MIN_STREAMS", 2048);
 		groups = std::min<uint32_t>(std::max<uint32_t>(envU("NVSP_GROUPS", 4), 1), kMaxGroups);
 		if (!cudaOk(cudaEventCreateWithFlags(&evStart, cudaEventDisableTiming), "cudaEventCreate")) return false;
@@ -932,3 +953,102 @@ int speechPlayer_batchGetLaunchStats(speechPlayer_batch_t *b, unsigned long long
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: long-utterance path (klatt_long.cu)
+// ------------------------------------------------------------------------------------------------
+extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPlayer_frame_t *frames,
+                                                 const unsigned int *minFrameDuration, const unsigned int *fadeDuration,
+                                                 const unsigned char *isNull, unsigned int numFrames, uint64_t seed,
+                                                 uint64_t streamId, unsigned int chunkTicks, sample *out,
+                                                 unsigned long long maxSamples, int outOnDevice, double *renderMs,
+                                                 unsigned long long *kernelLaunches) {
+	g_lastError.clear();
+	if (sampleRate <= 0) return fail("sampleRate must be positive");
+	if (numFrames && (!minFrameDuration || !fadeDuration)) return fail("durations missing");
+	if (numFrames == 0) return 0;
+	int dev = pickDevice();
+	if (dev < 0) return fail("no usable CUDA device (this library has no CPU fallback)");
+	DeviceGuard g(dev);
+	if (chunkTicks == 0) {
+		const char *e = getenv("NVSP_LONG_CHUNK");
+		chunkTicks = (e && *e) ? (unsigned)strtoul(e, nullptr, 0) : 1024u;
+	}
+	chunkTicks = std::max(chunkTicks, 64u);
+	const size_t n = numFrames;
+	DevBuf dFrames, dMin, dFade, dNull, dOff, dPlans, dStart, dPrev, dPitch, dVib;
+	struct Cleanup {
+		std::vector<DevBuf *> bufs;
+		cudaEvent_t e0 = nullptr, e1 = nullptr;
+		~Cleanup() {
+			for (DevBuf *b : bufs) b->release();
+			if (e0) cudaEventDestroy(e0);
+			if (e1) cudaEventDestroy(e1);
+		}
+	} cleanup;
+	cleanup.bufs = {&dFrames, &dMin, &dFade, &dNull, &dOff, &dPlans, &dStart, &dPrev, &dPitch, &dVib};
+	if (!dFrames.reserve(n * sizeof(speechPlayer_frame_t)) || !dMin.reserve(n * 4) || !dFade.reserve(n * 4) || !dNull.reserve(n) ||
+	    !dOff.reserve(16) || !dPlans.reserve(n * sizeof(FadePlanF32)) || !dStart.reserve((n + 1) * 8) || !dPrev.reserve(n * 4) ||
+	    !dPitch.reserve(n * 8 * 4) || !dVib.reserve(n * 8))
+		return -1;
+	cudaStream_t stream = nullptr;
+	if (frames) CU(cudaMemcpyAsync(dFrames.p, frames, n * sizeof(speechPlayer_frame_t), cudaMemcpyHostToDevice, stream));
+	else CU(cudaMemsetAsync(dFrames.p, 0, n * sizeof(speechPlayer_frame_t), stream));
+	CU(cudaMemcpyAsync(dMin.p, minFrameDuration, n * 4, cudaMemcpyHostToDevice, stream));
+	CU(cudaMemcpyAsync(dFade.p, fadeDuration, n * 4, cudaMemcpyHostToDevice, stream));
+	std::vector<unsigned char> allNull;
+	if (!frames) { allNull.assign(n, 1); isNull = allNull.data(); }
+	if (isNull) CU(cudaMemcpyAsync(dNull.p, isNull, n, cudaMemcpyHostToDevice, stream));
+	const int64_t offsets[2] = {0, (int64_t)n};
+	CU(cudaMemcpyAsync(dOff.p, offsets, sizeof offsets, cudaMemcpyHostToDevice, stream));
+	CU(cudaEventCreate(&cleanup.e0));
+	CU(cudaEventCreate(&cleanup.e1));
+	CU(cudaEventRecord(cleanup.e0, stream));
+	CU(launchKlattPlan(dOff.as<int64_t>(), 1, n, dFrames.as<double>(), dFade.as<uint32_t>(), isNull ? dNull.as<uint8_t>() : nullptr,
+	                   sampleRate, dPlans.as<FadePlanF32>(), stream));
+	LongStream L;
+	L.frames = dFrames.as<double>(); L.minDur = dMin.as<uint32_t>(); L.fadeDur = dFade.as<uint32_t>();
+	L.isNull = isNull ? dNull.as<uint8_t>() : nullptr;
+	L.plans = dPlans.as<FadePlanF32>(); L.nReq = numFrames; L.sampleRate = sampleRate; L.seed = seed; L.streamId = streamId;
+	L.start = dStart.as<uint64_t>(); L.prevReal = dPrev.as<int32_t>();
+	L.pitchPop = dPitch.as<double>(); L.pitchOld = L.pitchPop + n; L.pitchNew = L.pitchOld + n; L.pitchInc = L.pitchNew + n;
+	L.vibPosStart = dVib.as<uint64_t>();
+	CU(launchKlattLongTimeline(L, stream));
+	uint64_t total = 0;
+	CU(cudaMemcpyAsync(&total, L.start + n, 8, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	uint64_t ticks = std::min<uint64_t>(total, maxSamples);
+	unsigned long long launches = 2;
+	if (ticks) {
+		const uint64_t numChunks = (ticks + chunkTicks - 1) / chunkTicks;
+		if (numChunks > 0x7fffffffull) return fail("stream too long for one call");
+		const size_t pad = ticks + 64;
+		DevBuf sig, maps, st, ph, pcm;
+		cleanup.bufs.insert(cleanup.bufs.end(), {&sig, &maps, &st, &ph, &pcm});
+		if (!sig.reserve(5 * pad * sizeof(float)) || !maps.reserve(numChunks * 6 * sizeof(Affine)) ||
+		    !st.reserve(numChunks * 6 * sizeof(float2)) || !ph.reserve(numChunks * 2 * sizeof(double)))
+			return -1;
+		int16_t *dPcm = reinterpret_cast<int16_t *>(out);
+		if (!outOnDevice) {
+			if (!pcm.reserve(pad * sizeof(int16_t))) return -1;
+			dPcm = pcm.as<int16_t>();
+		}
+		float *f = sig.as<float>();
+		// the stream is rendered up to `ticks`: truncate the timeline by telling the kernels the shorter total
+		if (ticks < total) CU(cudaMemcpyAsync(L.start + n, &ticks, 8, cudaMemcpyHostToDevice, stream));
+		CU(launchKlattLongRender(L, ticks, chunkTicks, ph.as<double>(), ph.as<double>() + numChunks, f, f + pad, f + 2 * pad, f + 3 * pad,
+		                         f + 4 * pad, maps.as<Affine>(), st.as<float2>(), dPcm, &launches, stream));
+		CU(cudaEventRecord(cleanup.e1, stream));
+		if (!outOnDevice) CU(cudaMemcpyAsync(out, dPcm, ticks * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
+		CU(cudaStreamSynchronize(stream));
+		if (renderMs) {
+			float ms = 0;
+			CU(cudaEventElapsedTime(&ms, cleanup.e0, cleanup.e1));
+			*renderMs = ms;
+		}
+	} else if (renderMs) {
+		*renderMs = 0;
+	}
+	if (kernelLaunches) *kernelLaunches = launches;
+	return (long long)ticks;
+}

@@ -1,0 +1,612 @@
+// klatt_long: the long-utterance path.  ONE pre-queued stream is cut into chunks of L ticks and every chunk is
+// rendered by its own thread, all chunks at once.  What a chunk needs from its past is recovered in closed form
+// or by a scan instead of by running the past:
+//
+//   frame manager   the occupancy law max(M+1, F+2) (reference src/frame.cpp:41-80) gives every request its first
+//                   tick by a prefix sum; a chunk finds its request by bisection and its position in the fade / hold
+//                   from the tick index.  Interpolated parameters are a function of that position (src/frame.cpp:49-52),
+//                   the hold-phase pitch glide is an arithmetic progression (src/frame.cpp:77).
+//   vibrato phase   64-bit fixed point and piecewise-linear increments: an exact arithmetic series per request.
+//   glottal phase   needs the sum of all earlier per-tick increments (src/speechWaveGenerator.cpp:55,74), which has no
+//                   closed form under vibrato: every chunk sums its own increments in FP64 (klatt_long_phase_kernel) and
+//                   an exclusive scan over chunks gives the phase each chunk starts from.
+//   noise           Philox is random access; the 0.75-pole colouring filter (src/speechWaveGenerator.cpp:40) forgets its
+//                   past within 64 ticks (0.75^64 = 1e-8), so a chunk warms it up on the 64 ticks before its first one.
+//   resonators      each two-pole section is LINEAR in its state for a given input: over a chunk,
+//                   state_end = P * state_start + z with P the product of the per-tick 2x2 update matrices and z the
+//                   end state reached from zero.  Pass 1 of a stage computes (P, z) per chunk, a parallel scan with
+//                   warp shuffles composes these affine maps along the stream (klatt_long_scan_kernel) into the true
+//                   start state of every chunk, pass 2 re-runs the chunk from that state and writes the stage's output
+//                   signal for the next stage.  rN0 stores INPUTS (src/speechWaveGenerator.cpp:133): it is FIR and needs
+//                   no scan.  Stages run in the reference's order: parallel bank (6 sections in one stage), then
+//                   rN0+rNP, r6 ... r1; the last stage fuses the mix, gain, clamp and int16 store (:207-208).
+//
+// The arithmetic of a tick is the FP32 formulation of klatt_f32_core.cuh (delta-form sections, pole recurrences
+// during fades, FP64 pitch and phase); inside a fade the pole is re-based on its closed form every 64 ticks.  Parity
+// with the serial kernels is by tolerance (re-association), not bit for bit: the bar is the FP32 bar (<= 1 LSB on
+// >= 99.9 %, >= 60 dB SNR against the reference).
+#include <cuda_runtime.h>
+#include "klatt_common.h"
+#include "klatt_f32_core.cuh"
+
+namespace klatt {
+
+struct LongStream {
+	const double *frames;      // [nReq][47]
+	const uint32_t *minDur, *fadeDur;
+	const uint8_t *isNull;     // may be null
+	const FadePlanF32 *plans;  // [nReq]
+	uint32_t nReq;
+	int sampleRate;
+	uint64_t seed, streamId;
+	// made by klatt_long_timeline_kernel
+	uint64_t *start;        // [nReq+1] tick of each request's pop tick; start[nReq] = ticks the stream yields
+	int32_t *prevReal;      // [nReq] last non-NULL request before j, or -1
+	double *pitchPop;       // [nReq] cur.voicePitch on the pop tick (stale value)
+	double *pitchOld, *pitchNew, *pitchInc;  // [nReq] fade end points and hold glide
+	uint64_t *vibPosStart;  // [nReq] vibrato phase before the pop tick
+};
+
+namespace {
+
+constexpr int kWarmTicks = 64;
+
+__device__ __forceinline__ bool reqIsNull(const LongStream &L, uint32_t j) { return L.isNull && L.isNull[j] != 0; }
+
+// old / new value of frame parameter p for the fade of request j (plannedFrames() of klatt_f32_core.cuh, one slot)
+__device__ void fadeEnds(const LongStream &L, uint32_t j, int p, double &o, double &n) {
+	const bool curNull = reqIsNull(L, j);
+	const bool prevNull = (j == 0) || reqIsNull(L, j - 1);
+	const int32_t pr = L.prevReal[j];
+	double PR = pr >= 0 ? L.frames[(size_t)pr * kNumParams + p] : 0.0;
+	if (p == kPreFormantGain && prevNull) PR = 0.0;
+	if (curNull) {
+		o = PR;
+		n = (p == kPreFormantGain) ? 0.0 : o;
+	} else {
+		n = L.frames[(size_t)j * kNumParams + p];
+		o = prevNull ? ((p == kPreFormantGain) ? 0.0 : n) : PR;
+	}
+}
+
+// where a tick sits: request j, sampleCounter value c on that tick (0 on the pop tick), fade length F
+struct Cursor {
+	uint32_t j, c, F;
+	uint64_t left;  // ticks of this request still to come, this one included
+	__device__ void load(const LongStream &L) {
+		if (j < L.nReq) {
+			uint32_t fd = L.fadeDur[j];
+			F = fd > 1u ? fd : 1u;
+		} else {
+			F = 1;
+		}
+	}
+	__device__ void seek(const LongStream &L, uint64_t t) {
+		uint32_t lo = 0, hi = L.nReq;  // last j with start[j] <= t
+		while (hi - lo > 1) {
+			uint32_t mid = (lo + hi) >> 1;
+			if (L.start[mid] <= t) lo = mid; else hi = mid;
+		}
+		j = lo;
+		c = (uint32_t)(t - L.start[j]);
+		left = L.start[j + 1] - t;
+		load(L);
+	}
+	__device__ void next(const LongStream &L) {
+		++c;
+		if (--left == 0) {
+			++j;
+			c = 0;
+			if (j < L.nReq) left = L.start[j + 1] - L.start[j];
+			load(L);
+		}
+	}
+};
+
+// one directly used parameter along the stream (reference src/frame.cpp:49-52 + the stale pop tick)
+struct DirWalk {
+	float prevFinal, d0, ds, dF;
+	__device__ void load(const LongStream &L, uint32_t j, int slot) {
+		prevFinal = j > 0 ? L.plans[j - 1].dirFinal[slot] : 0.0f;
+		const FadePlanF32 &p = L.plans[j];
+		d0 = p.dir0[slot]; ds = p.dirStep[slot]; dF = p.dirFinal[slot];
+	}
+	__device__ __forceinline__ float at(uint32_t c, uint32_t F) const {
+		return c == 0 ? prevFinal : (c < F ? fmaf((float)c, ds, d0) : dF);
+	}
+};
+
+// zeta = 1 - pole of one section along the stream
+struct PoleWalk {
+	float zr, zi, wr, wi;
+	__device__ void exact(const LongStream &L, uint32_t j, uint32_t k, uint32_t F, int r) {
+		double f0, f1, b0, b1;
+		fadeEnds(L, j, resFreqParam(r), f0, f1);
+		fadeEnds(L, j, resBwParam(r), b0, b1);
+		if (f1 != f1) f1 = f0;
+		if (b1 != b1) b1 = b0;
+		const double ratio = (double)k / (double)F;
+		poleTerms(f0 + ((f1 - f0) * ratio), b0 + ((b1 - b0) * ratio), 1.0 / (double)L.sampleRate, zr, zi);
+	}
+	// state as it is AFTER the tick before (j, c)
+	__device__ void seek(const LongStream &L, uint32_t j, uint32_t c, uint32_t F, int r) {
+		wr = wi = 0.0f;
+		if (c <= 1) {
+			if (j > 0) { zr = L.plans[j - 1].zFre[r]; zi = L.plans[j - 1].zFim[r]; }
+			else { zr = zi = 0.0f; }
+		} else if (c <= F) {  // ticks 1 .. c-1 of the fade are behind us
+			if (c - 1 < F) { exact(L, j, c - 1, F, r); wr = L.plans[j].wre[r]; wi = L.plans[j].wim[r]; }
+		} else {
+			zr = L.plans[j].zFre[r]; zi = L.plans[j].zFim[r];
+		}
+	}
+	// the update of tick (j, c): afterwards (zr, zi) is what the tick renders with
+	__device__ __forceinline__ void tick(const LongStream &L, uint32_t j, uint32_t c, uint32_t F, int r) {
+		if (c == 0 || c > F) return;  // pop tick: stale; after the landing: constant
+		if (c == F) {
+			zr = L.plans[j].zFre[r]; zi = L.plans[j].zFim[r]; wr = wi = 0.0f;
+			return;
+		}
+		if (c == 1) {
+			const FadePlanF32 &p = L.plans[j];
+			zr = p.z0re[r]; zi = p.z0im[r]; wr = p.wre[r]; wi = p.wim[r];
+		}
+		if ((c & (uint32_t)(kCoarseTicks - 1)) == 0) {
+			exact(L, j, c, F, r);  // drift control: back onto the closed form
+			return;
+		}
+		float tr = fmaf(-zr, wr, wr);
+		tr = fmaf(zi, wi, tr);
+		float ti = fmaf(-zr, wi, wi);
+		ti = fmaf(-zi, wr, ti);
+		zr += tr;
+		zi += ti;
+	}
+	__device__ __forceinline__ void coef(float &a, float &rho) const {
+		a = fmaf(zr, zr, zi * zi);
+		rho = fmaf(2.0f, zr, -a);
+	}
+};
+
+__device__ __forceinline__ bool n0InvAt(const LongStream &L, uint32_t j, uint32_t c, uint32_t F) {
+	if (c == 0) return j > 0 ? L.plans[j - 1].n0InvFinal != 0 : false;
+	return (c < F ? L.plans[j].n0InvFade : L.plans[j].n0InvFinal) != 0;
+}
+
+// cur.voicePitch on tick (j, c)
+__device__ __forceinline__ double pitchAt(const LongStream &L, uint32_t j, uint32_t c, uint32_t F) {
+	if (c == 0) return L.pitchPop[j];
+	const double o = L.pitchOld[j], n = L.pitchNew[j];
+	if (c < F) return (n != n) ? o : o + ((n - o) * ((double)c / (double)F));
+	const double landing = (n != n) ? o : o + ((n - o) * 1.0);
+	if (c <= F + 1) return landing;
+	return landing + (double)(c - F - 1) * L.pitchInc[j];
+}
+
+// vibrato: per-tick increment on tick (j, c), and the phase after the ticks before (j, c)
+struct VibWalk {
+	int64_t vPrev, v0, vs, vF;
+	__device__ void load(const LongStream &L, uint32_t j) {
+		vPrev = j > 0 ? L.plans[j - 1].vibIncFinal : 0;
+		v0 = L.plans[j].vibInc0; vs = L.plans[j].vibIncStep; vF = L.plans[j].vibIncFinal;
+	}
+	__device__ __forceinline__ int64_t inc(uint32_t c, uint32_t F) const {
+		return c == 0 ? vPrev : (c < F ? v0 + (int64_t)c * vs : vF);
+	}
+	// sum of inc(c') for c' in [0, c)
+	__device__ uint64_t before(uint32_t c, uint32_t F) const {
+		if (c == 0) return 0;
+		uint64_t s = (uint64_t)vPrev;
+		const uint64_t kmax = (c - 1 < F - 1) ? c - 1 : F - 1;  // fade ticks 1 .. kmax are behind us
+		s += kmax * (uint64_t)v0 + (uint64_t)vs * (kmax * (kmax + 1) / 2);
+		if (c > F) s += (uint64_t)(c - F) * (uint64_t)vF;
+		return s;
+	}
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// timeline: one thread walks the queue once (a request per iteration; the per-tick work is all in the other kernels)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void klatt_long_timeline_kernel(LongStream L) {
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	uint64_t t = 0, vibPos = 0;
+	int32_t prevReal = -1;
+	bool oldIsNull = true;
+	double pitchCur = 0.0;
+	int64_t vPrev = 0;
+	for (uint32_t j = 0; j < L.nReq; ++j) {
+		const uint64_t M = L.minDur[j];
+		const uint32_t fd = L.fadeDur[j];
+		const uint64_t F = fd > 1u ? fd : 1u;
+		const bool null = reqIsNull(L, j);
+		L.start[j] = t;
+		L.prevReal[j] = prevReal;
+		L.pitchPop[j] = pitchCur;
+		double pOld = pitchCur, pNew, inc;
+		if (null) {  // src/frame.cpp:59-63
+			pNew = pitchCur;
+			inc = 0.0;
+		} else {
+			const double *fr = L.frames + (size_t)j * kNumParams;
+			pNew = fr[kVoicePitch];
+			inc = (fr[kEndVoicePitch] - fr[kVoicePitch]) / (double)M;  // src/frame.cpp:98
+			if (oldIsNull) pOld = pNew;                                // :64-67
+		}
+		pNew += inc * (double)F;  // :71
+		L.pitchOld[j] = pOld; L.pitchNew[j] = pNew; L.pitchInc[j] = inc;
+		const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
+		const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
+		pitchCur = landing + (double)(occ - F - 2) * inc;  // hold ticks F+2 .. occ-1 (src/frame.cpp:77)
+		L.vibPosStart[j] = vibPos;
+		const FadePlanF32 &p = L.plans[j];
+		uint64_t s = (uint64_t)vPrev + (F - 1) * (uint64_t)p.vibInc0 + (uint64_t)p.vibIncStep * ((F - 1) * F / 2) +
+		             (occ - F) * (uint64_t)p.vibIncFinal;
+		vibPos += s;
+		vPrev = p.vibIncFinal;
+		oldIsNull = null;
+		if (!null) prevReal = (int32_t)j;
+		t += occ;
+	}
+	L.start[L.nReq] = t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// source: vibrato, glottal phase, aspiration / frication noise (reference src/speechWaveGenerator.cpp:72-86, :205-206)
+// ---------------------------------------------------------------------------------------------------------------
+struct SourceWalk {
+	Cursor cur;
+	VibWalk vw;
+	DirWalk vpo, vta, goq, va, aa, fa, pfg;
+	uint64_t vibPos;
+	uint32_t loaded;
+	__device__ void loadReq(const LongStream &L, bool full) {
+		vw.load(L, cur.j);
+		vpo.load(L, cur.j, dVibratoPitchOffset);
+		if (full) {
+			vta.load(L, cur.j, dVoiceTurbulenceAmplitude); goq.load(L, cur.j, dGlottalOpenQuotient);
+			va.load(L, cur.j, dVoiceAmplitude); aa.load(L, cur.j, dAspirationAmplitude);
+			fa.load(L, cur.j, dFricationAmplitude); pfg.load(L, cur.j, dPreFormantGain);
+		}
+		loaded = cur.j;
+	}
+	__device__ void seek(const LongStream &L, uint64_t t, bool full) {
+		cur.seek(L, t);
+		loadReq(L, full);
+		vibPos = L.vibPosStart[cur.j] + vw.before(cur.c, cur.F);
+	}
+	// phase increment of this tick, in cycles (FP64)
+	__device__ __forceinline__ double phaseInc(const LongStream &L, double srInv) {
+		vibPos += (uint64_t)vw.inc(cur.c, cur.F);
+		float vph = (float)(int32_t)(uint32_t)(vibPos >> 32) * 2.3283064365386963e-10f;
+		float vib = (sinTurns(vph) * 0.06f) * vpo.at(cur.c, cur.F);
+		double base = pitchAt(L, cur.j, cur.c, cur.F) * srInv;
+		return fma(base, (double)vib, base);
+	}
+	__device__ __forceinline__ void next(const LongStream &L, bool full) {
+		cur.next(L);
+		if (cur.j != loaded && cur.j < L.nReq) loadReq(L, full);
+	}
+};
+
+// pass 1: the phase every chunk advances by (fraction of a cycle)
+__global__ void __launch_bounds__(128)
+klatt_long_phase_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, double *__restrict__ advance) {
+	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ch >= numChunks) return;
+	const uint64_t total = L.start[L.nReq];
+	const uint64_t t0 = (uint64_t)ch * chunkTicks;
+	const uint64_t t1 = (t0 + chunkTicks < total) ? t0 + chunkTicks : total;
+	const double srInv = 1.0 / (double)L.sampleRate;
+	SourceWalk w;
+	w.seek(L, t0, false);
+	double pos = 0.0;
+	for (uint64_t t = t0; t < t1; ++t) {
+		pos = fracRef(pos + w.phaseInc(L, srInv));
+		w.next(L, false);
+	}
+	advance[ch] = pos;
+}
+
+// exclusive scan of the per-chunk phase advances (one thread: numChunks dependent FP64 additions)
+__global__ void klatt_long_phase_scan_kernel(const double *__restrict__ advance, uint32_t numChunks, double *__restrict__ startPhase) {
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	double pos = 0.0;
+	for (uint32_t c = 0; c < numChunks; ++c) {
+		startPhase[c] = pos;
+		pos = fracRef(pos + advance[c]);
+	}
+}
+
+// pass 2: the two excitation signals of every tick: cascade input ci (:204, :148) and parallel input pin (:206, :171)
+__global__ void __launch_bounds__(128)
+klatt_long_source_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, const double *__restrict__ startPhase,
+                         float *__restrict__ ci, float *__restrict__ pin) {
+	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ch >= numChunks) return;
+	const uint64_t total = L.start[L.nReq];
+	const uint64_t t0 = (uint64_t)ch * chunkTicks;
+	const uint64_t t1 = (t0 + chunkTicks < total) ? t0 + chunkTicks : total;
+	const double srInv = 1.0 / (double)L.sampleRate;
+	// warm the two noise colouring filters up on the ticks before the chunk
+	float aspLast = 0.0f, fricLast = 0.0f;
+	for (uint64_t g = (t0 > (uint64_t)kWarmTicks ? t0 - kWarmTicks : 0); g < t0; ++g) {
+		Philox4 b = noiseBlock(L.seed, L.streamId, g >> 1);
+		const uint32_t wA = (g & 1) ? b.w[2] : b.w[0], wF = (g & 1) ? b.w[3] : b.w[1];
+		aspLast = fmaf(0.75f, aspLast, bitsToFloat(0x4B000000u | (wA >> 9)) - 8388608.0f);
+		fricLast = fmaf(0.75f, fricLast, bitsToFloat(0x4B000000u | (wF >> 9)) - 8388608.0f);
+	}
+	SourceWalk w;
+	w.seek(L, t0, true);
+	double pos = startPhase[ch];
+	Philox4 blk;
+	blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
+	for (uint64_t t = t0; t < t1; ++t) {
+		if ((t & 1) == 0 || t == t0) blk = noiseBlock(L.seed, L.streamId, t >> 1);
+		const uint32_t wA = (t & 1) ? blk.w[2] : blk.w[0], wF = (t & 1) ? blk.w[3] : blk.w[1];
+		pos = fracRef(pos + w.phaseInc(L, srInv));
+		const uint32_t c = w.cur.c, F = w.cur.F;
+		const float voice = (float)pos;
+		aspLast = fmaf(0.75f, aspLast, bitsToFloat(0x4B000000u | (wA >> 9)) - 8388608.0f);
+		float asp = aspLast * (0.2f * kDrawScale);
+		float turb = asp * w.vta.at(c, F);
+		if (voice < w.goq.at(c, F)) turb *= 0.01f;
+		float v = (fmaf(voice, 2.0f, -1.0f) + turb) * w.va.at(c, F);
+		float src = fmaf(asp, w.aa.at(c, F), v);
+		const float halfGain = w.pfg.at(c, F) * 0.5f;
+		ci[t] = src * halfGain;
+		fricLast = fmaf(0.75f, fricLast, bitsToFloat(0x4B000000u | (wF >> 9)) - 8388608.0f);
+		pin[t] = fricLast * (((0.3f * kDrawScale) * w.fa.at(c, F)) * halfGain);
+		w.next(L, true);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// resonator stages
+// ---------------------------------------------------------------------------------------------------------------
+enum Stage : int { kStageParallel = 0, kStageNasal = 1, kStageCascade = 2, kStageLast = 3 };
+
+template <int STAGE> struct StageTraits {
+	static constexpr int NR = STAGE == kStageParallel ? 6 : 1;  // scanned sections
+};
+
+// affine map of one section over one chunk, (y, d)_end = P (y, d)_start + z, row-major P
+struct Affine {
+	float p00, p01, p10, p11, zy, zd;
+};
+
+// One chunk of one stage.  PASS 1: from zero state, also accumulate P.  PASS 2: from the scanned start state, write
+// the stage's output signal (or, for the last stage, the int16 samples).
+//   kStageParallel: in = pin, sections 8..13, out = par (:170-180)
+//   kStageNasal   : in = ci, rN0 (FIR) then rNP (section 1), out = x after the caNP mix (:148-150)
+//   kStageCascade : in = x, section `res`, out = its output (:151-156)
+//   kStageLast    : like kStageCascade for r1, then (x + par) * outputGain * 4000, clamp, truncate (:207-208)
+template <int STAGE, int PASS>
+__global__ void __launch_bounds__(128)
+klatt_long_stage_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, int res, const float *__restrict__ in,
+                        const float *__restrict__ par, Affine *__restrict__ maps, const float2 *__restrict__ startState,
+                        float *__restrict__ out, int16_t *__restrict__ pcm) {
+	constexpr int NR = StageTraits<STAGE>::NR;
+	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ch >= numChunks) return;
+	const uint64_t total = L.start[L.nReq];
+	const uint64_t t0 = (uint64_t)ch * chunkTicks;
+	const uint64_t t1 = (t0 + chunkTicks < total) ? t0 + chunkTicks : total;
+	Cursor cur;
+	cur.seek(L, t0);
+	PoleWalk pw[NR], pw0;  // pw0: the FIR anti-resonator of the nasal stage
+	DirWalk mix[NR], extra;  // parallel: pa1..6 + bypass; nasal: caNP; last: outputGain
+	auto loadDirs = [&]() {
+		if (STAGE == kStageParallel) {
+#pragma unroll
+			for (int k = 0; k < NR; ++k) mix[k].load(L, cur.j, dPa1 + k);
+			extra.load(L, cur.j, dParallelBypass);
+		} else if (STAGE == kStageNasal) {
+			extra.load(L, cur.j, dCaNP);
+		} else if (STAGE == kStageLast) {
+			extra.load(L, cur.j, dOutputGain);
+		}
+	};
+#pragma unroll
+	for (int k = 0; k < NR; ++k) pw[k].seek(L, cur.j, cur.c, cur.F, STAGE == kStageParallel ? kResParallel + k : res);
+	if (STAGE == kStageNasal) pw0.seek(L, cur.j, cur.c, cur.F, kResN0);
+	loadDirs();
+	uint32_t loaded = cur.j;
+	float y[NR], d[NR];
+	float p00[NR], p01[NR], p10[NR], p11[NR];
+#pragma unroll
+	for (int k = 0; k < NR; ++k) {
+		if (PASS == 2) { float2 s = startState[(size_t)ch * NR + k]; y[k] = s.x; d[k] = s.y; }
+		else { y[k] = 0.0f; d[k] = 0.0f; p00[k] = 1.0f; p01[k] = 0.0f; p10[k] = 0.0f; p11[k] = 1.0f; }
+	}
+	// the FIR section needs the two inputs before the chunk
+	float in1 = 0.0f, in2 = 0.0f;
+	if (STAGE == kStageNasal) {
+		if (t0 >= 1) in1 = in[t0 - 1];
+		if (t0 >= 2) in2 = in[t0 - 2];
+	}
+	for (uint64_t t = t0; t < t1; ++t) {
+		const uint32_t j = cur.j, c = cur.c, F = cur.F;
+		float x = in[t];
+		const float xin = x;
+		if (STAGE == kStageNasal) {  // rN0 on inputs: src/speechWaveGenerator.cpp:129-135 with anti == true
+			pw0.tick(L, j, c, F, kResN0);
+			float a0, rho0;
+			pw0.coef(a0, rho0);
+			const float dprev = in1 - in2;
+			const float dx = x - in1;
+			const float dx1 = fmaf(-rho0, dprev, dprev);
+			x = n0InvAt(L, j, c, F) ? fmaf(dx - dx1, fastRcp(a0), in1) : fmaf(a0, dx, dx1 + in1);
+			in2 = in1;
+			in1 = xin;
+		}
+		float acc = 0.0f;
+#pragma unroll
+		for (int k = 0; k < NR; ++k) {
+			pw[k].tick(L, j, c, F, STAGE == kStageParallel ? kResParallel + k : res);
+			float a, rho;
+			pw[k].coef(a, rho);
+			float w = fmaf(-rho, d[k], d[k]);
+			w = fmaf(-a, y[k], w);
+			const float dn = fmaf(a, x, w);
+			d[k] = dn;
+			y[k] += dn;
+			if (PASS == 1) {  // P <- A P with A = [[1-a, 1-rho], [-a, 1-rho]] acting on (y, d)
+				const float g = 1.0f - rho;
+				const float n10 = fmaf(-a, p00[k], g * p10[k]), n11 = fmaf(-a, p01[k], g * p11[k]);
+				p00[k] += n10; p01[k] += n11;
+				p10[k] = n10; p11[k] = n11;
+			}
+			if (STAGE == kStageParallel) acc = fmaf(y[k] - x, mix[k].at(c, F), acc);
+		}
+		if (PASS == 2) {
+			if (STAGE == kStageParallel) {
+				out[t] = fmaf(x - acc, extra.at(c, F), acc);
+			} else if (STAGE == kStageNasal) {
+				out[t] = fmaf(y[0] - xin, extra.at(c, F), xin);
+			} else if (STAGE == kStageCascade) {
+				out[t] = y[0];
+			} else {
+				float s = (y[0] + par[t]) * (extra.at(c, F) * 4000.0f);
+				s = fminf(s, 32000.0f);
+				s = fmaxf(s, -32000.0f);
+				pcm[t] = (int16_t)(int)s;
+			}
+		}
+		cur.next(L);
+		if (cur.j != loaded && cur.j < L.nReq) { loadDirs(); loaded = cur.j; }
+	}
+	if (PASS == 1) {
+#pragma unroll
+		for (int k = 0; k < NR; ++k) {
+			Affine m;
+			m.p00 = p00[k]; m.p01 = p01[k]; m.p10 = p10[k]; m.p11 = p11[k]; m.zy = y[k]; m.zd = d[k];
+			maps[(size_t)ch * NR + k] = m;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// scan: start state of every chunk = z-part of the composition of all earlier chunks' maps (the stream starts from
+// zero state, reference src/speechWaveGenerator.cpp:104-110).  One block: each thread composes a contiguous run of
+// chunks, the 1024 run totals are scanned with warp shuffles, then each thread replays its run from its prefix.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct AffineD {  // composition is done in double: it is cheap and keeps the scan out of the error budget
+	double p00, p01, p10, p11, zy, zd;
+};
+__device__ __forceinline__ AffineD identityMap() { return AffineD{1.0, 0.0, 0.0, 1.0, 0.0, 0.0}; }
+__device__ __forceinline__ AffineD toD(const Affine &m) { return AffineD{m.p00, m.p01, m.p10, m.p11, m.zy, m.zd}; }
+// `second` after `first`
+__device__ __forceinline__ AffineD compose(const AffineD &second, const AffineD &first) {
+	AffineD r;
+	r.p00 = second.p00 * first.p00 + second.p01 * first.p10;
+	r.p01 = second.p00 * first.p01 + second.p01 * first.p11;
+	r.p10 = second.p10 * first.p00 + second.p11 * first.p10;
+	r.p11 = second.p10 * first.p01 + second.p11 * first.p11;
+	r.zy = second.p00 * first.zy + second.p01 * first.zd + second.zy;
+	r.zd = second.p10 * first.zy + second.p11 * first.zd + second.zd;
+	return r;
+}
+__device__ __forceinline__ AffineD shflUp(const AffineD &m, int delta) {
+	AffineD r;
+	r.p00 = __shfl_up_sync(0xffffffffu, m.p00, delta); r.p01 = __shfl_up_sync(0xffffffffu, m.p01, delta);
+	r.p10 = __shfl_up_sync(0xffffffffu, m.p10, delta); r.p11 = __shfl_up_sync(0xffffffffu, m.p11, delta);
+	r.zy = __shfl_up_sync(0xffffffffu, m.zy, delta); r.zd = __shfl_up_sync(0xffffffffu, m.zd, delta);
+	return r;
+}
+}  // namespace
+
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads)
+klatt_long_scan_kernel(const Affine *__restrict__ maps, uint32_t numChunks, int numSections, float2 *__restrict__ startState) {
+	__shared__ AffineD warpTotal[32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t per = (numChunks + kScanThreads - 1) / kScanThreads;
+	const uint32_t c0 = (uint32_t)tid * per < numChunks ? (uint32_t)tid * per : numChunks;
+	const uint32_t c1 = c0 + per < numChunks ? c0 + per : numChunks;
+	for (int k = 0; k < numSections; ++k) {
+		// 1. this thread's run
+		AffineD run = identityMap();
+		for (uint32_t c = c0; c < c1; ++c) run = compose(toD(maps[(size_t)c * numSections + k]), run);
+		// 2. inclusive scan of the run totals: within the warp by shuffles, then across warps
+		AffineD inc = run;
+#pragma unroll
+		for (int delta = 1; delta < 32; delta <<= 1) {
+			AffineD up = shflUp(inc, delta);
+			if (lane >= delta) inc = compose(inc, up);
+		}
+		if (lane == 31) warpTotal[warp] = inc;
+		__syncthreads();
+		if (warp == 0) {
+			AffineD w = warpTotal[lane];
+#pragma unroll
+			for (int delta = 1; delta < 32; delta <<= 1) {
+				AffineD up = shflUp(w, delta);
+				if (lane >= delta) w = compose(w, up);
+			}
+			warpTotal[lane] = w;
+		}
+		__syncthreads();
+		// exclusive prefix of this thread = (inclusive of the previous lane) after (inclusive total of earlier warps)
+		AffineD prev = shflUp(inc, 1);
+		AffineD pre = lane == 0 ? identityMap() : prev;
+		if (warp > 0) pre = compose(pre, warpTotal[warp - 1]);
+		// 3. replay the run
+		for (uint32_t c = c0; c < c1; ++c) {
+			startState[(size_t)c * numSections + k] = make_float2((float)pre.zy, (float)pre.zd);
+			pre = compose(toD(maps[(size_t)c * numSections + k]), pre);
+		}
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launcher: everything device-resident; scratch sized by the caller (see engine.cu)
+// ---------------------------------------------------------------------------------------------------------------
+cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_t totalRequests, const double *frames,
+                            const uint32_t *fadeDur, const uint8_t *isNull, int sampleRate, FadePlanF32 *plans,
+                            cudaStream_t stream);
+
+cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream) {
+	klatt_long_timeline_kernel<<<1, 1, 0, stream>>>(L);
+	return cudaGetLastError();
+}
+
+// signals: five float arrays of totalTicks (+ padding): ci, pin, par, xa, xb.  maps / startState: numChunks * 6.
+cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, double *advance,
+                                  double *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
+                                  float2 *startState, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream) {
+	if (totalTicks == 0) return cudaSuccess;
+	const uint32_t numChunks = (uint32_t)((totalTicks + chunkTicks - 1) / chunkTicks);
+	const dim3 grid((numChunks + 127) / 128), block(128);
+	klatt_long_phase_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, advance);
+	klatt_long_phase_scan_kernel<<<1, 1, 0, stream>>>(advance, numChunks, startPhase);
+	klatt_long_source_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, startPhase, ci, pin);
+	// parallel bank
+	klatt_long_stage_kernel<kStageParallel, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, maps, nullptr, nullptr, nullptr);
+	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 6, startState);
+	klatt_long_stage_kernel<kStageParallel, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, nullptr, startState, par, nullptr);
+	// rN0 + rNP
+	klatt_long_stage_kernel<kStageNasal, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResNP, ci, nullptr, maps, nullptr, nullptr, nullptr);
+	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
+	klatt_long_stage_kernel<kStageNasal, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResNP, ci, nullptr, nullptr, startState, xa, nullptr);
+	// r6 .. r2
+	float *src = xa, *dst = xb;
+	for (int r = kResCascade; r < kResParallel - 1; ++r) {
+		klatt_long_stage_kernel<kStageCascade, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, r, src, nullptr, maps, nullptr, nullptr, nullptr);
+		klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
+		klatt_long_stage_kernel<kStageCascade, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, r, src, nullptr, nullptr, startState, dst, nullptr);
+		float *tmp = src; src = dst; dst = tmp;
+	}
+	// r1 + output
+	klatt_long_stage_kernel<kStageLast, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, maps, nullptr, nullptr, nullptr);
+	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
+	klatt_long_stage_kernel<kStageLast, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, nullptr, startState, nullptr, pcm);
+	if (launchCounter) *launchCounter += 3 + 3 * 8;
+	return cudaGetLastError();
+}
+
+}  // namespace klatt

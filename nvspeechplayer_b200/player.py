@@ -90,6 +90,8 @@ def load_library():
     L.speechPlayer_batchGetLastIndices.argtypes = [vp, vp]
     L.speechPlayer_batchGetLaunchStats.restype = i32
     L.speechPlayer_batchGetLaunchStats.argtypes = [vp, vp, vp]
+    L.speechPlayer_synthesizeLong.restype = ctypes.c_longlong
+    L.speechPlayer_synthesizeLong.argtypes = [i32, vp, vp, vp, vp, u32, u64, u64, u32, vp, ctypes.c_ulonglong, i32, vp, vp]
     _lib = L
     return L
 
@@ -201,6 +203,33 @@ def synthesize_batch(players, num_samples):
     written = np.zeros(n, dtype=np.uint32)
     _check(L.speechPlayer_synthesizeBatch(handles, n, num_samples, _ptr(out), _ptr(written)), "speechPlayer_synthesizeBatch")
     return out, written
+
+
+def synthesize_long(sample_rate, frames, min_dur, fade_dur, is_null=None, seed=0xB200, stream_id=0, chunk_ticks=0,
+                    max_samples=None, out=None, device_out=None):
+    """speechPlayer_synthesizeLong: one pre-queued stream rendered with parallelism in time (kernel b).
+    Returns (int16 samples, render_ms, kernel_launches); with device_out (a raw device address) the samples stay in
+    HBM and the first element is the sample count."""
+    L = load_library()
+    frames = np.ascontiguousarray(frames, dtype=np.float64).reshape(-1, NUM_PARAMS)
+    m = np.ascontiguousarray(min_dur, dtype=np.uint32)
+    f = np.ascontiguousarray(fade_dur, dtype=np.uint32)
+    nul = None if is_null is None else np.ascontiguousarray(is_null, dtype=np.uint8)
+    if max_samples is None:
+        mm, ff = m.astype(np.int64), np.maximum(f.astype(np.int64), 1)
+        max_samples = int(np.maximum(mm + 1, ff + 2).sum())
+    ms, launches = ctypes.c_double(0), ctypes.c_ulonglong(0)
+    if device_out is not None:
+        got = L.speechPlayer_synthesizeLong(sample_rate, _ptr(frames), _ptr(m), _ptr(f), _ptr(nul), len(m), seed, stream_id,
+                                            chunk_ticks, device_out, max_samples, 1, ctypes.byref(ms), ctypes.byref(launches))
+        _check(got, "speechPlayer_synthesizeLong")
+        return got, ms.value, launches.value
+    if out is None:
+        out = np.zeros(max_samples, dtype=np.int16)
+    got = L.speechPlayer_synthesizeLong(sample_rate, _ptr(frames), _ptr(m), _ptr(f), _ptr(nul), len(m), seed, stream_id,
+                                        chunk_ticks, _ptr(out), max_samples, 0, ctypes.byref(ms), ctypes.byref(launches))
+    _check(got, "speechPlayer_synthesizeLong")
+    return out[:got], ms.value, launches.value
 
 
 class Batch(object):
