@@ -46,6 +46,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-streams-per-core", type=int, default=16)
+    ap.add_argument("--workload", default="batch", choices=["batch", "long"],
+                    help="batch: BASELINE config 3 (default, the headline); long: config 4, ONE stream of --long-seconds at "
+                         "--long-rate through the time-parallel kernel")
+    ap.add_argument("--long-seconds", type=float, default=3600.0)
+    ap.add_argument("--long-rate", type=int, default=44100)
     return ap.parse_args()
 
 
@@ -133,6 +138,83 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def long_arm(args, rank, world, local_rank):
+    """BASELINE config 4: a single long stream (config-3 frame generator at 44.1 kHz) through kernel (b).  The path does
+    not shard (one stream): N > 1 runs N independent replicas, one per GPU ("replicas only")."""
+    import numpy as np
+    import torch
+    from nvspeechplayer_b200 import player, workloads
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sr, secs = args.long_rate, args.long_seconds
+    fr, m, f, nul, ux = workloads.random_stream(4_000_000 + rank, secs, sr, seed=args.seed)
+    n = int(round(secs * sr))
+    fb = workloads._concat(sr, [(fr, m, f, nul, ux)], [4_000_000 + rank])
+    phi = fb.fade_fraction(n)
+    flops_per_sample = W_HOLD + W_FADE_EXTRA * phi
+    d_out = torch.empty(n + 64, dtype=torch.int16, device=dev)
+    lib = player.load_library()
+    lib.speechPlayer_debugFp32PeakTflops.restype = __import__("ctypes").c_double
+    peak_tf = float(lib.speechPlayer_debugFp32PeakTflops())
+    sampler = ClockSampler(local_rank)
+    times, launches = [], 0
+    for i in range(max(args.warmup, 3) + args.steps):
+        if i == max(args.warmup, 3) and rank == 0:
+            sampler.start()
+        torch.cuda.synchronize()
+        got, ms, launches = player.synthesize_long(sr, fr, m, f, nul, seed=args.seed, stream_id=4_000_000 + rank, max_samples=n,
+                                                   device_out=d_out.data_ptr())
+        assert got == n, (got, n)
+        if i >= max(args.warmup, 3):
+            times.append(ms)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(times) / len(times)
+    # e2e: host frames in, host int16 out, wall clock around the C-ABI call
+    h_out = np.zeros(n, dtype=np.int16)
+    t0 = time.perf_counter()
+    out, _, _ = player.synthesize_long(sr, fr, m, f, nul, seed=args.seed, stream_id=4_000_000 + rank, max_samples=n, out=h_out)
+    e2e_s = time.perf_counter() - t0
+    same = bool(np.array_equal(out[:100000], d_out[:100000].cpu().numpy()))
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle
+            ref = oracle.RefLib(philox=False) if oracle.have_ref() else None
+            cn = int(30.0 * sr)  # bounded sample: the first 30 s of the same stream, one core (a stream is serial on a CPU)
+            t0 = time.perf_counter()
+            if ref is not None:
+                got_cpu = ref.render(sr, fr, m, f, nul, max_samples=cn, seed=1)
+            else:
+                got_cpu = oracle.PortLib().render(sr, fr, m, f, nul, max_samples=cn, noise=("libc",))
+            dt = time.perf_counter() - t0
+            cpu = {"value": len(got_cpu) / sr / dt, "unit": "audio-seconds/s", "cores": 1, "kind": "reference" if ref else "port",
+                   "sample": "first 30 s of the same stream incl. queueing its frames, one core"}
+        achieved = n * flops_per_sample / (ms * 1e-3) / 1e12
+        line = {"metric": "audio-seconds synthesized/sec (single long stream)", "value": world * secs / (ms * 1e-3),
+                "unit": "audio-seconds/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "config4: single %.0f s stream @ %d Hz, random frames, time-parallel kernel (b)" % (secs, sr),
+                           "frames": int(len(m)), "fade_fraction_phi": round(phi, 4), "flops_per_sample_W": round(flops_per_sample, 1),
+                           "l2": "no flush needed: the stage signals (5 x %.2f GB) exceed the 126 MB L2" % (n * 4 / 1e9)},
+                "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                             "traffic": None, "kernel": "klatt_long_* (27 launches)",
+                             "note": "algorithmic flops of the SERIAL path; the scan formulation executes about 3x of them"},
+                "cpu_baseline": cpu,
+                "e2e": {"value": world * secs / e2e_s, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(fr.nbytes + m.nbytes + f.nbytes + nul.nbytes),
+                        "d2h_bytes_per_step": int(n * 2), "matches_device_path": same},
+                "gpu_launches": int(launches) * args.steps, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -140,6 +222,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.workload == "long":
+        long_arm(args, rank, world, local_rank)
         return
 
     import numpy as np
@@ -309,7 +394,7 @@ def main():
                          "peak_source": "FFMA loop measured on this GPU in this run (MEASURED_PEAKS.json has no FP32 entry)"
                                         if fp32_peak_measured > 0 else "SMs x 128 x 2 x max SM clock",
                          "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
-                         "kernel": "klatt_batch_f32_kernel" if prec == player.PRECISION_FP32 else "klatt_batch_f64_kernel",
+                         "kernel": "klatt_f32_hold_kernel + klatt_f32_general_pair_kernel (rounds)" if prec == player.PRECISION_FP32 else "klatt_batch_f64_kernel",
                          "flops_per_launch": S * count * flops_per_sample, "kernel_ms": kernel_ms,
                          "kernel_share_of_step": kernel_ms / ms_per_step},
             "roofline_hbm": {"bound": "hbm", "achieved": out_bytes_per_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
