@@ -390,7 +390,11 @@ def main():
                        "real_time_factor_per_gpu": samples_per_s_gpu / sr,
                        "host_enqueue_ms_per_step": round(1e3 * sum(enqueue_s) / max(len(enqueue_s), 1), 2)},
             "roofline": {"bound": "fp32_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "frac": achieved_tf / peak_tf,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
+                         # (klatt_f32_general_pair_kernel, one 256-tick round over ~35k streams), ncu --set full capture
+                         # summarised in profiles/r01_v2_ncu_summary.txt; algorithmic output of that launch: 18 MB
+                         "traffic": 84.9e6 if (prec == player.PRECISION_FP32 and S == 65536) else None,
                          "peak_source": "FFMA loop measured on this GPU in this run (MEASURED_PEAKS.json has no FP32 entry)"
                                         if fp32_peak_measured > 0 else "SMs x 128 x 2 x max SM clock",
                          "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
