@@ -288,7 +288,7 @@ struct HostPipe {
 
 static size_t stagingBudgetBytes() {
 	const char *e = getenv("NVSP_STAGE_MB");
-	size_t mb = (e && *e) ? (size_t)atoll(e) : 512;
+	size_t mb = (e && *e) ? (size_t)atoll(e) : 2048;
 	return std::max<size_t>(mb, 1) << 20;
 }
 
