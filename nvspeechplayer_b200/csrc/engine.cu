@@ -58,8 +58,8 @@ struct Affine {
 	float p00, p01, p10, p11, zy, zd;
 };
 cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream);
-cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, double *advance,
-                                  double *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
+cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
+                                  uint64_t *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
                                   float2 *startState, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream);
 }  // namespace klatt
 
@@ -1036,7 +1036,7 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 		float *f = sig.as<float>();
 		// the stream is rendered up to `ticks`: truncate the timeline by telling the kernels the shorter total
 		if (ticks < total) CU(cudaMemcpyAsync(L.start + n, &ticks, 8, cudaMemcpyHostToDevice, stream));
-		CU(launchKlattLongRender(L, ticks, chunkTicks, ph.as<double>(), ph.as<double>() + numChunks, f, f + pad, f + 2 * pad, f + 3 * pad,
+		CU(launchKlattLongRender(L, ticks, chunkTicks, ph.as<uint64_t>(), ph.as<uint64_t>() + numChunks, f, f + pad, f + 2 * pad, f + 3 * pad,
 		                         f + 4 * pad, maps.as<Affine>(), st.as<float2>(), dPcm, &launches, stream));
 		CU(cudaEventRecord(cleanup.e1, stream));
 		if (!outOnDevice) CU(cudaMemcpyAsync(out, dPcm, ticks * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));

@@ -104,7 +104,7 @@ struct alignas(16) FadePlanF32 {
 static_assert(sizeof(FadePlanF32) % 16 == 0, "plan records are read with 16-byte loads");
 
 struct GenStateF32 {
-	double pitchPos;               // glottal phase in cycles, FP64 by design
+	double pitchPos;               // glottal phase in cycles, FP64 and accumulated exactly like the reference does
 	double pitch;                  // cur.voicePitch
 	double pitchInc;               // its per-tick increment in force: fade step, hold glide, or 0 (pop / swap / landing tick)
 	double pitchOld, pitchNew;     // end points of the fade in progress (the landing tick evaluates old+(new-old)*1.0)

@@ -98,25 +98,33 @@ klatt_partition_kernel(const StreamDesc *__restrict__ descs, uint32_t firstStrea
 // ---- the two sides of a stream in different warps of one block ------------------------------------------------
 // block = 4 warps: warps 0,1 run the cascade side of streams [64b, 64b+32) and [64b+32, 64b+64) of the list,
 // warps 2,3 the parallel side of the same streams.  Warp w and warp w+2 share one named barrier and a
-// double-buffered shared-memory hand-over of (aspiration noise word, parallel-bank output, vibrato) x 8 ticks x 32 lanes.
+// double-buffered shared-memory hand-over of (aspiration noise word, parallel-bank output, sawtooth value) x 8 ticks x 32 lanes.
 struct XchgSmem {
 	uint32_t base;  // shared-space address of this lane's column of the pair's [2 buffers][8 ticks][32 lanes] x 16 bytes
 	uint32_t barId;
-	__device__ __forceinline__ void put(uint32_t t, uint32_t wA, float par, float vib) {
+	__device__ __forceinline__ void put(uint32_t t, uint32_t wA, float par, float voice) {
 		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(base + (t & 15u) * 512u), "r"(wA), "r"(__float_as_uint(par)),
-		             "r"(__float_as_uint(vib)) : "memory");
+		             "r"(__float_as_uint(voice)) : "memory");
 	}
-	__device__ __forceinline__ void get(uint32_t t, uint32_t &wA, float &par, float &vib) const {
+	__device__ __forceinline__ void get(uint32_t t, uint32_t &wA, float &par, float &voice) const {
 		uint32_t p, v, pad;
 		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wA), "=r"(p), "=r"(v), "=r"(pad) : "r"(base + (t & 15u) * 512u) : "memory");
 		par = __uint_as_float(p);
-		vib = __uint_as_float(v);
+		voice = __uint_as_float(v);
 	}
 	__device__ __forceinline__ void sync() { asm volatile("bar.sync %0, 64;" ::"r"(barId) : "memory"); }
 };
 struct NullOut {
 	__device__ __forceinline__ void push(int) {}
 };
+
+// Which side a warp runs.  A warp's scheduler is warp-id % 4, so "warps 0,1 cascade / 2,3 parallel" in every block would
+// give two schedulers of an SM nothing but the (lighter, latency-bound) cascade warps and the other two nothing but the
+// (heavier) parallel warps; flipping the assignment on a hash of the block index mixes both kinds on every scheduler.
+__device__ __forceinline__ bool cascadeRole(uint32_t warp) {
+	const uint32_t flip = (blockIdx.x * 0x9E3779B9u) >> 31;
+	return ((warp >> 1) ^ flip) == 0;
+}
 
 constexpr int kPairBlock = 128;        // threads
 constexpr int kPairStreams = 64;       // streams per block
@@ -135,15 +143,15 @@ klatt_f32_hold_kernel(const StreamDesc *__restrict__ descs, const uint32_t *__re
 	const uint32_t s = valid ? list[slot] : numStreams;
 	const StreamDesc &desc = descs[s];
 	XchgSmem xc{(uint32_t)__cvta_generic_to_shared(&xbuf[pair][lane]), 1u + pair};
-	if (warp < 2) {
+	if (cascadeRole(warp)) {
 		// idle lanes render the dummy stream into a scratch row of holdTicks samples
 		int16_t *row = valid ? out + (size_t)s * rowStride + desc.state->gen.f32.callPos : scratchRow;
 		OutWriter ow;
 		ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0));
-		renderHoldF32<kRoleCascade>(desc, sampleRate, holdTicks, ow, noise, xc);
+		renderHoldF32<kRoleCascadeOsc>(desc, sampleRate, holdTicks, ow, noise, xc);
 	} else {
 		NullOut no;
-		renderHoldF32<kRoleParallel>(desc, sampleRate, holdTicks, no, noise, xc);
+		renderHoldF32<kRoleParallelOnly>(desc, sampleRate, holdTicks, no, noise, xc);
 	}
 }
 
@@ -170,7 +178,7 @@ klatt_f32_general_pair_kernel(const StreamDesc *__restrict__ descs, const uint32
 	XchgSmem xc{(uint32_t)__cvta_generic_to_shared(&xbuf[pair][lane]), 1u + pair};
 	int32_t lastUserIndex;
 	uint32_t qHead;
-	if (warp < 2) {
+	if (cascadeRole(warp)) {
 		int16_t *row = out + (size_t)(valid ? s : 0) * rowStride;
 		OutWriter ow;
 		ow.init(row + pos, ((reinterpret_cast<uintptr_t>(row + pos) & 15u) == 0));  // idle lanes have no ticks: they never store

@@ -150,21 +150,26 @@ KLATT_HD void plannedFrames(const double *prevReal, bool prevIsNull, const doubl
 // ---------------------------------------------------------------------------------------------------
 // Roles.  A stream's tick splits into two halves that only meet in the final mix (reference
 // src/speechWaveGenerator.cpp:203-207):
-//   cascade side  : glottal phase, aspiration, rN0, rNP, r6..r1            (resonators 0..7)  -> x, and the sample
+//   cascade side  : aspiration, glottal shaping, rN0, rNP, r6..r1          (resonators 0..7)  -> x, and the sample
 //   parallel side : noise draws, frication, the six parallel sections      (resonators 8..13) -> par,
-//                   and the vibrato oscillator (it feeds the cascade side's phase increment, but depends on nothing
-//                   the cascade side computes, and moving it here balances the two halves)
+//                   and the two oscillators with their FP64 arithmetic: vibrato, pitch glide, glottal phase -> voice
+//                   (they feed the cascade side, but depend on nothing the cascade side computes; the cascade
+//                   side is a long dependent chain, the parallel side has independent work to hide them behind)
 // kRoleBoth runs both in one thread (per-handle API, host numerics build).  The batch kernels give each side its
 // own thread in a different warp of the block (half the registers per thread, twice the warps per SM); the
-// parallel side hands (aspiration noise word, par, vibrato) over through shared memory 8 ticks at a time.  Every role
+// parallel side hands (aspiration noise word, par, sawtooth value) over through shared memory 8 ticks at a time.  Every role
 // executes the same operations on the same values, so all of them produce the same bits.
 // ---------------------------------------------------------------------------------------------------
-enum Role : int { kRoleBoth = 0, kRoleCascade = 1, kRoleParallel = 2 };
+// kRoleCascade / kRoleParallel: the general kernel's split (oscillators on the parallel side: its cascade side is the
+// longer dependent chain).  kRoleCascadeOsc / kRoleParallelOnly: the hold kernel's split (straight-line code: the
+// oscillators overlap with the cascade chain there, and the parallel side carries the Philox generator).
+enum Role : int { kRoleBoth = 0, kRoleCascade = 1, kRoleParallel = 2, kRoleCascadeOsc = 3, kRoleParallelOnly = 4 };
 constexpr int kGroupTicks = 8;  // hand-over granularity, and one 16-byte output store
 
 template <int ROLE> struct RoleTraits {
-	static constexpr bool hasC = ROLE != kRoleParallel;
-	static constexpr bool hasP = ROLE != kRoleCascade;
+	static constexpr bool hasC = ROLE == kRoleBoth || ROLE == kRoleCascade || ROLE == kRoleCascadeOsc;      // cascade side
+	static constexpr bool hasP = ROLE == kRoleBoth || ROLE == kRoleParallel || ROLE == kRoleParallelOnly;   // noise + parallel bank
+	static constexpr bool hasO = ROLE == kRoleBoth || ROLE == kRoleParallel || ROLE == kRoleCascadeOsc;     // the two oscillators
 	static constexpr int R0 = hasC ? 0 : kResParallel;
 	static constexpr int R1 = hasP ? kNumResonators : kResParallel;
 };
@@ -174,19 +179,19 @@ KLATT_HD constexpr bool directOfCascade(int i) {
 	       i == dAspirationAmplitude || i == dCaNP || i == dPreFormantGain || i == dOutputGain;
 }
 KLATT_HD constexpr bool directOfParallel(int i) {
-	return i == dVibratoPitchOffset || i == dFricationAmplitude || (i >= dPa1 && i <= dPa6) || i == dParallelBypass ||
-	       i == dPreFormantGain;
+	return i == dFricationAmplitude || (i >= dPa1 && i <= dPa6) || i == dParallelBypass || i == dPreFormantGain;
 }
 template <int ROLE> KLATT_HD constexpr bool roleUsesDirect(int i) {
-	return (RoleTraits<ROLE>::hasC && directOfCascade(i)) || (RoleTraits<ROLE>::hasP && directOfParallel(i));
+	return (RoleTraits<ROLE>::hasC && directOfCascade(i)) || (RoleTraits<ROLE>::hasP && directOfParallel(i)) ||
+	       (RoleTraits<ROLE>::hasO && i == dVibratoPitchOffset);
 }
 
 // hand-over between the two sides when they share a thread: plain members
 struct XchgSelf {
 	uint32_t wA_;
-	float par_, vib_;
-	KLATT_HD void put(uint32_t, uint32_t wA, float par, float vib) { wA_ = wA; par_ = par; vib_ = vib; }
-	KLATT_HD void get(uint32_t, uint32_t &wA, float &par, float &vib) const { wA = wA_; par = par_; vib = vib_; }
+	float par_, voice_;
+	KLATT_HD void put(uint32_t, uint32_t wA, float par, float voice) { wA_ = wA; par_ = par; voice_ = voice; }
+	KLATT_HD void get(uint32_t, uint32_t &wA, float &par, float &voice) const { wA = wA_; par = par_; voice = voice_; }
 	KLATT_HD void sync() {}
 };
 
@@ -199,7 +204,8 @@ struct DspState {  // what every tick reads AND writes
 	float aspLast, fricLast;
 	uint64_t vibratoPos;
 	int64_t vibInc;
-	double pitchPos, pitch, pitchInc;
+	double pitchPos;         // glottal phase in cycles, FP64 like the reference's (parallel side)
+	double pitch, pitchInc;  // cur.voicePitch and its per-tick increment (parallel side)
 };
 
 struct CoefF32 {  // what a tick only reads: a pure function of (zeta, direct params)
@@ -243,9 +249,9 @@ KLATT_HD void buildCoef(CoefF32 &C, const float *zre, const float *zim, const fl
 #pragma unroll
 		for (int k = 0; k < 6; ++k) C.pa[k] = dir[dPa1 + k];
 		C.bypass = dir[dParallelBypass];
-		C.vpo = dir[dVibratoPitchOffset];
 		C.fricGain = ((0.3f * kDrawScale) * dir[dFricationAmplitude]) * C.halfGain;
 	}
+	if (T::hasO) C.vpo = dir[dVibratoPitchOffset];
 }
 
 // one tick of the pole recurrences: zeta' = zeta + omega - zeta*omega (a no-op when omega == 0)
@@ -298,6 +304,20 @@ KLATT_HD float bitsToFloat(uint32_t u) {
 #endif
 }
 
+// phase increment in cycles -> 2^-64-cycle fixed point (|x| < 0.5, i.e. |pitch| < sampleRate/2; saturates beyond).
+// Used by the time-parallel path (klatt_long.cu), where the phase must be summed associatively.
+KLATT_HD int64_t cyclesToFixed(double x) {
+#ifdef __CUDA_ARCH__
+	return __double2ll_rn(x * 18446744073709551616.0);
+#else
+	double y = x * 18446744073709551616.0;
+	if (y != y) return (int64_t)0x8000000000000000ull;
+	if (y >= 9223372036854775807.0) return 0x7fffffffffffffffll;
+	if (y <= -9223372036854775808.0) return (int64_t)0x8000000000000000ull;
+	return (int64_t)nearbyint(y);
+#endif
+}
+
 // x - trunc(x): the reference's fmod(x, 1) (src/speechWaveGenerator.cpp:55) without a branch; exact for |x| < 2^31
 KLATT_HD double fracRef(double x) {
 #ifdef __CUDA_ARCH__
@@ -320,23 +340,33 @@ KLATT_HD float parallelSide(DspState &S, const CoefF32 &C, uint32_t wF) {
 	return fmaf(pin - par, C.bypass, par);
 }
 
-// vibrato oscillator (reference src/speechWaveGenerator.cpp:73): the relative pitch offset of this tick
-KLATT_HD float vibratoSide(DspState &S, const CoefF32 &C) {
+// the two oscillators (reference src/speechWaveGenerator.cpp:73-74, :54-58): vibrato, pitch glide, glottal phase;
+// returns the sawtooth value in [0, 1).  The phase is accumulated exactly like the reference does it --
+// fmod((pitch*vibrato)/sampleRate + pos, 1) in double, with a true division -- because a pitch whose period is a whole
+// number of samples (150 Hz at 22 050 Hz) makes the wrap instant a matter of the last bit of that sum, and a wrap
+// that lands one sample apart from the reference's is a full-scale error once per period.
+// x / sr, correctly rounded, from the correctly rounded reciprocal (Markstein): q = RN(x*y), r = x - q*sr exactly (FMA),
+// RN(q + r*y) is the IEEE quotient.  Three FP64 instructions instead of a division sequence.
+KLATT_HD double divideBySampleRate(double x, double srD, double srInv) {
+	double q = x * srInv;
+	double r = fma(-q, srD, x);
+	return fma(r, srInv, q);
+}
+
+KLATT_HD float oscillatorSide(DspState &S, const CoefF32 &C, double srD, double srInv) {
 	S.vibratoPos += (uint64_t)S.vibInc;
 	// cycles in [-0.5, 0.5), rounded to nearest: a truncated phase is a systematic pitch error while a slow vibrato
 	// sits inside one quantisation step
 	float vph = (float)(int32_t)(uint32_t)(S.vibratoPos >> 32) * 2.3283064365386963e-10f;
-	return (sinTurns(vph) * 0.06f) * C.vpo;
+	float vib = (sinTurns(vph) * 0.06f) * C.vpo;
+	S.pitch += S.pitchInc;
+	double pos = fracRef(divideBySampleRate(S.pitch * ((double)vib + 1.0), srD, srInv) + S.pitchPos);
+	S.pitchPos = pos;
+	return (float)pos;
 }
 
 // cascade side (reference src/speechWaveGenerator.cpp:203-204, :72-86, :147-158) and the final mix (:207-208)
-KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, float vib, double srInv) {
-	// ---- glottal phase (:74, :55) ----
-	S.pitch += S.pitchInc;
-	double base = S.pitch * srInv;
-	double pos = fracRef(S.pitchPos + fma(base, (double)vib, base));
-	S.pitchPos = pos;
-	float voice = (float)pos;
+KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, float voice) {
 	// ---- aspiration noise + turbulence (:40, :75-80) ----
 	float uA = bitsToFloat(0x4B000000u | (wA >> 9)) - 8388608.0f;
 	S.aspLast = fmaf(0.75f, S.aspLast, uA);
@@ -389,22 +419,24 @@ KLATT_HD void loadDspState(DspState &S, const GenStateF32 &gs) {
 	using T = RoleTraits<ROLE>;
 #pragma unroll
 	for (int r = T::R0; r < T::R1; ++r) { S.y[r] = gs.y[r]; S.d[r] = gs.d[r]; }
-	if (T::hasC) {
-		S.aspLast = gs.aspLast;
+	if (T::hasC) S.aspLast = gs.aspLast;
+	if (T::hasP) S.fricLast = gs.fricLast;
+	if (T::hasO) {
+		S.vibratoPos = gs.vibratoPos; S.vibInc = gs.vibInc;
 		S.pitchPos = gs.pitchPos; S.pitch = gs.pitch; S.pitchInc = gs.pitchInc;
 	}
-	if (T::hasP) { S.fricLast = gs.fricLast; S.vibratoPos = gs.vibratoPos; S.vibInc = gs.vibInc; }
 }
 template <int ROLE>
 KLATT_HD void storeDspState(GenStateF32 &gs, const DspState &S) {
 	using T = RoleTraits<ROLE>;
 #pragma unroll
 	for (int r = T::R0; r < T::R1; ++r) { gs.y[r] = S.y[r]; gs.d[r] = S.d[r]; }
-	if (T::hasC) {
-		gs.aspLast = S.aspLast;
+	if (T::hasC) gs.aspLast = S.aspLast;
+	if (T::hasP) gs.fricLast = S.fricLast;
+	if (T::hasO) {
+		gs.vibratoPos = S.vibratoPos; gs.vibInc = S.vibInc;
 		gs.pitchPos = S.pitchPos; gs.pitch = S.pitch; gs.pitchInc = S.pitchInc;
 	}
-	if (T::hasP) { gs.fricLast = S.fricLast; gs.vibratoPos = S.vibratoPos; gs.vibInc = S.vibInc; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -424,7 +456,7 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 	using T = RoleTraits<ROLE>;
 	StreamState *st = desc.state;
 	GenStateF32 &gs = st->gen.f32;
-	const double srInv = 1.0 / (double)sampleRate;
+	const double srD = (double)sampleRate, srInv = 1.0 / (double)sampleRate;
 	DspState S;
 	loadDspState<ROLE>(S, gs);
 	CoefF32 C;
@@ -452,16 +484,17 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 #pragma unroll
 				for (int h = 0; h < 2; ++h) {
 					uint32_t wA = 0;
-					float par = 0.0f, vib = 0.0f;
+					float par = 0.0f, voice = 0.0f;
 					if (T::hasP) {
 						wA = blk.w[2 * h];
 						par = parallelSide(S, C, blk.w[2 * h + 1]);
-						vib = vibratoSide(S, C);
-						if (!T::hasC) xc.put(t + k + h, wA, par, vib);
+						if (T::hasO && !T::hasC) voice = oscillatorSide(S, C, srD, srInv);
+						if (!T::hasC) xc.put(t + k + h, wA, par, voice);
 					}
 					if (T::hasC) {
-						if (!T::hasP) xc.get(t + k + h, wA, par, vib);
-						out.push(cascadeSide(S, C, wA, par, vib, srInv));
+						if (!T::hasP) xc.get(t + k + h, wA, par, voice);
+						if (T::hasO) voice = oscillatorSide(S, C, srD, srInv);
+						out.push(cascadeSide(S, C, wA, par, voice));
 					}
 				}
 			}
@@ -469,10 +502,10 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 			for (int k = 0; k < kGroupTicks; ++k) {
 				uint32_t wA, wF;
 				ns.draw(noise, desc, streamId, gen + k, wA, wF);
-				float par = parallelSide(S, C, wF);
-				float vib = vibratoSide(S, C);
-				if (!T::hasC) xc.put(t + k, wA, par, vib);
-				if (T::hasC) out.push(cascadeSide(S, C, wA, par, vib, srInv));
+				float par = parallelSide(S, C, wF), voice = 0.0f;
+				if (T::hasO) voice = oscillatorSide(S, C, srD, srInv);
+				if (!T::hasC) xc.put(t + k, wA, par, voice);
+				if (T::hasC) out.push(cascadeSide(S, C, wA, par, voice));
 			}
 		}
 		gen += kGroupTicks;
@@ -500,14 +533,14 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 	StreamState *st = desc.state;
 	FrameMgrState &fm = st->fm;
 	GenStateF32 &gs = st->gen.f32;
-	const double srInv = 1.0 / (double)sampleRate;
+	const double srD = (double)sampleRate, srInv = 1.0 / (double)sampleRate;
 	const bool planned = desc.plans != nullptr;  // always true for the split roles
 
 	uint32_t counter = fm.counter, qHead = fm.qHead;
 	uint32_t oldM = fm.oldM, newM = fm.newM, newF = fm.newF;
 	int32_t lastUserIndex = fm.lastUserIndex;
 	bool hasNew = fm.hasNew, curIsNull = fm.curIsNull, oldIsNull = fm.oldIsNull, newIsNull = fm.newIsNull;
-	// (fm.oldInc / fm.newInc / gs.pitchOld / gs.pitchNew are only touched on event ticks, by the cascade side: they stay
+	// (fm.oldInc / fm.newInc / gs.pitchOld / gs.pitchNew are only touched on event ticks, by the parallel side: they stay
 	// in memory instead of occupying eight registers)
 	uint32_t nextEvent = gs.nextEvent;
 	bool holdArmed = gs.holdArmed != 0;
@@ -575,7 +608,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						if (ROLE == kRoleBoth && !planned)
 							for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
 						oldM = newM; oldIsNull = newIsNull;
-						if (T::hasC) fm.oldInc = fm.newInc;
+						if (T::hasO) fm.oldInc = fm.newInc;
 						hasNew = false;
 						S.pitchInc = 0.0;
 						nextEvent = counter + 1;  // next tick: first hold tick, or the next pop
@@ -588,13 +621,13 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						for (int i = 0; i < kNumDirect; ++i)
 							if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dir0[i]; dstep[i] = plan->dirStep[i]; }
 						kf = 0.0f; kfStep = 1.0f;
-						if (T::hasP) { S.vibInc = plan->vibInc0; vibIncStep = plan->vibIncStep; }
-						if (T::hasC) {
+						if (T::hasO) {
+							S.vibInc = plan->vibInc0; vibIncStep = plan->vibIncStep;
 							const double pitchOld = gs.pitchOld, pitchNew = gs.pitchNew;
 							S.pitch = pitchOld;
 							S.pitchInc = (pitchNew != pitchNew) ? 0.0 : (pitchNew - pitchOld) / (double)newF;
-							n0Inv = plan->n0InvFade != 0;
 						}
+						if (T::hasC) n0Inv = plan->n0InvFade != 0;
 						coarseAt = 0x80000000u;
 						nextEvent = newF;
 					} else {  // counter == newF, ratio == 1: land exactly on the planned end values
@@ -606,13 +639,13 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						for (int i = 0; i < kNumDirect; ++i)
 							if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dirFinal[i]; dstep[i] = 0.0f; }
 						kf = 0.0f; kfStep = 0.0f;
-						if (T::hasC) {
+						if (T::hasC) n0Inv = plan->n0InvFinal != 0;
+						if (T::hasO) {
 							const double pitchOld = gs.pitchOld, pitchNew = gs.pitchNew;
 							S.pitch = (pitchNew != pitchNew) ? pitchOld : pitchOld + ((pitchNew - pitchOld) * 1.0);
 							S.pitchInc = 0.0;
-							n0Inv = plan->n0InvFinal != 0;
+							S.vibInc = plan->vibIncFinal; vibIncStep = 0;
 						}
-						if (T::hasP) { S.vibInc = plan->vibIncFinal; vibIncStep = 0; }
 						nextEvent = newF + 1;
 					}
 				} else if (counter > oldM) {  // :54
@@ -657,7 +690,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						if (ux != -1) lastUserIndex = ux;  // :69
 						counter = 0;                       // :70
 						pitchNew += (newInc * (double)newF);  // :71
-						if (T::hasC) { gs.pitchOld = pitchOld; gs.pitchNew = pitchNew; fm.newInc = newInc; }
+						if (T::hasO) { gs.pitchOld = pitchOld; gs.pitchNew = pitchNew; fm.newInc = newInc; }
 						if (planned) {
 							plan = desc.plans + rel;
 						} else if (ROLE == kRoleBoth) {  // plan the fade here (double precision, once per request)
@@ -673,7 +706,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						curIsNull = true;  // :73-75
 					}
 				} else {  // :76-79 first hold tick: only the pitch glides from here on
-					if (T::hasC) S.pitchInc = fm.oldInc;
+					if (T::hasO) S.pitchInc = fm.oldInc;
 					holdArmed = true;
 					nextEvent = oldM + 1;
 				}
@@ -684,7 +717,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 			// ================= the straight-line per-tick update (all increments are zero outside fades) ===========
 			kf += kfStep;
 			stepPoles<ROLE>(zre, zim, wre, wim);
-			if (T::hasP) S.vibInc += vibIncStep;
+			if (T::hasO) S.vibInc += vibIncStep;
 			if ((gen & (uint64_t)(kCoarseTicks - 1)) == 0 && kfStep != 0.0f) {
 				// drift control, on a grid of ABSOLUTE sample indices (identical for every chunking of the render, and
 				// the same loop iteration for every lane of a batch that started together)
@@ -714,18 +747,19 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 			}
 			// ================= noise draws (two per generated sample) and the DSP =================
 			uint32_t wA = 0;
-			float par = 0.0f, vib = 0.0f;
+			float par = 0.0f, voice = 0.0f;
 			if (T::hasP) {
 				uint32_t wF;
 				ns.draw(noise, desc, streamId, gen, wA, wF);
 				par = parallelSide(S, C, wF);
-				vib = vibratoSide(S, C);
-				if (!T::hasC) xc.put(t, wA, par, vib);
+				if (T::hasO && !T::hasC) voice = oscillatorSide(S, C, srD, srInv);
+				if (!T::hasC) xc.put(t, wA, par, voice);
 			}
 			gen++;
 			if (T::hasC) {
-				if (!T::hasP) xc.get(t, wA, par, vib);
-				out.push(cascadeSide(S, C, wA, par, vib, srInv));
+				if (!T::hasP) xc.get(t, wA, par, voice);
+				if (T::hasO) voice = oscillatorSide(S, C, srD, srInv);
+				out.push(cascadeSide(S, C, wA, par, voice));
 			}
 			produced++;
 			if (produced == myTicks) active = false;

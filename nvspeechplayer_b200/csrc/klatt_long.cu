@@ -8,8 +8,9 @@
 //                   the hold-phase pitch glide is an arithmetic progression (src/frame.cpp:77).
 //   vibrato phase   64-bit fixed point and piecewise-linear increments: an exact arithmetic series per request.
 //   glottal phase   needs the sum of all earlier per-tick increments (src/speechWaveGenerator.cpp:55,74), which has no
-//                   closed form under vibrato: every chunk sums its own increments in FP64 (klatt_long_phase_kernel) and
-//                   an exclusive scan over chunks gives the phase each chunk starts from.
+//                   closed form under vibrato: every chunk sums its own increments (FP64 arithmetic per tick, converted to
+//                   2^-64-cycle fixed point, so the sums are exact and associative: klatt_long_phase_kernel) and an
+//                   exclusive scan over chunks (warp shuffles) gives the phase each chunk starts from.
 //   noise           Philox is random access; the 0.75-pole colouring filter (src/speechWaveGenerator.cpp:40) forgets its
 //                   past within 64 ticks (0.75^64 = 1e-8), so a chunk warms it up on the 64 ticks before its first one.
 //   resonators      each two-pole section is LINEAR in its state for a given input: over a chunk,
@@ -276,13 +277,13 @@ struct SourceWalk {
 		loadReq(L, full);
 		vibPos = L.vibPosStart[cur.j] + vw.before(cur.c, cur.F);
 	}
-	// phase increment of this tick, in cycles (FP64)
-	__device__ __forceinline__ double phaseInc(const LongStream &L, double srInv) {
+	// phase increment of this tick, 2^-64 cycles (FP64 arithmetic, exact integer from there on)
+	__device__ __forceinline__ uint64_t phaseInc(const LongStream &L, double srInv) {
 		vibPos += (uint64_t)vw.inc(cur.c, cur.F);
 		float vph = (float)(int32_t)(uint32_t)(vibPos >> 32) * 2.3283064365386963e-10f;
 		float vib = (sinTurns(vph) * 0.06f) * vpo.at(cur.c, cur.F);
 		double base = pitchAt(L, cur.j, cur.c, cur.F) * srInv;
-		return fma(base, (double)vib, base);
+		return (uint64_t)cyclesToFixed(fma(base, (double)vib, base));
 	}
 	__device__ __forceinline__ void next(const LongStream &L, bool full) {
 		cur.next(L);
@@ -292,7 +293,7 @@ struct SourceWalk {
 
 // pass 1: the phase every chunk advances by (fraction of a cycle)
 __global__ void __launch_bounds__(128)
-klatt_long_phase_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, double *__restrict__ advance) {
+klatt_long_phase_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, uint64_t *__restrict__ advance) {
 	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
 	if (ch >= numChunks) return;
 	const uint64_t total = L.start[L.nReq];
@@ -301,27 +302,53 @@ klatt_long_phase_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, d
 	const double srInv = 1.0 / (double)L.sampleRate;
 	SourceWalk w;
 	w.seek(L, t0, false);
-	double pos = 0.0;
+	uint64_t pos = 0;
 	for (uint64_t t = t0; t < t1; ++t) {
-		pos = fracRef(pos + w.phaseInc(L, srInv));
+		pos += w.phaseInc(L, srInv);
 		w.next(L, false);
 	}
 	advance[ch] = pos;
 }
 
-// exclusive scan of the per-chunk phase advances (one thread: numChunks dependent FP64 additions)
-__global__ void klatt_long_phase_scan_kernel(const double *__restrict__ advance, uint32_t numChunks, double *__restrict__ startPhase) {
-	if (blockIdx.x != 0 || threadIdx.x != 0) return;
-	double pos = 0.0;
-	for (uint32_t c = 0; c < numChunks; ++c) {
+// exclusive scan of the per-chunk phase advances: 64-bit integer sums modulo one cycle, exact.  One block; every thread
+// sums a contiguous run, the run totals are scanned with warp shuffles, the runs are replayed from their prefix.
+__global__ void __launch_bounds__(1024)
+klatt_long_phase_scan_kernel(const uint64_t *__restrict__ advance, uint32_t numChunks, uint64_t *__restrict__ startPhase) {
+	__shared__ uint64_t warpTotal[32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t per = (numChunks + 1023) / 1024;
+	const uint32_t c0 = (uint32_t)tid * per < numChunks ? (uint32_t)tid * per : numChunks;
+	const uint32_t c1 = c0 + per < numChunks ? c0 + per : numChunks;
+	uint64_t run = 0;
+	for (uint32_t c = c0; c < c1; ++c) run += advance[c];
+	uint64_t inc = run;
+#pragma unroll
+	for (int delta = 1; delta < 32; delta <<= 1) {
+		uint64_t up = __shfl_up_sync(0xffffffffu, inc, delta);
+		if (lane >= delta) inc += up;
+	}
+	if (lane == 31) warpTotal[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		uint64_t w = warpTotal[lane];
+#pragma unroll
+		for (int delta = 1; delta < 32; delta <<= 1) {
+			uint64_t up = __shfl_up_sync(0xffffffffu, w, delta);
+			if (lane >= delta) w += up;
+		}
+		warpTotal[lane] = w;
+	}
+	__syncthreads();
+	uint64_t pos = inc - run + (warp > 0 ? warpTotal[warp - 1] : 0);
+	for (uint32_t c = c0; c < c1; ++c) {
 		startPhase[c] = pos;
-		pos = fracRef(pos + advance[c]);
+		pos += advance[c];
 	}
 }
 
 // pass 2: the two excitation signals of every tick: cascade input ci (:204, :148) and parallel input pin (:206, :171)
 __global__ void __launch_bounds__(128)
-klatt_long_source_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, const double *__restrict__ startPhase,
+klatt_long_source_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, const uint64_t *__restrict__ startPhase,
                          float *__restrict__ ci, float *__restrict__ pin) {
 	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
 	if (ch >= numChunks) return;
@@ -339,15 +366,15 @@ klatt_long_source_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, 
 	}
 	SourceWalk w;
 	w.seek(L, t0, true);
-	double pos = startPhase[ch];
+	uint64_t pos = startPhase[ch];
 	Philox4 blk;
 	blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
 	for (uint64_t t = t0; t < t1; ++t) {
 		if ((t & 1) == 0 || t == t0) blk = noiseBlock(L.seed, L.streamId, t >> 1);
 		const uint32_t wA = (t & 1) ? blk.w[2] : blk.w[0], wF = (t & 1) ? blk.w[3] : blk.w[1];
-		pos = fracRef(pos + w.phaseInc(L, srInv));
+		pos += w.phaseInc(L, srInv);
 		const uint32_t c = w.cur.c, F = w.cur.F;
-		const float voice = (float)pos;
+		const float voice = bitsToFloat(0x3F800000u | (uint32_t)(pos >> 41)) - 1.0f;
 		aspLast = fmaf(0.75f, aspLast, bitsToFloat(0x4B000000u | (wA >> 9)) - 8388608.0f);
 		float asp = aspLast * (0.2f * kDrawScale);
 		float turb = asp * w.vta.at(c, F);
@@ -576,14 +603,14 @@ cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream) {
 }
 
 // signals: five float arrays of totalTicks (+ padding): ci, pin, par, xa, xb.  maps / startState: numChunks * 6.
-cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, double *advance,
-                                  double *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
+cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
+                                  uint64_t *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
                                   float2 *startState, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream) {
 	if (totalTicks == 0) return cudaSuccess;
 	const uint32_t numChunks = (uint32_t)((totalTicks + chunkTicks - 1) / chunkTicks);
 	const dim3 grid((numChunks + 127) / 128), block(128);
 	klatt_long_phase_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, advance);
-	klatt_long_phase_scan_kernel<<<1, 1, 0, stream>>>(advance, numChunks, startPhase);
+	klatt_long_phase_scan_kernel<<<1, 1024, 0, stream>>>(advance, numChunks, startPhase);
 	klatt_long_source_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, startPhase, ci, pin);
 	// parallel bank
 	klatt_long_stage_kernel<kStageParallel, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, maps, nullptr, nullptr, nullptr);
