@@ -11,6 +11,7 @@
 //
 // There is no CPU synthesis path in this library: every sample comes out of a CUDA kernel.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +38,12 @@ cudaError_t launchKlattF32Rounds(const StreamDesc *descs, uint32_t numStreams, i
                                  uint32_t *listGen, uint32_t *counters, int16_t *scratchRow, cudaStream_t stream, uint32_t numGroups,
                                  cudaStream_t *lanes, cudaEvent_t evStart, cudaEvent_t *evFork, cudaEvent_t *evJoin,
                                  unsigned long long *launchCounter);
+cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
+                                uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride, uint32_t *samplesWritten,
+                                StreamResult *results, NoiseConfig noise, uint32_t *ring, uint32_t ringCap, void *ctlMem,
+                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, cudaStream_t stream,
+                                unsigned long long *launchCounter);
+int klattF32SchedBlocksPerSm();
 cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_t totalRequests, const double *frames,
                             const uint32_t *fadeDur, const uint8_t *isNull, int sampleRate, FadePlanF32 *plans,
                             cudaStream_t stream);
@@ -177,6 +184,10 @@ __global__ void build_descs_kernel(StreamDesc *descs, StreamState *states, const
 struct RoundsCtx {
 	static constexpr uint32_t kMaxGroups = 8;
 	DevBuf listHold, listGen, counters, scratchRow;
+	DevBuf ring, ctl;            // stream scheduler (persistent kernel, klatt_f32_sched.cu)
+	bool persistent = false;     // NVSP_SCHED=persistent selects it; the default is the round-based launch sequence
+	uint32_t *hostFault = nullptr;  // pinned: the scheduler watchdog's verdict of the last call
+	uint32_t schedHoldTicks = 256, schedGenTicks = 256, schedBlocks = 0;
 	cudaStream_t lanes[2 * kMaxGroups] = {};
 	cudaEvent_t evStart = nullptr, evFork[kMaxGroups] = {}, evJoin[kMaxGroups] = {};
 	uint32_t holdTicks = 512, genTicks = 256, minStreams = 2048, groups = 4;
@@ -193,6 +204,20 @@ struct RoundsCtx {
 		holdTicks = std::max<uint32_t>(envU("NVSP_HOLD_TICKS", 512) & ~63u, 64);
 		minStreams = envU("NVSP_ROUNDS_MIN_STREAMS", 2048);
 		groups = std::min<uint32_t>(std::max<uint32_t>(envU("NVSP_GROUPS", 4), 1), kMaxGroups);
+		{
+			const char *e = getenv("NVSP_SCHED");
+			persistent = e && strcmp(e, "persistent") == 0;
+			schedGenTicks = std::max<uint32_t>(envU("NVSP_SCHED_GEN_TICKS", 256) & ~63u, 64);
+			schedHoldTicks = std::max<uint32_t>(envU("NVSP_SCHED_HOLD_TICKS", 256) & ~63u, 64);
+			int dev = 0, sms = 0;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+			const int perSm = klattF32SchedBlocksPerSm();
+			schedBlocks = envU("NVSP_SCHED_BLOCKS", (uint32_t)(sms * std::max(perSm, 1)));
+			if (getenv("NVSP_VERBOSE"))
+				fprintf(stderr, "[nvspeechplayer_b200] scheduler: %d SMs x %d blocks, %u blocks, hold %u / general %u ticks\n", sms, perSm,
+				        schedBlocks, schedHoldTicks, schedGenTicks);
+		}
 		if (!cudaOk(cudaEventCreateWithFlags(&evStart, cudaEventDisableTiming), "cudaEventCreate")) return false;
 		for (uint32_t g = 0; g < groups; ++g) {
 			if (!cudaOk(cudaStreamCreateWithFlags(&lanes[2 * g], cudaStreamNonBlocking), "cudaStreamCreate")) return false;
@@ -204,7 +229,9 @@ struct RoundsCtx {
 		return true;
 	}
 	void destroy() {
-		listHold.release(); listGen.release(); counters.release(); scratchRow.release();
+		listHold.release(); listGen.release(); counters.release(); scratchRow.release(); ring.release(); ctl.release();
+		if (hostFault) cudaFreeHost(hostFault);
+		hostFault = nullptr;
 		if (evStart) cudaEventDestroy(evStart);
 		for (uint32_t g = 0; g < kMaxGroups; ++g) {
 			if (evFork[g]) cudaEventDestroy(evFork[g]);
@@ -227,6 +254,21 @@ static cudaError_t launchRender(int precision, const StreamDesc *descs, uint32_t
 	if (precision == kPrecisionF64) {
 		if (launchCounter) ++*launchCounter;
 		return launchKlattF64(descs, n, sampleRate, sampleCount, out, rowStride, written, results, noise, stream);
+	}
+	if (rc && planned && rc->init() && rc->persistent && n >= rc->minStreams && sampleCount > rc->schedGenTicks) {
+		uint32_t cap = 64;
+		while (cap < 2 * n) cap <<= 1;
+		if (!rc->hostFault) {
+			if (cudaMallocHost((void **)&rc->hostFault, sizeof(uint32_t)) != cudaSuccess) return cudaErrorMemoryAllocation;
+			*rc->hostFault = 0;
+		}
+		if (*rc->hostFault) return cudaErrorLaunchTimeout;  // an earlier call of this batch tripped the watchdog
+		if (!rc->ring.reserve(sizeof(uint32_t) * 2 * (size_t)cap) || !rc->ctl.reserve(2048) ||
+		    !rc->scratchRow.reserve(sizeof(int16_t) * (size_t)std::max(rc->schedHoldTicks, rc->holdTicks)))
+			return cudaErrorMemoryAllocation;
+		return launchKlattF32Sched(descs, n, sampleRate, sampleCount, rc->schedHoldTicks, rc->schedGenTicks, out, rowStride, written,
+		                           results, noise, rc->ring.as<uint32_t>(), cap, rc->ctl.p, rc->scratchRow.as<int16_t>(),
+		                           rc->schedBlocks, rc->hostFault, stream, launchCounter);
 	}
 	if (rc && planned && rc->init() && n >= rc->minStreams && sampleCount > rc->genTicks) {
 		const uint32_t rounds = (sampleCount + rc->genTicks - 1) / rc->genTicks;
@@ -316,6 +358,9 @@ static long long renderToHost(HostPipe &pipe, int precision, const StreamDesc *d
 	}
 	std::vector<uint32_t> total(n, 0);
 	uint32_t numChunks = (sampleCount + chunk - 1) / chunk;
+	const bool verbose = getenv("NVSP_VERBOSE") != nullptr;
+	auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	const double tStart = now();
 	auto harvest = [&](uint32_t c) -> bool {  // wait for chunk c's copies and fold its results
 		int b = c & 1;
 		if (!cudaOk(cudaEventSynchronize(pipe.copyDone[b]), "cudaEventSynchronize")) return false;
@@ -324,24 +369,47 @@ static long long renderToHost(HostPipe &pipe, int precision, const StreamDesc *d
 		if (lastResults && c + 1 == numChunks) memcpy(lastResults, r, sizeof(StreamResult) * (size_t)n);
 		return true;
 	};
+	std::vector<cudaEvent_t> tev;
+	if (verbose) {
+		tev.resize(4 * (size_t)numChunks);
+		for (auto &e : tev) cudaEventCreate(&e);
+	}
 	for (uint32_t c = 0; c < numChunks; ++c) {
 		int b = c & 1;
 		uint32_t t0 = c * chunk, len = std::min(chunk, sampleCount - t0);
+		const double tA = now();
 		if (c >= 2 && !harvest(c - 2)) return -1;  // staging buffer b is free again
+		const double tB = now();
+		if (verbose) cudaEventRecord(tev[4 * c + 0], pipe.compute);
 		CU(launchRender(precision, dDescs, n, sampleRate, len, pipe.stage[b].as<int16_t>(), stride, nullptr,
 		                pipe.res[b].as<StreamResult>(), noise, pipe.compute, &pipe.rounds, planned, launchCounter));
+		if (verbose) cudaEventRecord(tev[4 * c + 1], pipe.compute);
 		CU(cudaEventRecord(pipe.kernelDone[b], pipe.compute));
 		CU(cudaStreamWaitEvent(pipe.copy, pipe.kernelDone[b], 0));
+		if (verbose) cudaEventRecord(tev[4 * c + 2], pipe.copy);
 		CU(cudaMemcpy2DAsync(hostOut + t0, (size_t)sampleCount * sizeof(int16_t), pipe.stage[b].p,
 		                     stride * sizeof(int16_t), (size_t)len * sizeof(int16_t), n, cudaMemcpyDeviceToHost, pipe.copy));
 		CU(cudaMemcpyAsync(pipe.hostRes + (size_t)b * n, pipe.res[b].p, sizeof(StreamResult) * (size_t)n,
 		                   cudaMemcpyDeviceToHost, pipe.copy));
+		if (verbose) cudaEventRecord(tev[4 * c + 3], pipe.copy);
 		CU(cudaEventRecord(pipe.copyDone[b], pipe.copy));
-		// the next kernel that reuses staging buffer b must wait for this copy
-		CU(cudaStreamWaitEvent(pipe.compute, pipe.copyDone[b], 0));
+		// (the kernel that reuses staging buffer b is chunk c+2: harvest(c) above has waited for this copy on the host by
+		// then, so the compute stream needs no wait of its own -- and chunk c+1 must NOT wait for it)
+		if (verbose) fprintf(stderr, "[renderToHost] chunk %u/%u len %u: t=%.2f ms, waited %.2f ms for chunk-2, enqueue %.2f ms\n", c, numChunks, len,
+		                     tA - tStart, tB - tA, now() - tB);
 	}
 	for (uint32_t c = (numChunks >= 2 ? numChunks - 2 : 0); c < numChunks; ++c)
 		if (!harvest(c)) return -1;
+	if (verbose) {
+		fprintf(stderr, "[renderToHost] done at t=%.2f ms\n", now() - tStart);
+		for (uint32_t c = 0; c < numChunks; ++c) {
+			float k0, k1, c0, c1;
+			cudaEventElapsedTime(&k0, tev[0], tev[4 * c + 0]); cudaEventElapsedTime(&k1, tev[0], tev[4 * c + 1]);
+			cudaEventElapsedTime(&c0, tev[0], tev[4 * c + 2]); cudaEventElapsedTime(&c1, tev[0], tev[4 * c + 3]);
+			fprintf(stderr, "[renderToHost]   chunk %u: kernel %.2f..%.2f ms, copy %.2f..%.2f ms\n", c, k0, k1, c0, c1);
+		}
+		for (auto &e : tev) cudaEventDestroy(e);
+	}
 	long long sum = 0;
 	for (uint32_t s = 0; s < n; ++s) {
 		sum += total[s];

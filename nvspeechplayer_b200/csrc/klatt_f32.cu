@@ -21,18 +21,12 @@
 #include "klatt_common.h"
 #include "klatt_f32_core.cuh"
 #include "out_writer.cuh"
+#include "klatt_f32_pair.cuh"
 
 namespace klatt {
 
 constexpr int kF32Block = 64;
 
-namespace {
-
-__device__ __forceinline__ void zeroRow(int16_t *row, uint32_t from, uint32_t to) {
-	for (uint32_t i = from; i < to; ++i) row[i] = 0;
-}
-
-}  // namespace
 
 // ---------------------------------------------------------------------------------------------------
 // plans for pre-queued batches
@@ -94,40 +88,6 @@ klatt_partition_kernel(const StreamDesc *__restrict__ descs, uint32_t firstStrea
 	if (cls == 1) listHold[baseH + __popc(mH & below)] = s;
 	if (cls == 2) listGen[baseG + __popc(mG & below)] = s;
 }
-
-// ---- the two sides of a stream in different warps of one block ------------------------------------------------
-// block = 4 warps: warps 0,1 run the cascade side of streams [64b, 64b+32) and [64b+32, 64b+64) of the list,
-// warps 2,3 the parallel side of the same streams.  Warp w and warp w+2 share one named barrier and a
-// double-buffered shared-memory hand-over of (aspiration noise word, parallel-bank output, sawtooth value) x 8 ticks x 32 lanes.
-struct XchgSmem {
-	uint32_t base;  // shared-space address of this lane's column of the pair's [2 buffers][8 ticks][32 lanes] x 16 bytes
-	uint32_t barId;
-	__device__ __forceinline__ void put(uint32_t t, uint32_t wA, float par, float voice) {
-		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %3};" ::"r"(base + (t & 15u) * 512u), "r"(wA), "r"(__float_as_uint(par)),
-		             "r"(__float_as_uint(voice)) : "memory");
-	}
-	__device__ __forceinline__ void get(uint32_t t, uint32_t &wA, float &par, float &voice) const {
-		uint32_t p, v, pad;
-		asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wA), "=r"(p), "=r"(v), "=r"(pad) : "r"(base + (t & 15u) * 512u) : "memory");
-		par = __uint_as_float(p);
-		voice = __uint_as_float(v);
-	}
-	__device__ __forceinline__ void sync() { asm volatile("bar.sync %0, 64;" ::"r"(barId) : "memory"); }
-};
-struct NullOut {
-	__device__ __forceinline__ void push(int) {}
-};
-
-// Which side a warp runs.  A warp's scheduler is warp-id % 4, so "warps 0,1 cascade / 2,3 parallel" in every block would
-// give two schedulers of an SM nothing but the (lighter, latency-bound) cascade warps and the other two nothing but the
-// (heavier) parallel warps; flipping the assignment on a hash of the block index mixes both kinds on every scheduler.
-__device__ __forceinline__ bool cascadeRole(uint32_t warp) {
-	const uint32_t flip = (blockIdx.x * 0x9E3779B9u) >> 31;
-	return ((warp >> 1) ^ flip) == 0;
-}
-
-constexpr int kPairBlock = 128;        // threads
-constexpr int kPairStreams = 64;       // streams per block
 
 // descs[numStreams] is a dummy stream (fresh state, empty queue) that the idle lanes of a partially filled warp run
 __global__ void __launch_bounds__(kPairBlock, 6)
@@ -238,6 +198,12 @@ klatt_finalize_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams,
 // ---------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------
+cudaError_t launchKlattFinalize(const StreamDesc *descs, uint32_t numStreams, uint32_t *samplesWritten, StreamResult *results,
+                                cudaStream_t stream) {
+	klatt_finalize_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, numStreams, samplesWritten, results);
+	return cudaGetLastError();
+}
+
 cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_t totalRequests, const double *frames,
                             const uint32_t *fadeDur, const uint8_t *isNull, int sampleRate, FadePlanF32 *plans,
                             cudaStream_t stream) {

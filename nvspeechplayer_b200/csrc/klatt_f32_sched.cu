@@ -1,0 +1,348 @@
+// The persistent stream scheduler of the FP32 batch path (opt-in: NVSP_SCHED=persistent; the default is the
+// round-based launch sequence of klatt_f32.cu -- measured equal in throughput on config 3).
+// Same render bodies as the round kernels (klatt_f32_core.cuh), so the same bits.
+//
+// This translation unit is compiled with -fmad=false like klatt_f32.cu AND with -Xptxas -dlcm=cg: the kernel moves a
+// stream's state between SMs without a kernel boundary in between, so no global load may be served from a stale L1
+// line.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include "klatt_common.h"
+#include "klatt_f32_core.cuh"
+#include "out_writer.cuh"
+#include "klatt_f32_pair.cuh"
+
+namespace klatt {
+
+cudaError_t launchKlattFinalize(const StreamDesc *descs, uint32_t numStreams, uint32_t *samplesWritten, StreamResult *results,
+                                cudaStream_t stream);
+
+#ifdef KLATT_SCHED_PROFILE
+#define PROF_LAP(acc) { long long t1 = clock64(); acc += t1 - t0; t0 = t1; }
+#else
+#define PROF_LAP(acc)
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// The stream scheduler: ONE persistent launch renders the whole call.
+//
+// The rounds above re-sort the streams with a kernel boundary per round: every round ends with a tail (the last blocks
+// of the slower kernel run on an emptying GPU), the two kernels of a round are only balanced on average, and a call is
+// ~10^4 launches.  Here the sorting is done by the render warps themselves.  Two device-side rings hold the streams that
+// are ready for a pure-hold chunk (class 0) or need the frame manager (class 1).  A WORKER is a cascade/parallel warp
+// pair; it claims up to 32 streams of one class, renders one chunk of them (the same renderHoldF32 / renderGeneralF32
+// as the round kernels: same arithmetic, same bits), classifies each stream's next chunk and pushes it back, until no
+// stream of the call has ticks left.  Nothing waits on another worker except through the rings, so the kernel is
+// correct for any number of resident blocks; the grid is sized to fill the GPU once.
+//
+//   ring[c][i & mask] : stream index, kRingEmpty or kRingAbandoned.  Both cursors of a ring only ever move by atomicAdd
+//                       (a claim by compare-and-swap collapses when ~10^3 workers arrive within one L2 round trip of
+//                       each other: measured 10x slower than the rounds).  Producers reserve [tail, tail+n) and write
+//                       their slots; a consumer takes a TICKET [head, head+32) -- possibly ahead of the tail -- and
+//                       each of its lanes waits for its own slot to be written, which future pushes do in ticket
+//                       order.  A lane that has waited too long abandons its slot (EMPTY -> ABANDONED by CAS; if the
+//                       CAS finds a stream, it takes it): the warp then runs with the lanes it has, or picks a ring
+//                       again if it has none.  A producer that finds its reserved slot abandoned restores it to
+//                       EMPTY and pushes again with a new reservation.  A stream is in at most one ring and tickets
+//                       run at most one batch per worker ahead, so a ring of >= 2 x numStreams slots (and far more
+//                       than 32 x workers) cannot wrap onto a live entry.
+//   state hand-over   : both warps of the pair store their half of the stream state, fence, meet at the pair's
+//                       barrier; then the cascade warp pushes.  The consumer fences after taking the slot.  This
+//                       translation unit is compiled with -dlcm=cg: global loads bypass L1, so a stream that comes
+//                       back to an SM it visited before cannot see a stale line.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kRingEmpty = 0xffffffffu, kRingAbandoned = 0xfffffffeu;
+constexpr uint32_t kClassHold = 0, kClassGen = 1, kClassExit = 2;
+
+struct SchedCtl {  // every hot word on its own 128-byte line
+	uint32_t head0, padA[31];
+	uint32_t head1, padB[31];
+	uint32_t tail0, padC[31];
+	uint32_t tail1, padD[31];
+	uint32_t remaining, padE[31];  // streams of this call that still have ticks to render
+	uint32_t fault, padF[31];      // set by the watchdog: a worker waited kWatchdogNs for work that never came
+	__device__ __forceinline__ uint32_t *head(uint32_t c) { return c ? &head1 : &head0; }
+	__device__ __forceinline__ uint32_t *tail(uint32_t c) { return c ? &tail1 : &tail0; }
+};
+
+// A worker that has found both rings empty with streams still unaccounted for, for this long, declares the call
+// failed: it zeroes `remaining` (every worker then leaves at its next look) and raises `fault`, which the host turns
+// into an error.  It cannot fire on a correct run: a chunk takes well under a millisecond.
+constexpr unsigned long long kWatchdogNs = 20ull * 1000 * 1000 * 1000;
+
+namespace {
+
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+__device__ __forceinline__ uint32_t ldVolatile(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void stVolatile(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+// class of a stream's next chunk, or kClassExit when the call is complete for it
+__device__ __forceinline__ uint32_t classifyNext(const StreamState *st, uint32_t sampleCount, uint32_t holdTicks) {
+	const GenStateF32 &gs = st->gen.f32;
+	const uint32_t pos = gs.callPos;
+	if (pos >= sampleCount || gs.callDrained != 0) return kClassExit;
+	return (sampleCount - pos >= holdTicks && canHoldF32(*st, holdTicks)) ? kClassHold : kClassGen;
+}
+
+// every lane of the calling warp: push stream s into ring cls (cls == kClassExit: nothing to push, the stream is done)
+template <bool SEED>
+__device__ __forceinline__ void schedPush(SchedCtl *ctl, uint32_t *ring, uint32_t ringCap, uint32_t cls, uint32_t s, bool valid) {
+	const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+	const unsigned mH = __ballot_sync(0xffffffffu, valid && cls == kClassHold);
+	const unsigned mG = __ballot_sync(0xffffffffu, valid && cls == kClassGen);
+	const unsigned mX = __ballot_sync(0xffffffffu, valid && cls == kClassExit);
+	uint32_t baseH = 0, baseG = 0;
+	if (lane == 0) {
+		if (mH) baseH = atomicAdd(ctl->tail(kClassHold), (uint32_t)__popc(mH));
+		if (mG) baseG = atomicAdd(ctl->tail(kClassGen), (uint32_t)__popc(mG));
+	}
+	baseH = __shfl_sync(0xffffffffu, baseH, 0);
+	baseG = __shfl_sync(0xffffffffu, baseG, 0);
+	const uint32_t mask = ringCap - 1u;
+	if (valid && cls != kClassExit) {
+		uint32_t *r = ring + cls * ringCap;
+		uint32_t idx = cls == kClassHold ? baseH + __popc(mH & below) : baseG + __popc(mG & below);
+		if (SEED) {
+			stVolatile(r + (idx & mask), s);  // nobody holds a ticket yet
+		} else {
+			while (atomicCAS(r + (idx & mask), kRingEmpty, s) != kRingEmpty) {  // the ticket of this slot was abandoned
+				stVolatile(r + (idx & mask), kRingEmpty);
+				idx = atomicAdd(ctl->tail(cls), 1u);
+			}
+		}
+	}
+	if (SEED) {  // the seed kernel counts the streams in; the workers count them out
+		if (lane == 0 && (mH | mG)) atomicAdd(&ctl->remaining, (uint32_t)__popc(mH | mG));
+	} else {
+		if (lane == 0 && mX) atomicSub(&ctl->remaining, (uint32_t)__popc(mX));
+	}
+}
+
+// All 32 lanes of a worker's cascade warp: take a ticket of 32 slots in the ring with the most work waiting (a general
+// chunk costs about as much as two hold chunks of the same length) and collect the streams.  Returns the class, or
+// kClassExit when the call is complete; s = the lane's stream, or kRingEmpty for a lane that got none.
+// Tickets are only taken from a ring that shows a backlog, so consumers run ahead of the producers by at most the
+// workers that raced for the same entries; those wait for the next pushes.
+__device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, uint32_t ringCap, uint32_t &s) {
+	const unsigned lane = threadIdx.x & 31u;
+	const uint32_t mask = ringCap - 1u;
+	for (;;) {
+		uint32_t cls = kClassExit, base = 0;
+		if (lane == 0) {
+			uint32_t backoff = 128;
+			unsigned long long idleSince = 0;
+			for (;;) {
+				const int32_t b0 = (int32_t)(ldVolatile(&ctl->tail0) - ldVolatile(&ctl->head0));
+				const int32_t b1 = (int32_t)(ldVolatile(&ctl->tail1) - ldVolatile(&ctl->head1));
+				if (b0 > 0 || b1 > 0) {
+					cls = (2 * b1 >= b0) ? kClassGen : kClassHold;
+					if ((cls == kClassGen ? b1 : b0) < 32 && (cls == kClassGen ? b0 : b1) >= 32) cls ^= 1u;  // a full warp beats the weights
+					base = atomicAdd(ctl->head(cls), 32u);
+					break;
+				}
+				if (ldVolatile(&ctl->remaining) == 0u) break;
+				__nanosleep(backoff);
+				if (backoff < 4096u) {
+					backoff *= 2u;
+				} else {  // idle at full back-off: watchdog
+					const unsigned long long now = globalTimerNs();
+					if (idleSince == 0) idleSince = now;
+					else if (now - idleSince > kWatchdogNs) {
+						stVolatile(&ctl->fault, 1u);
+						stVolatile(&ctl->remaining, 0u);
+					}
+				}
+			}
+		}
+		cls = __shfl_sync(0xffffffffu, cls, 0);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (cls == kClassExit) return kClassExit;
+		uint32_t *slot = ring + cls * ringCap + ((base + lane) & mask);
+		s = kRingEmpty;
+		bool abandoned = false;
+		for (uint32_t spins = 0;; ++spins) {
+			if (s == kRingEmpty && !abandoned) {
+				const uint32_t v = ldVolatile(slot);
+				if (v < kRingAbandoned) { s = v; stVolatile(slot, kRingEmpty); }
+			}
+			const unsigned got = __ballot_sync(0xffffffffu, s != kRingEmpty);
+			const unsigned open = __ballot_sync(0xffffffffu, s == kRingEmpty && !abandoned);
+			if (open == 0u) {
+				if (got) return cls;
+				break;  // nothing came: pick a ring again (or find the call complete)
+			}
+			// Give up on the missing lanes: after ~10 us with streams in hand (they should not wait for stragglers); with
+			// none in hand only when the call is over or the other ring has a full warp waiting.
+			uint32_t quit = 0;
+			if (lane == 0) {
+				if (got) quit = spins >= 64u;
+				else if ((spins & 15u) == 15u)
+					quit = ldVolatile(&ctl->remaining) == 0u ||
+					       (int32_t)(ldVolatile(ctl->tail(cls ^ 1u)) - ldVolatile(ctl->head(cls ^ 1u))) >= 32;
+			}
+			quit = __shfl_sync(0xffffffffu, quit, 0);
+			if (quit) {
+				if (s == kRingEmpty && !abandoned) {
+					const uint32_t v = atomicCAS(slot, kRingEmpty, kRingAbandoned);
+					if (v < kRingAbandoned) { s = v; stVolatile(slot, kRingEmpty); }
+					else abandoned = true;
+				}
+			} else {
+				__nanosleep(160);
+			}
+		}
+	}
+}
+
+}  // namespace
+
+// start of a call: reset the per-call cursors of every stream and seed the rings
+__global__ void __launch_bounds__(256)
+klatt_sched_seed_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, uint32_t sampleCount, uint32_t holdTicks,
+                        SchedCtl *ctl, uint32_t *ring, uint32_t ringCap) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = s < numStreams;
+	uint32_t cls = kClassExit;
+	if (valid) {
+		StreamState *st = descs[s].state;
+		st->gen.f32.callPos = 0;
+		st->gen.f32.callDrained = 0;
+		cls = classifyNext(st, sampleCount, holdTicks);
+	}
+	schedPush<true>(ctl, ring, ringCap, cls, s, valid);
+}
+
+#ifndef KLATT_SCHED_MINB
+#define KLATT_SCHED_MINB 4
+#endif
+__global__ void __launch_bounds__(kPairBlock, KLATT_SCHED_MINB)
+klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
+                       uint32_t holdTicks, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,
+                       int16_t *__restrict__ scratchRow, NoiseConfig noise, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap) {
+	__shared__ uint4 xbuf[2][2 * kGroupTicks * 32];
+	__shared__ uint32_t work[2][34];  // per worker: 32 stream indices, class
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, pair = warp & 1u;
+	const bool cascade = cascadeRole(warp);
+	XchgSmem xc{(uint32_t)__cvta_generic_to_shared(&xbuf[pair][lane]), 1u + pair};
+#ifdef KLATT_SCHED_PROFILE
+	long long tClaim = 0, tHold = 0, tGen = 0, tPush = 0, nHold = 0, nGen = 0, nLanes = 0;
+	long long t0 = clock64();
+#endif
+	for (;;) {
+		if (cascade) {
+			uint32_t s = kRingEmpty;
+			const uint32_t cls = schedClaim(ctl, ring, ringCap, s);
+			if (s == kRingEmpty) s = numStreams;  // idle lanes run the dummy stream
+			__threadfence();
+			work[pair][lane] = s;
+			if (lane == 0) work[pair][32] = cls;
+		}
+		xc.sync();
+		const uint32_t s = work[pair][lane], cls = work[pair][32];
+		PROF_LAP(tClaim)
+		if (cls == kClassExit) break;
+		const bool valid = s < numStreams;
+		const StreamDesc &desc = descs[s];
+		if (cls == kClassHold) {
+			if (cascade) {
+				int16_t *row = valid ? out + (size_t)s * rowStride + desc.state->gen.f32.callPos : scratchRow;
+				OutWriter ow;
+				ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0));
+				renderHoldF32<kRoleCascadeOsc>(desc, sampleRate, holdTicks, ow, noise, xc);
+			} else {
+				NullOut no;
+				renderHoldF32<kRoleParallelOnly>(desc, sampleRate, holdTicks, no, noise, xc);
+			}
+		} else {
+			const uint32_t pos = desc.state->gen.f32.callPos;
+			uint32_t ticks = 0;
+			if (valid) {
+				ticks = sampleCount - pos;
+				if (ticks > genTicks) ticks = genTicks;
+			}
+			int32_t lastUserIndex;
+			uint32_t qHead;
+			if (cascade) {
+				int16_t *row = out + (size_t)(valid ? s : 0) * rowStride;
+				OutWriter ow;
+				ow.init(row + pos, ((reinterpret_cast<uintptr_t>(row + pos) & 15u) == 0));
+				const uint32_t produced = renderGeneralF32<kRoleCascade>(desc, sampleRate, ticks, genTicks, ow, noise, xc, &lastUserIndex, &qHead);
+				ow.flush();
+				if (produced < ticks) zeroRow(row, pos + produced, sampleCount);
+			} else {
+				NullOut no;
+				renderGeneralF32<kRoleParallel>(desc, sampleRate, ticks, genTicks, no, noise, xc, &lastUserIndex, &qHead);
+			}
+		}
+		__threadfence();
+		xc.sync();  // both halves of every stream of this batch are stored
+#ifdef KLATT_SCHED_PROFILE
+		if (cls == kClassHold) { PROF_LAP(tHold) nHold++; } else { PROF_LAP(tGen) nGen++; }
+		nLanes += __popc(__ballot_sync(0xffffffffu, valid));
+#endif
+		if (cascade) {
+			const uint32_t next = valid ? classifyNext(desc.state, sampleCount, holdTicks) : kClassExit;
+			schedPush<false>(ctl, ring, ringCap, next, s, valid);
+		}
+		PROF_LAP(tPush)
+	}
+#ifdef KLATT_SCHED_PROFILE
+	if (lane == 0) {
+		unsigned long long *p = reinterpret_cast<unsigned long long *>(ctl) + 128 + (cascade ? 0 : 8);
+		atomicAdd(p + 0, (unsigned long long)tClaim); atomicAdd(p + 1, (unsigned long long)tHold);
+		atomicAdd(p + 2, (unsigned long long)tGen); atomicAdd(p + 3, (unsigned long long)tPush);
+		atomicAdd(p + 4, (unsigned long long)nHold); atomicAdd(p + 5, (unsigned long long)nGen);
+		atomicAdd(p + 6, (unsigned long long)nLanes);
+	}
+#endif
+}
+
+// One call through the stream scheduler: seed the rings, then one persistent launch.  scratch: ring[2 * ringCap]
+// (ringCap a power of two >= 2 * numStreams), ctl, scratchRow[holdTicks].  descs holds numStreams + 1 entries.
+cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
+                                uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride, uint32_t *samplesWritten,
+                                StreamResult *results, NoiseConfig noise, uint32_t *ring, uint32_t ringCap, void *ctlMem,
+                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, cudaStream_t stream,
+                                unsigned long long *launchCounter) {
+	if (numStreams == 0 || sampleCount == 0) return cudaSuccess;
+	SchedCtl *ctl = static_cast<SchedCtl *>(ctlMem);
+	cudaError_t e = cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * 2 * (size_t)ringCap, stream);
+	if (e != cudaSuccess) return e;
+	if ((e = cudaMemsetAsync(ctl, 0, 2048, stream)) != cudaSuccess) return e;
+	klatt_sched_seed_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, numStreams, sampleCount, holdTicks, ctl, ring, ringCap);
+	const uint32_t batches = (numStreams + 31) / 32;
+	// paired workers: two warps per batch, two batches per block
+	const uint32_t blocksWanted = (batches + 1) / 2, grid = blocksWanted < numBlocks ? blocksWanted : numBlocks;
+	klatt_f32_sched_kernel<<<grid, kPairBlock, 0, stream>>>(descs, numStreams, sampleRate, sampleCount, holdTicks, genTicks, out,
+	                                                         rowStride, scratchRow, noise, ctl, ring, ringCap);
+	// the watchdog's verdict travels to a pinned host word; the engine reads it at its next synchronisation point
+	if (hostFault && (e = cudaMemcpyAsync(hostFault, &ctl->fault, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+	if ((e = launchKlattFinalize(descs, numStreams, samplesWritten, results, stream)) != cudaSuccess) return e;
+	if (launchCounter) *launchCounter += 3;
+#ifdef KLATT_SCHED_PROFILE
+	{
+		unsigned long long h[16];
+		cudaStreamSynchronize(stream);
+		cudaMemcpy(h, reinterpret_cast<unsigned long long *>(ctl) + 128, sizeof(h), cudaMemcpyDeviceToHost);
+		for (int k = 0; k < 2; ++k)
+			fprintf(stderr, "[sched profile] %s warps: claim %.1f  hold %.1f  gen %.1f  push %.1f Mcycles; batches hold %llu gen %llu; lanes/batch %.2f\n",
+			        k ? "parallel" : "cascade ", h[8 * k] / 1e6, h[8 * k + 1] / 1e6, h[8 * k + 2] / 1e6, h[8 * k + 3] / 1e6, h[8 * k + 4], h[8 * k + 5],
+			        (double)h[8 * k + 6] / (double)(h[8 * k + 4] + h[8 * k + 5]));
+	}
+#endif
+	return cudaGetLastError();
+}
+
+// resident blocks of the scheduler kernel per SM (occupancy query; the grid is SMs x this)
+int klattF32SchedBlocksPerSm() {
+	int n = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, klatt_f32_sched_kernel, kPairBlock, 0) != cudaSuccess) n = 0;
+	return n;
+}
+
+}  // namespace klatt

@@ -135,16 +135,19 @@ def test_philox_noise_statistics():
 
 def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
     """The batch engine's round-based execution (phase-sorted hold / general chunks, the two sides of a stream in
-    paired warps, several stream groups in flight) renders the same bits as the one-thread-per-stream kernel,
+    paired warps, several stream groups in flight) and its persistent stream scheduler (the same chunks handed out by
+    device-side rings inside one launch) render the same bits as the one-thread-per-stream kernel,
     including streams that drain mid-call, partially filled warps and calls that end inside a chunk."""
     sr, n = 22050, 203
     streams = [workloads.random_stream(500 + s, 0.35 if s % 7 == 3 else 1.0, sr) for s in range(n)]
     fb = workloads._concat(sr, streams, np.arange(500, 500 + n, dtype=np.uint64))
     count = int(1.0 * sr)
     res = {}
-    for mode, min_streams in (("single", "100000000"), ("rounds", "1")):
+    for mode, min_streams in (("single", "100000000"), ("rounds", "1"), ("sched", "1")):
         monkeypatch.setenv("NVSP_ROUNDS_MIN_STREAMS", min_streams)
         monkeypatch.setenv("NVSP_GROUPS", "3")
+        monkeypatch.setenv("NVSP_SCHED", "persistent" if mode == "sched" else "rounds")
+        monkeypatch.setenv("NVSP_SCHED_BLOCKS", "3")  # fewer workers than stream batches: streams queue up in the rings
         b = player.Batch(sr, n, precision=player.PRECISION_FP32, seed=77, stream_ids=fb.stream_ids)
         b.set_frames_host(fb)
         parts, written = [], np.zeros(n, dtype=np.int64)
@@ -155,6 +158,9 @@ def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
         res[mode] = (np.concatenate(parts, axis=1), written, b.last_indices(), b.launch_stats()[0])
         b.close()
     assert res["rounds"][3] > res["single"][3] + 50, "the rounds path did not run"
+    assert res["sched"][3] == res["single"][3] + 2 * 3, "the stream scheduler did not run (seed + workers + finalize per call)"
+    for k in range(3):
+        np.testing.assert_array_equal(res["single"][k], res["sched"][k])
     np.testing.assert_array_equal(res["single"][1], res["rounds"][1])
     np.testing.assert_array_equal(res["single"][2], res["rounds"][2])
     np.testing.assert_array_equal(res["single"][0], res["rounds"][0])
