@@ -330,7 +330,7 @@ struct HostPipe {
 
 static size_t stagingBudgetBytes() {
 	const char *e = getenv("NVSP_STAGE_MB");
-	size_t mb = (e && *e) ? (size_t)atoll(e) : 2048;
+	size_t mb = (e && *e) ? (size_t)atoll(e) : 1024;
 	return std::max<size_t>(mb, 1) << 20;
 }
 
@@ -357,7 +357,24 @@ static long long renderToHost(HostPipe &pipe, int precision, const StreamDesc *d
 		pipe.hostResCap = (size_t)n * 2;
 	}
 	std::vector<uint32_t> total(n, 0);
-	uint32_t numChunks = (sampleCount + chunk - 1) / chunk;
+	// Chunk plan.  The first kernel has no copy to hide behind and the last copy no kernel, so large requests start with
+	// a short chunk (~128 MB of output) and double up to the staging size: a copy takes ~2.3x as long as the render of
+	// the same ticks (PCIe Gen5 vs. the render rate), so the copy of chunk c still covers the render of chunk c+1.
+	std::vector<uint32_t> chunkStart, chunkLen;
+	{
+		uint32_t len = chunk;
+		if ((size_t)n * sampleCount * sizeof(int16_t) > ((size_t)256 << 20)) {
+			uint64_t first = (((size_t)128 << 20) / ((size_t)n * sizeof(int16_t))) & ~(uint64_t)63;
+			len = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(first, 64), chunk);
+		}
+		for (uint32_t t = 0; t < sampleCount;) {
+			uint32_t l = std::min(len, sampleCount - t);
+			chunkStart.push_back(t); chunkLen.push_back(l);
+			t += l;
+			len = std::min<uint32_t>(len * 2, chunk >= 64 ? (chunk & ~63u) : chunk);  // interior chunk boundaries stay on the 64-tick grid
+		}
+	}
+	const uint32_t numChunks = (uint32_t)chunkStart.size();
 	const bool verbose = getenv("NVSP_VERBOSE") != nullptr;
 	auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	const double tStart = now();
@@ -376,7 +393,7 @@ static long long renderToHost(HostPipe &pipe, int precision, const StreamDesc *d
 	}
 	for (uint32_t c = 0; c < numChunks; ++c) {
 		int b = c & 1;
-		uint32_t t0 = c * chunk, len = std::min(chunk, sampleCount - t0);
+		const uint32_t t0 = chunkStart[c], len = chunkLen[c];
 		const double tA = now();
 		if (c >= 2 && !harvest(c - 2)) return -1;  // staging buffer b is free again
 		const double tB = now();

@@ -26,6 +26,9 @@
 namespace klatt {
 
 constexpr int kF32Block = 64;
+#ifndef KLATT_GEN_MINB
+#define KLATT_GEN_MINB 4
+#endif
 
 
 // ---------------------------------------------------------------------------------------------------
@@ -116,7 +119,7 @@ klatt_f32_hold_kernel(const StreamDesc *__restrict__ descs, const uint32_t *__re
 }
 
 // a round of the general path: thread pair = stream list[slot], at most genTicks ticks from where the stream stands
-__global__ void __launch_bounds__(kPairBlock, 4)
+__global__ void __launch_bounds__(kPairBlock, KLATT_GEN_MINB)
 klatt_f32_general_pair_kernel(const StreamDesc *__restrict__ descs, const uint32_t *__restrict__ list,
                               const uint32_t *__restrict__ counters, uint32_t numStreams, int sampleRate,
                               uint32_t sampleCount, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,

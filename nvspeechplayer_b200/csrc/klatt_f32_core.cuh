@@ -39,8 +39,8 @@ namespace klatt {
 // slots of GenStateF32::dir
 enum Direct : int {
 	dVibratoPitchOffset = 0, dVoiceTurbulenceAmplitude, dGlottalOpenQuotient, dVoiceAmplitude,
-	dAspirationAmplitude, dCaNP, dFricationAmplitude, dPa1, dPa2, dPa3, dPa4, dPa5, dPa6, dParallelBypass,
-	dPreFormantGain, dOutputGain
+	dAspirationAmplitude, dCaNP, dPa1, dPa2, dPa3, dPa4, dPa5, dPa6, dFricationAmplitude, dParallelBypass,
+	dPreFormantGain, dOutputGain  // (pa1, pa2) (pa3, pa4) (pa5, pa6) sit in pairs 3..5: they multiply resonator pairs
 };
 static_assert(dOutputGain + 1 == kNumDirect, "direct slots");
 
@@ -196,11 +196,83 @@ struct XchgSelf {
 };
 
 // ---------------------------------------------------------------------------------------------------
+// Packed pairs.  sm_100a issues fma/mul/add/sub.rn.f32x2 (SASS FFMA2 / FMUL2 / FADD2): two independent IEEE FP32
+// operations on an aligned register pair in ONE issue slot, with the dependent latency of a scalar FFMA (measured on
+// B200, tools/ubench/ffma2.cu: 4.5 cycles; half the issue rate, so the same FP32 peak).  The render kernels are
+// bound by issue slots and dependent latency, not by the FMA pipe (ncu: pipe_fma ~33 % busy), so everything that
+// comes in independent pairs is computed in pairs: the pole recurrences, the coefficients and the memory part of the
+// sections of resonators 2k and 2k+1, the whole parallel bank (three pairs), and the direct parameters.  Each half is
+// exactly the scalar operation (the host build below IS the scalar operation), so pairing changes no bit.
+// f32x2 has no operand negation, so the working set is kept in the signs that need none:
+//   nz  = -zeta   (u = -Re zeta, v = -Im zeta)          ny = -y (negated section output)
+//   nrho = -(1 - |pole|^2)                               npar accumulates -par
+// Negation commutes with IEEE rounding, so every value is the exact negative of the one the scalar formulation had.
+// ---------------------------------------------------------------------------------------------------
+struct F2 { float lo, hi; };
+KLATT_HD F2 f2(float lo, float hi) { F2 r; r.lo = lo; r.hi = hi; return r; }
+KLATT_HD F2 f2s(float x) { F2 r; r.lo = x; r.hi = x; return r; }
+KLATT_HD F2 fma2(F2 a, F2 b, F2 c) {
+	F2 r;
+#ifdef __CUDA_ARCH__
+	asm("{ .reg .b64 pa, pb, pc, pd; mov.b64 pa, {%2, %3}; mov.b64 pb, {%4, %5}; mov.b64 pc, {%6, %7}; "
+	    "fma.rn.f32x2 pd, pa, pb, pc; mov.b64 {%0, %1}, pd; }"
+	    : "=f"(r.lo), "=f"(r.hi) : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi), "f"(c.lo), "f"(c.hi));
+#else
+	r.lo = fmaf(a.lo, b.lo, c.lo); r.hi = fmaf(a.hi, b.hi, c.hi);
+#endif
+	return r;
+}
+KLATT_HD F2 mul2(F2 a, F2 b) {
+	F2 r;
+#ifdef __CUDA_ARCH__
+	asm("{ .reg .b64 pa, pb, pd; mov.b64 pa, {%2, %3}; mov.b64 pb, {%4, %5}; mul.rn.f32x2 pd, pa, pb; mov.b64 {%0, %1}, pd; }"
+	    : "=f"(r.lo), "=f"(r.hi) : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi));
+#else
+	r.lo = a.lo * b.lo; r.hi = a.hi * b.hi;
+#endif
+	return r;
+}
+KLATT_HD F2 add2(F2 a, F2 b) {
+	F2 r;
+#ifdef __CUDA_ARCH__
+	asm("{ .reg .b64 pa, pb, pd; mov.b64 pa, {%2, %3}; mov.b64 pb, {%4, %5}; add.rn.f32x2 pd, pa, pb; mov.b64 {%0, %1}, pd; }"
+	    : "=f"(r.lo), "=f"(r.hi) : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi));
+#else
+	r.lo = a.lo + b.lo; r.hi = a.hi + b.hi;
+#endif
+	return r;
+}
+KLATT_HD F2 sub2(F2 a, F2 b) {
+	F2 r;
+#ifdef __CUDA_ARCH__
+	asm("{ .reg .b64 pa, pb, pd; mov.b64 pa, {%2, %3}; mov.b64 pb, {%4, %5}; sub.rn.f32x2 pd, pa, pb; mov.b64 {%0, %1}, pd; }"
+	    : "=f"(r.lo), "=f"(r.hi) : "f"(a.lo), "f"(a.hi), "f"(b.lo), "f"(b.hi));
+#else
+	r.lo = a.lo - b.lo; r.hi = a.hi - b.hi;
+#endif
+	return r;
+}
+// half r&1 of pair r>>1 (r is a compile-time constant everywhere: the loops are fully unrolled)
+KLATT_HD float &half(F2 *arr, int r) { return (r & 1) ? arr[r >> 1].hi : arr[r >> 1].lo; }
+KLATT_HD const float &half(const F2 *arr, int r) { return (r & 1) ? arr[r >> 1].hi : arr[r >> 1].lo; }
+
+constexpr int kNumPairs = kNumResonators / 2;       // (rN0, rNP) (r6, r5) (r4, r3) (r2, r1) | (p1, p2) (p3, p4) (p5, p6)
+constexpr int kNumDirectPairs = kNumDirect / 2;     // direct params 2k and 2k+1
+static_assert(kResCascade % 2 == 0 && kResParallel % 2 == 0, "role boundaries fall between pairs");
+template <int ROLE> struct PairTraits {
+	static constexpr int P0 = RoleTraits<ROLE>::R0 / 2, P1 = RoleTraits<ROLE>::R1 / 2;
+};
+template <int ROLE> KLATT_HD constexpr bool roleUsesDirectPair(int k) {
+	return roleUsesDirect<ROLE>(2 * k) || roleUsesDirect<ROLE>(2 * k + 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // per-stream working set (registers on the device).  Arrays are indexed with compile-time constants only
 // (every loop below is fully unrolled), so a role never materialises the elements it does not touch.
 // ---------------------------------------------------------------------------------------------------
 struct DspState {  // what every tick reads AND writes
-	float y[kNumResonators], d[kNumResonators];
+	F2 ny[kNumPairs];  // NEGATED last output of each section; ny[0].lo is rN0's last INPUT, not negated (it stores inputs)
+	F2 d[kNumPairs];   // last output difference (rN0: last input difference)
 	float aspLast, fricLast;
 	uint64_t vibratoPos;
 	int64_t vibInc;
@@ -209,9 +281,10 @@ struct DspState {  // what every tick reads AND writes
 };
 
 struct CoefF32 {  // what a tick only reads: a pure function of (zeta, direct params)
-	float a[kNumResonators], rho[kNumResonators];
+	F2 a[kNumPairs], nrho[kNumPairs];  // |1 - pole|^2 and -(1 - |pole|^2)
 	float invA0;  // 1/a of the anti-resonator
-	float vpo, vta, goq, va, aa, caNP, pa[6], bypass;
+	float vpo, vta, goq, va, aa, caNP, bypass;
+	F2 pa[3];
 	float halfGain, fricGain, og4000;
 	bool n0Inv;
 };
@@ -228,56 +301,64 @@ KLATT_HD float fastRcp(float x) {
 
 constexpr float kDrawScale = 1.0f / 8388608.0f;  // noise draws enter as 23-bit integers
 
+// nz = -zeta as pairs (u = -Re, v = -Im); dir = the direct params as pairs
 template <int ROLE>
-KLATT_HD void buildCoef(CoefF32 &C, const float *zre, const float *zim, const float *dir, bool n0Inv) {
+KLATT_HD void buildCoef(CoefF32 &C, const F2 *u, const F2 *v, const F2 *dir, bool n0Inv) {
 	using T = RoleTraits<ROLE>;
+	using P = PairTraits<ROLE>;
 #pragma unroll
-	for (int r = T::R0; r < T::R1; ++r) {
-		float a = fmaf(zre[r], zre[r], zim[r] * zim[r]);  // |1 - pole|^2
-		C.a[r] = a;
-		C.rho[r] = fmaf(2.0f, zre[r], -a);                // 1 - |pole|^2
+	for (int k = P::P0; k < P::P1; ++k) {
+		F2 a = fma2(u[k], u[k], mul2(v[k], v[k]));  // |1 - pole|^2
+		C.a[k] = a;
+		C.nrho[k] = fma2(f2s(2.0f), u[k], a);        // -(2 Re zeta - a) = -(1 - |pole|^2)
 	}
-	C.halfGain = dir[dPreFormantGain] * 0.5f;
+	C.halfGain = half(dir, dPreFormantGain) * 0.5f;
 	if (T::hasC) {
-		C.invA0 = fastRcp(C.a[kResN0]);
-		C.vta = dir[dVoiceTurbulenceAmplitude]; C.goq = dir[dGlottalOpenQuotient];
-		C.va = dir[dVoiceAmplitude]; C.aa = dir[dAspirationAmplitude]; C.caNP = dir[dCaNP];
-		C.og4000 = dir[dOutputGain] * 4000.0f;
+		C.invA0 = fastRcp(C.a[0].lo);
+		C.vta = half(dir, dVoiceTurbulenceAmplitude); C.goq = half(dir, dGlottalOpenQuotient);
+		C.va = half(dir, dVoiceAmplitude); C.aa = half(dir, dAspirationAmplitude); C.caNP = half(dir, dCaNP);
+		C.og4000 = half(dir, dOutputGain) * 4000.0f;
 		C.n0Inv = n0Inv;
 	}
 	if (T::hasP) {
+		static_assert(dPa1 % 2 == 0, "the parallel amplitudes are whole pairs of the direct params");
 #pragma unroll
-		for (int k = 0; k < 6; ++k) C.pa[k] = dir[dPa1 + k];
-		C.bypass = dir[dParallelBypass];
-		C.fricGain = ((0.3f * kDrawScale) * dir[dFricationAmplitude]) * C.halfGain;
+		for (int k = 0; k < 3; ++k) C.pa[k] = dir[dPa1 / 2 + k];
+		C.bypass = half(dir, dParallelBypass);
+		C.fricGain = ((0.3f * kDrawScale) * half(dir, dFricationAmplitude)) * C.halfGain;
 	}
-	if (T::hasO) C.vpo = dir[dVibratoPitchOffset];
+	if (T::hasO) C.vpo = half(dir, dVibratoPitchOffset);
 }
 
-// one tick of the pole recurrences: zeta' = zeta + omega - zeta*omega (a no-op when omega == 0)
+// one tick of the pole recurrences: zeta' = zeta + omega - zeta*omega (a no-op when omega == 0), on nz = -zeta:
+//   tr = fma(-zr, wr, wr);  tr = fma(zi, wi, tr);  ti = fma(-zr, wi, wi);  ti = fma(-zi, wr, ti);  nz' = nz - (tr, ti)
 template <int ROLE>
-KLATT_HD void stepPoles(float *zre, float *zim, const float *wre, const float *wim) {
-	using T = RoleTraits<ROLE>;
+KLATT_HD void stepPoles(F2 *u, F2 *v, const F2 *wr, const F2 *wi) {
+	using P = PairTraits<ROLE>;
 #pragma unroll
-	for (int r = T::R0; r < T::R1; ++r) {
-		float zr = zre[r], zi = zim[r], wr = wre[r], wi = wim[r];
-		float tr = fmaf(-zr, wr, wr);   // omega - zeta*omega, real
-		tr = fmaf(zi, wi, tr);
-		float ti = fmaf(-zr, wi, wi);   // imaginary
-		ti = fmaf(-zi, wr, ti);
-		zre[r] = zr + tr;
-		zim[r] = zi + ti;
+	for (int k = P::P0; k < P::P1; ++k) {
+		F2 zi = mul2(v[k], f2s(-1.0f));
+		F2 tr = fma2(u[k], wr[k], wr[k]);
+		tr = fma2(zi, wi[k], tr);
+		F2 ti = fma2(u[k], wi[k], wi[k]);
+		ti = fma2(v[k], wr[k], ti);
+		u[k] = sub2(u[k], tr);
+		v[k] = sub2(v[k], ti);
 	}
 }
 
-// delta-form two-pole section; returns the new output
-KLATT_HD float resonate(DspState &S, const CoefF32 &C, int r, float x) {
-	float w = fmaf(-C.rho[r], S.d[r], S.d[r]);  // (1-rho)*d
-	w = fmaf(-C.a[r], S.y[r], w);
-	float dn = fmaf(C.a[r], x, w);
-	S.d[r] = dn;
-	S.y[r] += dn;
-	return S.y[r];
+// delta-form two-pole section, scalar (the cascade chain): w = (1-rho)*d - a*y has been prepared (memory part);
+// returns the new output
+KLATT_HD float sectionOut(float &ny, float &d, float a, float w, float x) {
+	float dn = fmaf(a, x, w);
+	d = dn;
+	ny = ny - dn;
+	return -ny;
+}
+// memory part of two sections at once: (1-rho)*d - a*y
+KLATT_HD F2 sectionMemory(const DspState &S, const CoefF32 &C, int k) {
+	F2 w = fma2(C.nrho[k], S.d[k], S.d[k]);
+	return fma2(C.a[k], S.ny[k], w);
 }
 
 // sin(2*pi*t) for |t| <= 0.5: fold to |t| <= 0.25, then t*(c0 + u*Q(u)), u = t^2 (odd degree-11 least-squares fit on
@@ -318,9 +399,16 @@ KLATT_HD int64_t cyclesToFixed(double x) {
 #endif
 }
 
-// x - trunc(x): the reference's fmod(x, 1) (src/speechWaveGenerator.cpp:55) without a branch; exact for |x| < 2^31
+// x - trunc(x): the reference's fmod(x, 1) (src/speechWaveGenerator.cpp:55); exact for |x| < 2^31.  |x| < 2 whenever
+// |pitch| < sampleRate: trunc(x) is then -1, 0 or 1 and two compares replace the double->int->double round trip
+// through the conversion unit (which sits on the loop-carried chain of the phase: ~40 cycles per tick).
 KLATT_HD double fracRef(double x) {
 #ifdef __CUDA_ARCH__
+	if (fabs(x) < 2.0) {
+		double t = x >= 1.0 ? 1.0 : 0.0;
+		t = x <= -1.0 ? -1.0 : t;
+		return x - t;
+	}
 	return x - (double)__double2int_rz(x);
 #else
 	double t = (x != x) ? 0.0 : (x >= 2147483647.0 ? 2147483647.0 : (x <= -2147483648.0 ? -2147483648.0 : (double)(int32_t)x));
@@ -329,14 +417,23 @@ KLATT_HD double fracRef(double x) {
 }
 
 // parallel side of one generated sample (reference src/speechWaveGenerator.cpp:205-206, :170-180): wF is the
-// frication noise word (the reference's rand() value is word>>1; the top 23 bits are used)
+// frication noise word (the reference's rand() value is word>>1; the top 23 bits are used).  The six sections run as
+// three pairs; the weighted sum is accumulated per half and folded at the end.
 KLATT_HD float parallelSide(DspState &S, const CoefF32 &C, uint32_t wF) {
 	float uF = bitsToFloat(0x4B000000u | (wF >> 9)) - 8388608.0f;  // exact integer 0..2^23-1
 	S.fricLast = fmaf(0.75f, S.fricLast, uF);
 	float pin = S.fricLast * C.fricGain;
-	float par = 0.0f;
+	const F2 pin2 = f2s(pin);
+	F2 nacc = f2s(0.0f);  // -(sum of (y_k - pin) * pa_k), per half
 #pragma unroll
-	for (int k = 0; k < 6; ++k) par = fmaf(resonate(S, C, kResParallel + k, pin) - pin, C.pa[k], par);
+	for (int k = 0; k < 3; ++k) {
+		const int p = kResParallel / 2 + k;
+		F2 dn = fma2(C.a[p], pin2, sectionMemory(S, C, p));
+		S.d[p] = dn;
+		S.ny[p] = sub2(S.ny[p], dn);
+		nacc = fma2(add2(S.ny[p], pin2), C.pa[k], nacc);  // (ny + pin) = -(y - pin)
+	}
+	float par = -(nacc.lo + nacc.hi);
 	return fmaf(pin - par, C.bypass, par);
 }
 
@@ -377,16 +474,23 @@ KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, 
 	float src = fmaf(asp, C.aa, v);
 	// ---- cascade (:147-158) ----
 	float ci = src * C.halfGain;
-	float dx = ci - S.y[kResN0];  // anti-resonator: memories hold INPUTS (:133)
-	float dx1 = fmaf(-C.rho[kResN0], S.d[kResN0], S.d[kResN0]);  // (1-rho) * previous input difference
-	float n0 = C.n0Inv ? fmaf(dx - dx1, C.invA0, S.y[kResN0])
-	                   : fmaf(C.a[kResN0], dx, dx1 + S.y[kResN0]);
-	S.d[kResN0] = dx;
-	S.y[kResN0] = ci;
-	float np = resonate(S, C, kResNP, n0);
+	const F2 w23 = sectionMemory(S, C, 1), w45 = sectionMemory(S, C, 2), w67 = sectionMemory(S, C, 3);  // r6 r5 | r4 r3 | r2 r1
+	float dx = ci - S.ny[0].lo;  // anti-resonator: memories hold INPUTS (:133)
+	float dx1 = fmaf(C.nrho[0].lo, S.d[0].lo, S.d[0].lo);  // (1-rho) * previous input difference
+	float n0 = C.n0Inv ? fmaf(dx - dx1, C.invA0, S.ny[0].lo)
+	                   : fmaf(C.a[0].lo, dx, dx1 + S.ny[0].lo);
+	S.d[0].lo = dx;
+	S.ny[0].lo = ci;
+	float wNP = fmaf(C.nrho[0].hi, S.d[0].hi, S.d[0].hi);
+	wNP = fmaf(C.a[0].hi, S.ny[0].hi, wNP);
+	float np = sectionOut(S.ny[0].hi, S.d[0].hi, C.a[0].hi, wNP, n0);
 	float x = fmaf(np - ci, C.caNP, ci);
-#pragma unroll
-	for (int r = kResCascade; r < kResParallel; ++r) x = resonate(S, C, r, x);
+	x = sectionOut(S.ny[1].lo, S.d[1].lo, C.a[1].lo, w23.lo, x);
+	x = sectionOut(S.ny[1].hi, S.d[1].hi, C.a[1].hi, w23.hi, x);
+	x = sectionOut(S.ny[2].lo, S.d[2].lo, C.a[2].lo, w45.lo, x);
+	x = sectionOut(S.ny[2].hi, S.d[2].hi, C.a[2].hi, w45.hi, x);
+	x = sectionOut(S.ny[3].lo, S.d[3].lo, C.a[3].lo, w67.lo, x);
+	x = sectionOut(S.ny[3].hi, S.d[3].hi, C.a[3].hi, w67.hi, x);
 	// ---- mix, gain, clamp with the Win32 macro NaN behaviour (NaN -> +32000), truncate (:207-208) ----
 	float s = (x + par) * C.og4000;
 	s = fminf(s, 32000.0f);  // fminf(NaN, 32000) == 32000
@@ -418,7 +522,7 @@ template <int ROLE>
 KLATT_HD void loadDspState(DspState &S, const GenStateF32 &gs) {
 	using T = RoleTraits<ROLE>;
 #pragma unroll
-	for (int r = T::R0; r < T::R1; ++r) { S.y[r] = gs.y[r]; S.d[r] = gs.d[r]; }
+	for (int r = T::R0; r < T::R1; ++r) { half(S.ny, r) = (r == kResN0) ? gs.y[r] : -gs.y[r]; half(S.d, r) = gs.d[r]; }
 	if (T::hasC) S.aspLast = gs.aspLast;
 	if (T::hasP) S.fricLast = gs.fricLast;
 	if (T::hasO) {
@@ -430,7 +534,7 @@ template <int ROLE>
 KLATT_HD void storeDspState(GenStateF32 &gs, const DspState &S) {
 	using T = RoleTraits<ROLE>;
 #pragma unroll
-	for (int r = T::R0; r < T::R1; ++r) { gs.y[r] = S.y[r]; gs.d[r] = S.d[r]; }
+	for (int r = T::R0; r < T::R1; ++r) { gs.y[r] = (r == kResN0) ? half(S.ny, r) : -half(S.ny, r); gs.d[r] = half(S.d, r); }
 	if (T::hasC) gs.aspLast = S.aspLast;
 	if (T::hasP) gs.fricLast = S.fricLast;
 	if (T::hasO) {
@@ -461,13 +565,13 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 	loadDspState<ROLE>(S, gs);
 	CoefF32 C;
 	{
-		float zre[kNumResonators], zim[kNumResonators], dir[kNumDirect];
+		F2 u[kNumPairs], v[kNumPairs], dir[kNumDirectPairs];
 #pragma unroll
-		for (int r = T::R0; r < T::R1; ++r) { zre[r] = gs.zre[r]; zim[r] = gs.zim[r]; }
+		for (int r = T::R0; r < T::R1; ++r) { half(u, r) = -gs.zre[r]; half(v, r) = -gs.zim[r]; }
 #pragma unroll
 		for (int i = 0; i < kNumDirect; ++i)
-			if (roleUsesDirect<ROLE>(i)) dir[i] = gs.dir[i];
-		buildCoef<ROLE>(C, zre, zim, dir, gs.n0Inv != 0);
+			if (roleUsesDirectPair<ROLE>(i / 2)) half(dir, i) = roleUsesDirect<ROLE>(i) ? gs.dir[i] : 0.0f;
+		buildCoef<ROLE>(C, u, v, dir, gs.n0Inv != 0);
 	}
 	uint64_t gen = gs.samplesGenerated;
 	const uint64_t streamId = desc.streamId;
@@ -548,15 +652,16 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 
 	DspState S;
 	loadDspState<ROLE>(S, gs);
-	float zre[kNumResonators], zim[kNumResonators], wre[kNumResonators], wim[kNumResonators];
-	float dir0[kNumDirect], dstep[kNumDirect];
+	using P = PairTraits<ROLE>;
+	F2 u[kNumPairs], v[kNumPairs], wr[kNumPairs], wi[kNumPairs];  // -zeta and omega, as pairs of resonators
+	F2 dir0[kNumDirectPairs], dstep[kNumDirectPairs];
 	float kf = 0.0f, kfStep = 0.0f;
 	int64_t vibIncStep = 0;
 #pragma unroll
-	for (int r = T::R0; r < T::R1; ++r) { zre[r] = gs.zre[r]; zim[r] = gs.zim[r]; wre[r] = 0.0f; wim[r] = 0.0f; }
+	for (int r = T::R0; r < T::R1; ++r) { half(u, r) = -gs.zre[r]; half(v, r) = -gs.zim[r]; half(wr, r) = 0.0f; half(wi, r) = 0.0f; }
 #pragma unroll
 	for (int i = 0; i < kNumDirect; ++i)
-		if (roleUsesDirect<ROLE>(i)) { dir0[i] = gs.dir[i]; dstep[i] = 0.0f; }
+		if (roleUsesDirectPair<ROLE>(i / 2)) { half(dir0, i) = roleUsesDirect<ROLE>(i) ? gs.dir[i] : 0.0f; half(dstep, i) = 0.0f; }
 	uint64_t gen = gs.samplesGenerated;
 	const uint64_t streamId = desc.streamId;
 
@@ -580,10 +685,10 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 		plan = planned ? desc.plans + (qHead - 1 - desc.qBase) : &gs.plan;
 		if (counter >= 1 && counter < newF) {  // resuming in the middle of a fade: the increments are in force
 #pragma unroll
-			for (int r = T::R0; r < T::R1; ++r) { wre[r] = plan->wre[r]; wim[r] = plan->wim[r]; }
+			for (int r = T::R0; r < T::R1; ++r) { half(wr, r) = plan->wre[r]; half(wi, r) = plan->wim[r]; }
 #pragma unroll
 			for (int i = 0; i < kNumDirect; ++i)
-				if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dir0[i]; dstep[i] = plan->dirStep[i]; }
+				if (roleUsesDirect<ROLE>(i)) { half(dir0, i) = plan->dir0[i]; half(dstep, i) = plan->dirStep[i]; }
 			kf = (float)counter;
 			kfStep = 1.0f;
 			vibIncStep = plan->vibIncStep;
@@ -615,11 +720,11 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 					} else if (counter == 1 && newF > 1) {  // :49-52 first fade tick: start from the (possibly rewritten) old frame
 #pragma unroll
 						for (int r = T::R0; r < T::R1; ++r) {
-							zre[r] = plan->z0re[r]; zim[r] = plan->z0im[r]; wre[r] = plan->wre[r]; wim[r] = plan->wim[r];
+							half(u, r) = -plan->z0re[r]; half(v, r) = -plan->z0im[r]; half(wr, r) = plan->wre[r]; half(wi, r) = plan->wim[r];
 						}
 #pragma unroll
 						for (int i = 0; i < kNumDirect; ++i)
-							if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dir0[i]; dstep[i] = plan->dirStep[i]; }
+							if (roleUsesDirect<ROLE>(i)) { half(dir0, i) = plan->dir0[i]; half(dstep, i) = plan->dirStep[i]; }
 						kf = 0.0f; kfStep = 1.0f;
 						if (T::hasO) {
 							S.vibInc = plan->vibInc0; vibIncStep = plan->vibIncStep;
@@ -633,11 +738,11 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 					} else {  // counter == newF, ratio == 1: land exactly on the planned end values
 #pragma unroll
 						for (int r = T::R0; r < T::R1; ++r) {
-							zre[r] = plan->zFre[r]; zim[r] = plan->zFim[r]; wre[r] = 0.0f; wim[r] = 0.0f;
+							half(u, r) = -plan->zFre[r]; half(v, r) = -plan->zFim[r]; half(wr, r) = 0.0f; half(wi, r) = 0.0f;
 						}
 #pragma unroll
 						for (int i = 0; i < kNumDirect; ++i)
-							if (roleUsesDirect<ROLE>(i)) { dir0[i] = plan->dirFinal[i]; dstep[i] = 0.0f; }
+							if (roleUsesDirect<ROLE>(i)) { half(dir0, i) = plan->dirFinal[i]; half(dstep, i) = 0.0f; }
 						kf = 0.0f; kfStep = 0.0f;
 						if (T::hasC) n0Inv = plan->n0InvFinal != 0;
 						if (T::hasO) {
@@ -716,7 +821,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 		if (active) {
 			// ================= the straight-line per-tick update (all increments are zero outside fades) ===========
 			kf += kfStep;
-			stepPoles<ROLE>(zre, zim, wre, wim);
+			stepPoles<ROLE>(u, v, wr, wi);
 			if (T::hasO) S.vibInc += vibIncStep;
 			if ((gen & (uint64_t)(kCoarseTicks - 1)) == 0 && kfStep != 0.0f) {
 				// drift control, on a grid of ABSOLUTE sample indices (identical for every chunking of the render, and
@@ -724,26 +829,27 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 				if (counter - coarseAt == (uint32_t)kCoarseTicks) {
 #pragma unroll
 					for (int r = T::R0; r < T::R1; ++r) {
-						float zr = gs.zc[r], zi = gs.zc[kNumResonators + r], wr = plan->Wre[r], wi = plan->Wim[r];
-						float tr = fmaf(-zr, wr, wr);
-						tr = fmaf(zi, wi, tr);
-						float ti = fmaf(-zr, wi, wi);
-						ti = fmaf(-zi, wr, ti);
-						zre[r] = zr + tr;
-						zim[r] = zi + ti;
+						float zr = gs.zc[r], zi = gs.zc[kNumResonators + r], Wr = plan->Wre[r], Wi = plan->Wim[r];
+						float tr = fmaf(-zr, Wr, Wr);
+						tr = fmaf(zi, Wi, tr);
+						float ti = fmaf(-zr, Wi, Wi);
+						ti = fmaf(-zi, Wr, ti);
+						half(u, r) = -(zr + tr);
+						half(v, r) = -(zi + ti);
 					}
 				}
 #pragma unroll
-				for (int r = T::R0; r < T::R1; ++r) { gs.zc[r] = zre[r]; gs.zc[kNumResonators + r] = zim[r]; }
+				for (int r = T::R0; r < T::R1; ++r) { gs.zc[r] = -half(u, r); gs.zc[kNumResonators + r] = -half(v, r); }
 				coarseAt = counter;
 			}
 			CoefF32 C;
 			{
-				float dir[kNumDirect];
+				F2 dir[kNumDirectPairs];
+				const F2 kf2 = f2s(kf);
 #pragma unroll
-				for (int i = 0; i < kNumDirect; ++i)
-					if (roleUsesDirect<ROLE>(i)) dir[i] = fmaf(kf, dstep[i], dir0[i]);
-				buildCoef<ROLE>(C, zre, zim, dir, n0Inv);
+				for (int k = 0; k < kNumDirectPairs; ++k)
+					if (roleUsesDirectPair<ROLE>(k)) dir[k] = fma2(kf2, dstep[k], dir0[k]);
+				buildCoef<ROLE>(C, u, v, dir, n0Inv);
 			}
 			// ================= noise draws (two per generated sample) and the DSP =================
 			uint32_t wA = 0;
@@ -786,10 +892,10 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 	}
 	storeDspState<ROLE>(gs, S);
 #pragma unroll
-	for (int r = T::R0; r < T::R1; ++r) { gs.zre[r] = zre[r]; gs.zim[r] = zim[r]; }
+	for (int r = T::R0; r < T::R1; ++r) { gs.zre[r] = -half(u, r); gs.zim[r] = -half(v, r); }
 #pragma unroll
 	for (int i = 0; i < kNumDirect; ++i)
-		if (roleUsesDirect<ROLE>(i) && (T::hasC || i != dPreFormantGain)) gs.dir[i] = fmaf(kf, dstep[i], dir0[i]);
+		if (roleUsesDirect<ROLE>(i) && (T::hasC || i != dPreFormantGain)) gs.dir[i] = fmaf(kf, half(dstep, i), half(dir0, i));
 	if (T::hasC) {
 		fm.counter = counter; fm.qHead = qHead; fm.oldM = oldM; fm.newM = newM; fm.newF = newF;
 		fm.lastUserIndex = lastUserIndex;
