@@ -450,21 +450,54 @@ KLATT_HD double divideBySampleRate(double x, double srD, double srInv) {
 	return fma(r, srInv, q);
 }
 
+// The oscillators of one tick as SEGMENTS of one dependent chain (~16 operations through the FP64 and conversion
+// units, ~200 cycles end to end).  ptxas keeps close to source order, and the SM issues in order: a warp only keeps
+// issuing while the NEXT instruction is independent.  The general kernel therefore threads these segments between
+// its other phases (pole recurrences, coefficients, the parallel bank), which do not depend on them; oscillatorSide()
+// below is the same segments back to back -- same operations, same bits.
+struct OscChain {
+	float t, u, q, vib;
+	double m, quot, pos;
+	KLATT_HD void seg1(DspState &S) {  // vibrato phase -> folded quarter-period argument
+		S.vibratoPos += (uint64_t)S.vibInc;
+		// cycles in [-0.5, 0.5), rounded to nearest: a truncated phase is a systematic pitch error while a slow vibrato
+		// sits inside one quantisation step
+		t = (float)(int32_t)(uint32_t)(S.vibratoPos >> 32) * 2.3283064365386963e-10f;
+		if (t > 0.25f) t = 0.5f - t;
+		if (t < -0.25f) t = -0.5f - t;
+		u = t * t;
+	}
+	KLATT_HD void seg2() {  // the sine polynomial (sinTurns)
+		q = fmaf(u, -14.3368558883667f, 41.999961853027344f);
+		q = fmaf(u, q, -76.70366668701172f);
+		q = fmaf(u, q, 81.60520935058594f);
+		q = fmaf(u, q, -41.34170150756836f);
+		q = fmaf(t * u, q, t * 6.2831854820251465f);
+	}
+	KLATT_HD void seg3(DspState &S, float vpo) {  // pitch glide, pitch * (1 + vibrato)
+		vib = (q * 0.06f) * vpo;
+		S.pitch += S.pitchInc;
+		m = S.pitch * ((double)vib + 1.0);
+	}
+	KLATT_HD void seg4(double srD, double srInv) { quot = divideBySampleRate(m, srD, srInv); }
+	KLATT_HD void seg5(DspState &S) {
+		pos = fracRef(quot + S.pitchPos);
+		S.pitchPos = pos;
+	}
+	KLATT_HD float seg6() const { return (float)pos; }
+};
+
 KLATT_HD float oscillatorSide(DspState &S, const CoefF32 &C, double srD, double srInv) {
-	S.vibratoPos += (uint64_t)S.vibInc;
-	// cycles in [-0.5, 0.5), rounded to nearest: a truncated phase is a systematic pitch error while a slow vibrato
-	// sits inside one quantisation step
-	float vph = (float)(int32_t)(uint32_t)(S.vibratoPos >> 32) * 2.3283064365386963e-10f;
-	float vib = (sinTurns(vph) * 0.06f) * C.vpo;
-	S.pitch += S.pitchInc;
-	double pos = fracRef(divideBySampleRate(S.pitch * ((double)vib + 1.0), srD, srInv) + S.pitchPos);
-	S.pitchPos = pos;
-	return (float)pos;
+	OscChain o;
+	o.seg1(S); o.seg2(); o.seg3(S, C.vpo); o.seg4(srD, srInv); o.seg5(S);
+	return o.seg6();
 }
 
-// cascade side (reference src/speechWaveGenerator.cpp:203-204, :72-86, :147-158) and the final mix (:207-208)
-KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, float voice) {
-	// ---- aspiration noise + turbulence (:40, :75-80) ----
+// cascade side (reference src/speechWaveGenerator.cpp:203-204, :72-86, :147-158) and the final mix (:207-208), as
+// stages: source -> nasal pair -> six sections -> output.  cascadeSide() runs them tick by tick; cascadeGroup() runs
+// the same stages of eight ticks as a wavefront.
+// ---- aspiration noise + turbulence + glottal shaping (:40, :75-80), returns the cascade input (:147) ----
+KLATT_HD float stageSource(DspState &S, const CoefF32 &C, uint32_t wA, float voice) {
 	float uA = bitsToFloat(0x4B000000u | (wA >> 9)) - 8388608.0f;
 	S.aspLast = fmaf(0.75f, S.aspLast, uA);
 	float asp = S.aspLast * (0.2f * kDrawScale);
@@ -472,10 +505,11 @@ KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, 
 	if (voice < C.goq) turb *= 0.01f;
 	float v = (fmaf(voice, 2.0f, -1.0f) + turb) * C.va;
 	float src = fmaf(asp, C.aa, v);
-	// ---- cascade (:147-158) ----
-	float ci = src * C.halfGain;
-	const F2 w23 = sectionMemory(S, C, 1), w45 = sectionMemory(S, C, 2), w67 = sectionMemory(S, C, 3);  // r6 r5 | r4 r3 | r2 r1
-	float dx = ci - S.ny[0].lo;  // anti-resonator: memories hold INPUTS (:133)
+	return src * C.halfGain;
+}
+// ---- rN0 (anti-resonator: memories hold INPUTS, :133), rNP, caNP mix (:148-150) ----
+KLATT_HD float stageNasal(DspState &S, const CoefF32 &C, float ci) {
+	float dx = ci - S.ny[0].lo;
 	float dx1 = fmaf(C.nrho[0].lo, S.d[0].lo, S.d[0].lo);  // (1-rho) * previous input difference
 	float n0 = C.n0Inv ? fmaf(dx - dx1, C.invA0, S.ny[0].lo)
 	                   : fmaf(C.a[0].lo, dx, dx1 + S.ny[0].lo);
@@ -484,18 +518,69 @@ KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, 
 	float wNP = fmaf(C.nrho[0].hi, S.d[0].hi, S.d[0].hi);
 	wNP = fmaf(C.a[0].hi, S.ny[0].hi, wNP);
 	float np = sectionOut(S.ny[0].hi, S.d[0].hi, C.a[0].hi, wNP, n0);
-	float x = fmaf(np - ci, C.caNP, ci);
-	x = sectionOut(S.ny[1].lo, S.d[1].lo, C.a[1].lo, w23.lo, x);
-	x = sectionOut(S.ny[1].hi, S.d[1].hi, C.a[1].hi, w23.hi, x);
-	x = sectionOut(S.ny[2].lo, S.d[2].lo, C.a[2].lo, w45.lo, x);
-	x = sectionOut(S.ny[2].hi, S.d[2].hi, C.a[2].hi, w45.hi, x);
-	x = sectionOut(S.ny[3].lo, S.d[3].lo, C.a[3].lo, w67.lo, x);
-	x = sectionOut(S.ny[3].hi, S.d[3].hi, C.a[3].hi, w67.hi, x);
-	// ---- mix, gain, clamp with the Win32 macro NaN behaviour (NaN -> +32000), truncate (:207-208) ----
+	return fmaf(np - ci, C.caNP, ci);
+}
+// ---- section q = 0..5 (r6..r1, :151-156); w = its memory part ----
+KLATT_HD float stageSection(DspState &S, const CoefF32 &C, int q, float w, float x) {
+	const int r = kResCascade + q;
+	return sectionOut(half(S.ny, r), half(S.d, r), half(C.a, r), w, x);
+}
+// ---- mix, gain, clamp with the Win32 macro NaN behaviour (NaN -> +32000), truncate (:207-208) ----
+KLATT_HD int stageOut(const CoefF32 &C, float x, float par) {
 	float s = (x + par) * C.og4000;
 	s = fminf(s, 32000.0f);  // fminf(NaN, 32000) == 32000
 	s = fmaxf(s, -32000.0f);
 	return (int)s;
+}
+
+KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, float voice) {
+	float ci = stageSource(S, C, wA, voice);
+	F2 w[3];
+#pragma unroll
+	for (int p = 0; p < 3; ++p) w[p] = sectionMemory(S, C, 1 + p);  // r6 r5 | r4 r3 | r2 r1
+	float x = stageNasal(S, C, ci);
+#pragma unroll
+	for (int q = 0; q < 6; ++q) x = stageSection(S, C, q, half(w, q), x);
+	return stageOut(C, x, par);
+}
+
+// Eight ticks of the cascade side with CONSTANT coefficients (hold chunks) as a wavefront: in step s, stage j works on
+// tick s - j.  Within a tick the stages form one dependent chain of ~35 operations (the hold kernel's cascade warps were
+// bound by exactly that chain: ncu showed their partner warps waiting at the pair barrier for half of their time), but
+// stage j of tick t+1 only needs stage j of tick t and stage j-1 of tick t+1, so a step offers nine independent
+// pieces of work.  Every stage does what cascadeSide() does, on the same values, in the same order per stage: same bits.
+// The memory parts of a pair of sections are taken at the top of each step: its two halves are one tick apart, which is
+// what the step needs.  voice[k] is the sawtooth of tick k; wA and par come from the hand-over records.
+constexpr int kCascadeStages = 9;  // source, nasal pair, six sections, output
+template <class Out, class Xchg>
+KLATT_HD void cascadeGroup(DspState &S, const CoefF32 &C, Xchg &xc, uint32_t t0, const float *voice, Out &out) {
+	float ci = 0.0f, xN = 0.0f, xq[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // pipeline registers between the stages
+#pragma unroll
+	for (int s = 0; s < kGroupTicks + kCascadeStages - 1; ++s) {
+		F2 w[3];
+#pragma unroll
+		for (int p = 0; p < 3; ++p) {  // pair p = sections 2p, 2p+1 = stages 2+2p, 3+2p
+			const bool active = (s - (2 + 2 * p) >= 0 && s - (2 + 2 * p) < kGroupTicks) || (s - (3 + 2 * p) >= 0 && s - (3 + 2 * p) < kGroupTicks);
+			if (active) w[p] = sectionMemory(S, C, 1 + p);
+		}
+		// last stage first: every stage reads what its predecessor produced in the previous step
+		if (s - 8 >= 0 && s - 8 < kGroupTicks) {
+			uint32_t wA;
+			float par, vo;
+			xc.get(t0 + (uint32_t)(s - 8), wA, par, vo);
+			out.push(stageOut(C, xq[5], par));
+		}
+#pragma unroll
+		for (int q = 5; q >= 0; --q)
+			if (s - (2 + q) >= 0 && s - (2 + q) < kGroupTicks) xq[q] = stageSection(S, C, q, half(w, q), q == 0 ? xN : xq[q - 1]);
+		if (s - 1 >= 0 && s - 1 < kGroupTicks) xN = stageNasal(S, C, ci);
+		if (s < kGroupTicks) {
+			uint32_t wA;
+			float par, vo;
+			xc.get(t0 + (uint32_t)s, wA, par, vo);
+			ci = stageSource(S, C, wA, voice ? voice[s] : vo);
+		}
+	}
 }
 
 // the two noise words of generated sample `gen` (Philox mode caches the 4-word block of samples 2b, 2b+1)
@@ -580,7 +665,14 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 	const bool evenPhilox = noise.mode == kNoisePhilox && (gen & 1ull) == 0;
 	for (uint32_t t = 0; t < ticks; t += kGroupTicks) {
 		if (T::hasC && !T::hasP) xc.sync();  // the parallel side has finished this group
-		if (!T::hasP || evenPhilox) {  // straight-line group: one Philox block per two ticks
+		if (T::hasC && !T::hasP) {  // cascade warp of a pair: the eight ticks as a wavefront
+			float voice[kGroupTicks];
+			if (T::hasO) {
+#pragma unroll
+				for (int k = 0; k < kGroupTicks; ++k) voice[k] = oscillatorSide(S, C, srD, srInv);
+			}
+			cascadeGroup(S, C, xc, t, T::hasO ? voice : nullptr, out);
+		} else if (!T::hasP || evenPhilox) {  // straight-line group: one Philox block per two ticks
 #pragma unroll
 			for (int k = 0; k < kGroupTicks; k += 2) {
 				Philox4 blk;
@@ -820,12 +912,19 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 		}
 		if (active) {
 			// ================= the straight-line per-tick update (all increments are zero outside fades) ===========
+			// Order matters for speed, not for the result: the noise block (every other tick, a chain of ten dependent
+			// rounds) is drawn first so that the rest is one basic block, and the oscillator chain is threaded through
+			// the phases that do not depend on it.
+			uint32_t wA = 0, wF = 0;
+			if (T::hasP) ns.draw(noise, desc, streamId, gen, wA, wF);
+			const bool oscHere = T::hasO && !T::hasC;  // the parallel warp of a pair carries the oscillators
+			OscChain osc;
 			kf += kfStep;
-			stepPoles<ROLE>(u, v, wr, wi);
 			if (T::hasO) S.vibInc += vibIncStep;
 			if ((gen & (uint64_t)(kCoarseTicks - 1)) == 0 && kfStep != 0.0f) {
 				// drift control, on a grid of ABSOLUTE sample indices (identical for every chunking of the render, and
-				// the same loop iteration for every lane of a batch that started together)
+				// the same loop iteration for every lane of a batch that started together): the poles of this tick come
+				// from the coarse recurrence instead of the per-tick one
 				if (counter - coarseAt == (uint32_t)kCoarseTicks) {
 #pragma unroll
 					for (int r = T::R0; r < T::R1; ++r) {
@@ -837,11 +936,17 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						half(u, r) = -(zr + tr);
 						half(v, r) = -(zi + ti);
 					}
+				} else {
+					stepPoles<ROLE>(u, v, wr, wi);
 				}
 #pragma unroll
 				for (int r = T::R0; r < T::R1; ++r) { gs.zc[r] = -half(u, r); gs.zc[kNumResonators + r] = -half(v, r); }
 				coarseAt = counter;
+			} else {
+				stepPoles<ROLE>(u, v, wr, wi);
 			}
+			// (one basic block from here to the end of the tick)
+			if (oscHere) { osc.seg1(S); osc.seg2(); }
 			CoefF32 C;
 			{
 				F2 dir[kNumDirectPairs];
@@ -849,16 +954,16 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 #pragma unroll
 				for (int k = 0; k < kNumDirectPairs; ++k)
 					if (roleUsesDirectPair<ROLE>(k)) dir[k] = fma2(kf2, dstep[k], dir0[k]);
+				if (oscHere) osc.seg3(S, half(dir, dVibratoPitchOffset));
 				buildCoef<ROLE>(C, u, v, dir, n0Inv);
 			}
-			// ================= noise draws (two per generated sample) and the DSP =================
-			uint32_t wA = 0;
+			if (oscHere) osc.seg4(srD, srInv);
+			// ================= the DSP =================
 			float par = 0.0f, voice = 0.0f;
 			if (T::hasP) {
-				uint32_t wF;
-				ns.draw(noise, desc, streamId, gen, wA, wF);
+				if (oscHere) osc.seg5(S);
 				par = parallelSide(S, C, wF);
-				if (T::hasO && !T::hasC) voice = oscillatorSide(S, C, srD, srInv);
+				if (oscHere) voice = osc.seg6();
 				if (!T::hasC) xc.put(t, wA, par, voice);
 			}
 			gen++;
