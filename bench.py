@@ -49,9 +49,12 @@ def parse_args():
                          "consumer): 65536 x 2 s = 5.8 GB pinned per rank instead of 28.9 GB, so 8 ranks fit the host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-streams-per-core", type=int, default=16)
-    ap.add_argument("--workload", default="batch", choices=["batch", "long"],
-                    help="batch: BASELINE config 3 (default, the headline); long: config 4, ONE stream of --long-seconds at "
-                         "--long-rate through the time-parallel kernel")
+    ap.add_argument("--workload", default="batch", choices=["batch", "vowel", "midi", "long"],
+                    help="batch: BASELINE config 3 (default, the headline); vowel: config 2, vowel-chart pairs x --voices "
+                         "voices at 16 kHz (one fresh player per (voice, pair)); midi: config 5, midi-sing style streams "
+                         "(--streams per GPU x 5 s); long: config 4, ONE stream of --long-seconds at --long-rate through "
+                         "the time-parallel kernel")
+    ap.add_argument("--voices", type=int, default=1024, help="--workload vowel: voices per GPU (1369 pairs each)")
     ap.add_argument("--long-seconds", type=float, default=3600.0)
     ap.add_argument("--long-rate", type=int, default=44100)
     return ap.parse_args()
@@ -248,8 +251,24 @@ def main():
         torch.cuda.synchronize()
 
     sr, S, secs = args.sample_rate, args.streams, args.seconds
+    if args.workload == "vowel":    # config 2: 16 kHz (the NVDA rate), 13 926 ticks per (voice, pair) stream
+        sr, secs = 16000, 13926 / 16000.0
+        S = args.voices * 1369
+    elif args.workload == "midi":   # config 5: 5 s per stream; 2^20 streams over 8 GPUs = 131 072 per GPU
+        secs = 5.0 if args.seconds == 10.0 else args.seconds
+        S = 131072 if args.streams == 65536 else args.streams
     count = int(round(secs * sr))
     prec = player.PRECISION_FP32 if args.precision == "fp32" else player.PRECISION_FP64
+
+    def make_workload(n, first):
+        if args.workload == "vowel":
+            return workloads.vowel_chart(max(n // 1369, 1), sr, seed=args.seed, first_stream=first)
+        if args.workload == "midi":
+            return workloads.midi_sing(n, secs, sr, seed=args.seed, first_stream=first)
+        return workloads.random_frames(n, secs, sr, seed=args.seed, first_stream=first)
+
+    workload_name = {"batch": "config3: synthetic random-frame batch", "vowel": "config2: vowel-chart pairs x voices (fresh player per pair)",
+                     "midi": "config5: midi-sing style pitch-sweep streams"}[args.workload]
 
     # ---- CPU baseline first (spawns processes; keep it away from the timed GPU region) ----
     cpu = None
@@ -259,9 +278,9 @@ def main():
 
     # ---- workload: this rank's shard of config 3 ----
     t_gen = time.time()
-    fb = workloads.random_frames(S, secs, sr, seed=args.seed, first_stream=rank * S)
-    phi = fb.fade_fraction(count) if S <= 4096 else workloads.random_frames(
-        1024, secs, sr, seed=args.seed, first_stream=rank * S).fade_fraction(count)
+    fb = make_workload(S, rank * S)
+    phi = fb.fade_fraction(count) if S <= 4096 else make_workload(1369 if args.workload == "vowel" else 1024,
+                                                                  rank * S).fade_fraction(count)
     t_gen = time.time() - t_gen
     flops_per_sample = W_HOLD + W_FADE_EXTRA * phi
     total_frames = int(fb.offsets[-1])
@@ -308,7 +327,9 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    assert int(d_written.min()) == count, "a stream drained early: workload shorter than the render"
+    if args.workload == "batch":
+        assert int(d_written.min()) == count, "a stream drained early: workload shorter than the render"
+    rendered = int(d_written.to(torch.int64).sum())  # midi streams end at their own length: count what was rendered
     launches0, _ = batch.launch_stats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -329,8 +350,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    value = world * S * secs * args.steps / (elapsed_ms * 1e-3)          # audio-seconds per wall-second, whole job
-    samples_per_s_gpu = S * count * args.steps / (elapsed_ms * 1e-3)      # per GPU
+    rendered_all = torch.tensor([float(rendered)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rendered_all, op=dist.ReduceOp.SUM)
+    rendered_all = float(rendered_all.item())                            # samples rendered per step, all ranks
+    value = rendered_all / sr * args.steps / (elapsed_ms * 1e-3)          # audio-seconds per wall-second, whole job
+    samples_per_s_gpu = rendered * args.steps / (elapsed_ms * 1e-3)       # per GPU
 
     # ---- e2e: host buffers through the C-ABI (H2D of the frames + D2H of the int16 inside the timed region) ----
     e2e = None
@@ -356,7 +381,7 @@ def main():
                 n_now = min(slice_ticks, count - done)
                 dst = h_out if done == 0 else h_scratch
                 got = L.speechPlayer_batchSynthesizeHost(eb._h, n_now, dst.data_ptr(), None)
-                assert got == S * n_now, (got, player.last_error())
+                assert got >= 0 and (args.workload != "batch" or got == S * n_now), (got, player.last_error())
                 done += n_now
 
         h_scratch = torch.empty((S, slice_ticks), dtype=torch.int16).pin_memory() if count > slice_ticks else h_out
@@ -372,7 +397,7 @@ def main():
         e2e_launches = eb.launch_stats()[0]
         # the device-resident and the host path must agree bit for bit
         same = bool(torch.equal(d_out[:64, :slice_ticks].cpu(), h_out[:64]))
-        e2e = {"value": world * S * secs * args.e2e_steps / float(dt.item()), "unit": "audio-seconds/s",
+        e2e = {"value": rendered_all / sr * args.e2e_steps / float(dt.item()), "unit": "audio-seconds/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                "ms_per_step": 1e3 * float(dt.item()) / args.e2e_steps, "matches_device_path": same,
                "slice_seconds": slice_ticks / sr,
@@ -381,7 +406,7 @@ def main():
 
     if rank == 0:
         peaks = measured_peaks()
-        achieved_tf = S * count * flops_per_sample / (kernel_ms * 1e-3) / 1e12  # dominant kernel alone
+        achieved_tf = rendered * flops_per_sample / (kernel_ms * 1e-3) / 1e12  # dominant kernel alone
         sm_max = (clocks or {}).get("sm_max_mhz") or (peaks or {}).get("sm_max_mhz") or 1965.0
         nominal_tf = props.multi_processor_count * 128 * 2 * sm_max * 1e6 / 1e12
         peak_tf = fp32_peak_measured if fp32_peak_measured > 0 else nominal_tf
@@ -392,8 +417,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if prec == player.PRECISION_FP32 else "f64", "data": "synthetic",
-            "config": {"workload": "config3: synthetic random-frame batch, %d streams x %.1f s @ %d Hz per GPU, all frame "
-                                   "params randomised (seed 0x%X)" % (S, secs, sr, args.seed),
+            "config": {"workload": "%s, %d streams x %.2f s @ %d Hz per GPU (seed 0x%X)" % (workload_name, S, secs, sr, args.seed),
+                       "rendered_fraction": rendered / float(S * count),
                        "streams_per_gpu": S, "seconds_per_stream": secs, "sample_rate": sr, "frames_per_gpu": total_frames,
                        "fade_fraction_phi": round(phi, 4), "flops_per_sample_W": round(flops_per_sample, 1),
                        "noise": "philox4x32-10", "precision": args.precision,
@@ -403,14 +428,14 @@ def main():
             "roofline": {"bound": "fp32_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
-                         # (klatt_f32_general_pair_kernel, one 256-tick round over ~35k streams), ncu --set full capture
-                         # summarised in profiles/r01_v2_ncu_summary.txt; algorithmic output of that launch: 18 MB
-                         "traffic": 84.9e6 if (prec == player.PRECISION_FP32 and S == 65536) else None,
+                         # (klatt_f32_general_pair_kernel, one 256-tick round over ~47k streams), ncu --set full capture
+                         # summarised in profiles/r01_v3_ncu_summary.txt; algorithmic output of that launch: 24 MB
+                         "traffic": 87.4e6 if (prec == player.PRECISION_FP32 and S == 65536 and args.workload == "batch") else None,
                          "peak_source": "FFMA loop measured on this GPU in this run (MEASURED_PEAKS.json has no FP32 entry)"
                                         if fp32_peak_measured > 0 else "SMs x 128 x 2 x max SM clock",
                          "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
                          "kernel": "klatt_f32_hold_kernel + klatt_f32_general_pair_kernel (rounds)" if prec == player.PRECISION_FP32 else "klatt_batch_f64_kernel",
-                         "flops_per_launch": S * count * flops_per_sample, "kernel_ms": kernel_ms,
+                         "flops_per_launch": rendered * flops_per_sample, "kernel_ms": kernel_ms,
                          "kernel_share_of_step": kernel_ms / ms_per_step},
             "roofline_hbm": {"bound": "hbm", "achieved": out_bytes_per_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": out_bytes_per_s / 1e9 / hbm_peak,
