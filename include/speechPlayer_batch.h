@@ -51,6 +51,18 @@ int speechPlayer_batchSetFramesDevice(speechPlayer_batch_t *batch, const void *d
                                       const void *dFadeDur /* u32 */, const void *dUserIndex /* i32 or NULL */,
                                       const void *dIsNull /* u8 or NULL */, void *cudaStream);
 
+/* Voices (reference nvdaAddon/synthDrivers/nvSpeechPlayer/__init__.py:86-125,
+ * applyVoiceToFrame): rewrite the queued frames of every stream with its voice, on the device, in place:
+ *     value = isnan(voiceAbs[v][p]) ? frame[p] : voiceAbs[v][p];   frame[p] = value * voiceMul[v][p]
+ * for each of the 47 params p, v = voiceOfStream[s] -- the reference's "absolute override, then _mul factor" per
+ * parameter, in double, so a voiced batch renders exactly what uploading host-rewritten frames would.
+ *   voiceAbs, voiceMul : HOST double [numVoices][47]  (voiceAbs: NaN = no override; voiceMul: 1.0 = none)
+ *   voiceOfStream      : HOST u32 [numStreams], or NULL = stream s uses voice s % numVoices
+ * Call after SetFramesHost (the batch's own copy is rewritten) or SetFramesDevice (the CALLER'S frame array is
+ * rewritten).  NULL-request rows are left alone.  Fade plans are re-made by the next synthesize call. */
+int speechPlayer_batchApplyVoices(speechPlayer_batch_t *batch, const double *voiceAbs, const double *voiceMul,
+                                  const unsigned int *voiceOfStream, unsigned int numVoices, void *cudaStream);
+
 /* SPEECHPLAYER_NOISE_REPLAY: device int32 [numStreams][drawsPerStream]; draw d of stream s is at [s][d]. */
 int speechPlayer_batchSetNoiseReplayDevice(speechPlayer_batch_t *batch, const void *dDraws, size_t drawsPerStream);
 

@@ -155,6 +155,23 @@ __global__ void init_states_kernel(StreamState *states, uint32_t n) {
 	states[i].fm.oldIsNull = 1;
 }
 
+// reference nvdaAddon/synthDrivers/nvSpeechPlayer/__init__.py:117-125 (applyVoiceToFrame), one thread per frame value
+__global__ void apply_voices_kernel(double *frames, const int64_t *offsets, const uint8_t *isNull, const double *voiceAbs,
+                                    const double *voiceMul, const uint32_t *voiceOfStream, uint32_t numVoices, uint32_t numStreams) {
+	const uint32_t s = blockIdx.y;
+	const int64_t a = offsets[s], b = offsets[s + 1];
+	const uint32_t v = voiceOfStream ? voiceOfStream[s] % numVoices : s % numVoices;
+	const int64_t cells = (b - a) * kNumParams;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t row = a + i / kNumParams;
+		const int p = (int)(i % kNumParams);
+		if (isNull && isNull[row]) continue;
+		const double ab = voiceAbs[(size_t)v * kNumParams + p];
+		const double cur = frames[(size_t)row * kNumParams + p];
+		frames[(size_t)row * kNumParams + p] = ((ab != ab) ? cur : ab) * voiceMul[(size_t)v * kNumParams + p];
+	}
+}
+
 __global__ void build_descs_kernel(StreamDesc *descs, StreamState *states, const int64_t *offsets, const double *frames,
                                    const uint32_t *minDur, const uint32_t *fadeDur, const int32_t *userIndex,
                                    const uint8_t *isNull, const int32_t *replay, uint64_t drawsPerStream,
@@ -834,6 +851,7 @@ struct speechPlayer_batch {
 	const int32_t *dReplay = nullptr;
 	uint64_t drawsPerStream = 0;
 	DevBuf ownOffsets, ownFrames, ownMin, ownFade, ownUix, ownNull;
+	DevBuf voiceTables;        // speechPlayer_batchApplyVoices: abs | mul | voiceOfStream
 	DevBuf plans;              // FadePlanF32 per queued request (FP32 precision)
 	bool plansDirty = false;   // frames changed since the plans were made
 	uint64_t totalRequests = 0;
@@ -901,6 +919,7 @@ void speechPlayer_batchDestroy(speechPlayer_batch_t *b) {
 	b->pipe.destroy();
 	b->rounds.destroy();
 	b->plans.release();
+	b->voiceTables.release();
 	b->ownOffsets.release(); b->ownFrames.release(); b->ownMin.release(); b->ownFade.release(); b->ownUix.release(); b->ownNull.release();
 	if (b->dStates) cudaFree(b->dStates);
 	if (b->dDescs) cudaFree(b->dDescs);
@@ -974,6 +993,30 @@ int speechPlayer_batchSetFramesHost(speechPlayer_batch_t *b, const int64_t *offs
 	if (r != 0) return r;
 	DeviceGuard g(b->device);
 	CU(cudaStreamSynchronize(stream));  // the caller's host arrays may be reused now
+	return 0;
+}
+
+int speechPlayer_batchApplyVoices(speechPlayer_batch_t *b, const double *voiceAbs, const double *voiceMul,
+                                  const unsigned int *voiceOfStream, unsigned int numVoices, void *cudaStream) {
+	if (!b) return fail("null batch");
+	if (!voiceAbs || !voiceMul || numVoices == 0) return fail("voice tables are required");
+	std::lock_guard<std::mutex> lk(b->mu);
+	if (!b->dOffsets || !b->dFrames) return fail("no frames queued (call SetFrames first)");
+	DeviceGuard g(b->device);
+	cudaStream_t stream = static_cast<cudaStream_t>(cudaStream);
+	const size_t tableBytes = sizeof(double) * (size_t)numVoices * kNumParams;
+	if (!b->voiceTables.reserve(2 * tableBytes + sizeof(uint32_t) * (size_t)b->n)) return -1;
+	char *base = b->voiceTables.as<char>();
+	CU(cudaMemcpyAsync(base, voiceAbs, tableBytes, cudaMemcpyHostToDevice, stream));
+	CU(cudaMemcpyAsync(base + tableBytes, voiceMul, tableBytes, cudaMemcpyHostToDevice, stream));
+	if (voiceOfStream) CU(cudaMemcpyAsync(base + 2 * tableBytes, voiceOfStream, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyHostToDevice, stream));
+	apply_voices_kernel<<<dim3(4, b->n), 128, 0, stream>>>(const_cast<double *>(b->dFrames), b->dOffsets, b->dNull,
+	                                                      reinterpret_cast<const double *>(base), reinterpret_cast<const double *>(base + tableBytes),
+	                                                      voiceOfStream ? reinterpret_cast<const uint32_t *>(base + 2 * tableBytes) : nullptr, numVoices, b->n);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(stream));  // the host tables may be reused
+	b->launches += 1;
+	if (b->precision == kPrecisionF32) b->plansDirty = true;
 	return 0;
 }
 

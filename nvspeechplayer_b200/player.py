@@ -80,6 +80,8 @@ def load_library():
     L.speechPlayer_batchSetFramesHost.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.speechPlayer_batchSetFramesDevice.restype = i32
     L.speechPlayer_batchSetFramesDevice.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.speechPlayer_batchApplyVoices.restype = i32
+    L.speechPlayer_batchApplyVoices.argtypes = [vp, vp, vp, vp, u32, vp]
     L.speechPlayer_batchSetNoiseReplayDevice.restype = i32
     L.speechPlayer_batchSetNoiseReplayDevice.argtypes = [vp, vp, ctypes.c_size_t]
     L.speechPlayer_batchSynthesizeDevice.restype = i32
@@ -261,6 +263,18 @@ class Batch(object):
         _check(self._L.speechPlayer_batchSetFramesDevice(self._h, d_offsets, d_frames, d_min, d_fade, d_user_index, d_is_null,
                                                          cuda_stream), "speechPlayer_batchSetFramesDevice")
 
+    def apply_voices(self, voice_abs, voice_mul, voice_of_stream=None, cuda_stream=None):
+        """Rewrite the queued frames with per-stream voices on the device (reference applyVoiceToFrame,
+        nvdaAddon/synthDrivers/nvSpeechPlayer/__init__.py:117-125): value = abs if not NaN else frame; frame = value * mul.
+        voice_abs / voice_mul: [numVoices][47] doubles; voice_of_stream: [numStreams] or None (stream s -> voice s % numVoices)."""
+        va = np.ascontiguousarray(voice_abs, dtype=np.float64)
+        vm = np.ascontiguousarray(voice_mul, dtype=np.float64)
+        assert va.shape == vm.shape and va.ndim == 2 and va.shape[1] == 47
+        vs = None if voice_of_stream is None else np.ascontiguousarray(voice_of_stream, dtype=np.uint32)
+        assert vs is None or vs.shape == (self.num_streams,)
+        _check(self._L.speechPlayer_batchApplyVoices(self._h, _ptr(va), _ptr(vm), None if vs is None else _ptr(vs), va.shape[0],
+                                                     cuda_stream), "speechPlayer_batchApplyVoices")
+
     def set_noise_replay_device(self, d_draws, draws_per_stream):
         _check(self._L.speechPlayer_batchSetNoiseReplayDevice(self._h, d_draws, draws_per_stream),
                "speechPlayer_batchSetNoiseReplayDevice")
@@ -298,3 +312,38 @@ class Batch(object):
             self.close()
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------------------------
+# Output sinks: what the reference's demo players do with the int16 buffers
+# ----------------------------------------------------------------------------------------------
+def to_float32(pcm):
+    """int16 -> float32 in [-1, 1] exactly as reference lavPlayer.py:17 feeds its audio graph (value / 32767.0)."""
+    return (np.asarray(pcm, dtype=np.int16).astype(np.float64) / 32767.0).astype(np.float32)
+
+
+def write_wav(path, pcm, sample_rate):
+    """Mono 16-bit PCM WAV of one stream (1-D int16) or the concatenation of the rows of a batch (2-D, with a matching
+    `written` handled by the caller slicing rows first)."""
+    import wave
+    data = np.ascontiguousarray(np.asarray(pcm, dtype=np.int16).reshape(-1))
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(int(sample_rate))
+        w.writeframes(data.astype("<i2").tobytes())
+
+
+def nvda_voice_tables(voices):
+    """[(abs[47], mul[47])] tables for Batch.apply_voices from NVDA-style voice dicts ({'cb1_mul': 1.3, 'cf4': 3770, ...},
+    reference nvdaAddon/synthDrivers/nvSpeechPlayer/__init__.py:86-115)."""
+    names = [f[0] for f in Frame._fields_]
+    va = np.full((len(voices), 47), np.nan)
+    vm = np.ones((len(voices), 47))
+    for i, v in enumerate(voices):
+        for k, x in v.items():
+            if k.endswith("_mul"):
+                vm[i, names.index(k[:-4])] = x
+            else:
+                va[i, names.index(k)] = x
+    return va, vm

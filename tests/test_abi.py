@@ -72,3 +72,22 @@ def test_no_cpu_fallback():
         player.SpeechPlayer(22050)
     with pytest.raises(player.EngineError):
         player.Batch(22050, 4)
+
+
+def test_output_sinks_and_voice_tables(tmp_path):
+    """Host-side sinks of SURVEY.md 8f rank 4 (reference lavPlayer.py:14-17: int16 / 32767.0) and the NVDA-style voice
+    tables of rank 2 (reference nvdaAddon/synthDrivers/nvSpeechPlayer/__init__.py:86-125)."""
+    import wave
+    pcm = np.array([0, 1, -1, 32767, -32767, -32768, 12345], dtype=np.int16)
+    f = player.to_float32(pcm)
+    assert f.dtype == np.float32 and f[3] == 1.0 and f[4] == -1.0 and abs(f[6] - 12345 / 32767.0) < 1e-7
+    path = str(tmp_path / "x.wav")
+    player.write_wav(path, pcm, 22050)
+    with wave.open(path, "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 22050, len(pcm))
+        np.testing.assert_array_equal(np.frombuffer(w.readframes(len(pcm)), dtype="<i2"), pcm)
+    va, vm = player.nvda_voice_tables([{"cb1_mul": 1.3, "pa6_mul": 1.3, "fricationAmplitude_mul": 0.85},
+                                       {"cf4": 3770, "cf1_mul": 1.01, "voiceAmplitude": 0, "aspirationAmplitude": 1}])
+    names = list(player.PARAM_NAMES)
+    assert vm[0, names.index("cb1")] == 1.3 and np.isnan(va[0]).all()
+    assert va[1, names.index("cf4")] == 3770 and vm[1, names.index("cf1")] == 1.01 and va[1, names.index("voiceAmplitude")] == 0

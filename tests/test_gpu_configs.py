@@ -118,3 +118,45 @@ def test_batch_is_the_concatenation_of_its_streams(family):
     np.testing.assert_array_equal(chunked, part)
     np.testing.assert_array_equal(wch, wpart)
     np.testing.assert_array_equal(wfull, np.minimum(fb.timeline_samples(), count))
+
+
+@pytest.mark.parametrize("precision", [player.PRECISION_FP64, player.PRECISION_FP32])
+def test_voices_applied_on_device_equal_host_rewritten_frames(port, precision):
+    """speechPlayer_batchApplyVoices rewrites the queued frames like the NVDA driver's
+    applyVoiceToFrame (absolute override, then _mul factor, per parameter); the render equals uploading frames rewritten
+    on the host with the same rule, bit for bit, and the oracle's render of those frames within the precision's bar."""
+    sr, secs, n = 22050, 0.5, 70
+    fb = workloads.random_frames(n, secs, sr, first_stream=4000)
+    count = int(secs * sr)
+    va, vm = player.nvda_voice_tables([
+        {"cb1_mul": 1.3, "pa6_mul": 1.3, "fricationAmplitude_mul": 0.85},
+        {"cf1_mul": 1.01, "cf2_mul": 1.02, "cf4": 3770, "cf5": 4100, "cf6": 5000, "cfNP_mul": 0.9, "cb1_mul": 1.3,
+         "fricationAmplitude_mul": 0.7, "pa6_mul": 1.3},
+        {"aspirationAmplitude": 1, "voiceAmplitude": 0},
+        {"voicePitch_mul": 0.75, "endVoicePitch_mul": 0.75, "cf1_mul": 0.75, "cf2_mul": 0.85, "cf3_mul": 0.85}])
+    rng = np.random.default_rng(5)
+    vos = rng.integers(0, 4, size=n).astype(np.uint32)
+    # host rule
+    host = workloads._concat(sr, [fb.stream(s) for s in range(n)], fb.stream_ids)
+    for s in range(n):
+        a, b_ = int(host.offsets[s]), int(host.offsets[s + 1])
+        rows = host.frames[a:b_]
+        keep = host.is_null[a:b_] == 0
+        new = np.where(np.isnan(va[vos[s]]), rows, va[vos[s]]) * vm[vos[s]]
+        rows[keep] = new[keep]
+    b = player.Batch(sr, n, precision=precision, noise=player.NOISE_PHILOX, seed=SEED, stream_ids=fb.stream_ids)
+    b.set_frames_host(fb)
+    b.apply_voices(va, vm, vos)
+    dev_out, dev_w = b.synthesize_host(count)
+    b.set_frames_host(host)
+    host_out, host_w = b.synthesize_host(count)
+    b.close()
+    np.testing.assert_array_equal(dev_out, host_out)
+    np.testing.assert_array_equal(dev_w, host_w)
+    assert not np.array_equal(dev_out, _render(fb, sr, count, precision)[0])  # the voices did change the audio
+    for s in (0, 17, 42):
+        want = _oracle(port, host, sr, s, count)
+        if precision == player.PRECISION_FP64:
+            assert_f64_parity(dev_out[s, :len(want)], want, "voiced stream %d" % s)
+        else:
+            parity.assert_f32_parity(dev_out[s, :len(want)], want, "voiced stream %d" % s)
