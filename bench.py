@@ -27,6 +27,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in some images) goes nowhere near it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 W_HOLD, W_FADE_EXTRA = 128.0, 270.0  # flops per sample: hold tick, extra on a fade tick
 
