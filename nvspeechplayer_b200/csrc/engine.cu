@@ -77,11 +77,16 @@ using namespace klatt;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_lastError;
 
+namespace klatt {
+void setLastError(const char *what);  // also used by the host-only translation units (ipa_frames.cpp)
+}
 static int fail(const std::string &what) {
 	g_lastError = what;
 	if (getenv("NVSP_VERBOSE")) fprintf(stderr, "[nvspeechplayer_b200] %s\n", what.c_str());
 	return -1;
 }
+void klatt::setLastError(const char *what) { fail(what ? what : "error"); }
+
 static bool cudaOk(cudaError_t e, const char *what) {
 	if (e == cudaSuccess) return true;
 	fail(std::string(what) + ": " + cudaGetErrorString(e));

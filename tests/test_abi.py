@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for h in ("speechPlayer.h", "speechPlayer_batch.h"):
+    for h in ("speechPlayer.h", "speechPlayer_batch.h", "speechPlayer_ipa.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(speechPlayer_[A-Za-z]+)\s*\(", src))

@@ -160,3 +160,21 @@ def test_voices_applied_on_device_equal_host_rewritten_frames(port, precision):
             assert_f64_parity(dev_out[s, :len(want)], want, "voiced stream %d" % s)
         else:
             parity.assert_f32_parity(dev_out[s, :len(want)], want, "voiced stream %d" % s)
+
+
+def test_ipa_text_to_pcm_end_to_end(golden_config1):
+    """Config 1 without the reference's Python in the loop: sampleIpa.txt -> native bulk frame producer
+    (include/speechPlayer_ipa.h) -> one FP64 player -> the int16 stream the compiled reference renders from its own
+    ipa.py + speechPlayer.py (tests/golden/config1.npz), bit for bit."""
+    import os
+    from nvspeechplayer_b200 import ipa
+    g = golden_config1
+    lines = [str(t) for t in np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ipa_frames.npz"))["texts"][:8]]
+    sr = int(g["sample_rate"])
+    fb = ipa.frames_for_texts(lines, speed=0.6, sample_rate=sr, trailing_silence_ms=150.0)
+    p = player.SpeechPlayer(sr, precision=player.PRECISION_FP64, noise=player.NOISE_PHILOX, seed=int(g["philox_seed"]),
+                            streamId=int(g["philox_stream"]))
+    p.queue_frames(fb.frames, fb.min_dur, fb.fade_dur, None, fb.is_null)  # all eight lines into ONE player, in order
+    pcm = p.synthesize_np(300000)
+    p.close()
+    assert_f64_parity(pcm, g["pcm_philox"], "sampleIpa.txt end to end")
