@@ -494,8 +494,7 @@ KLATT_HD float oscillatorSide(DspState &S, const CoefF32 &C, double srD, double 
 }
 
 // cascade side (reference src/speechWaveGenerator.cpp:203-204, :72-86, :147-158) and the final mix (:207-208), as
-// stages: source -> nasal pair -> six sections -> output.  cascadeSide() runs them tick by tick; cascadeGroup() runs
-// the same stages of eight ticks as a wavefront.
+// stages: source -> nasal pair -> six sections -> output.
 // ---- aspiration noise + turbulence + glottal shaping (:40, :75-80), returns the cascade input (:147) ----
 KLATT_HD float stageSource(DspState &S, const CoefF32 &C, uint32_t wA, float voice) {
 	float uA = bitsToFloat(0x4B000000u | (wA >> 9)) - 8388608.0f;
@@ -542,45 +541,6 @@ KLATT_HD int cascadeSide(DspState &S, const CoefF32 &C, uint32_t wA, float par, 
 #pragma unroll
 	for (int q = 0; q < 6; ++q) x = stageSection(S, C, q, half(w, q), x);
 	return stageOut(C, x, par);
-}
-
-// Eight ticks of the cascade side with CONSTANT coefficients (hold chunks) as a wavefront: in step s, stage j works on
-// tick s - j.  Within a tick the stages form one dependent chain of ~35 operations (the hold kernel's cascade warps were
-// bound by exactly that chain: ncu showed their partner warps waiting at the pair barrier for half of their time), but
-// stage j of tick t+1 only needs stage j of tick t and stage j-1 of tick t+1, so a step offers nine independent
-// pieces of work.  Every stage does what cascadeSide() does, on the same values, in the same order per stage: same bits.
-// The memory parts of a pair of sections are taken at the top of each step: its two halves are one tick apart, which is
-// what the step needs.  voice[k] is the sawtooth of tick k; wA and par come from the hand-over records.
-constexpr int kCascadeStages = 9;  // source, nasal pair, six sections, output
-template <class Out, class Xchg>
-KLATT_HD void cascadeGroup(DspState &S, const CoefF32 &C, Xchg &xc, uint32_t t0, const float *voice, Out &out) {
-	float ci = 0.0f, xN = 0.0f, xq[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // pipeline registers between the stages
-#pragma unroll
-	for (int s = 0; s < kGroupTicks + kCascadeStages - 1; ++s) {
-		F2 w[3];
-#pragma unroll
-		for (int p = 0; p < 3; ++p) {  // pair p = sections 2p, 2p+1 = stages 2+2p, 3+2p
-			const bool active = (s - (2 + 2 * p) >= 0 && s - (2 + 2 * p) < kGroupTicks) || (s - (3 + 2 * p) >= 0 && s - (3 + 2 * p) < kGroupTicks);
-			if (active) w[p] = sectionMemory(S, C, 1 + p);
-		}
-		// last stage first: every stage reads what its predecessor produced in the previous step
-		if (s - 8 >= 0 && s - 8 < kGroupTicks) {
-			uint32_t wA;
-			float par, vo;
-			xc.get(t0 + (uint32_t)(s - 8), wA, par, vo);
-			out.push(stageOut(C, xq[5], par));
-		}
-#pragma unroll
-		for (int q = 5; q >= 0; --q)
-			if (s - (2 + q) >= 0 && s - (2 + q) < kGroupTicks) xq[q] = stageSection(S, C, q, half(w, q), q == 0 ? xN : xq[q - 1]);
-		if (s - 1 >= 0 && s - 1 < kGroupTicks) xN = stageNasal(S, C, ci);
-		if (s < kGroupTicks) {
-			uint32_t wA;
-			float par, vo;
-			xc.get(t0 + (uint32_t)s, wA, par, vo);
-			ci = stageSource(S, C, wA, voice ? voice[s] : vo);
-		}
-	}
 }
 
 // the two noise words of generated sample `gen` (Philox mode caches the 4-word block of samples 2b, 2b+1)
@@ -665,14 +625,7 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 	const bool evenPhilox = noise.mode == kNoisePhilox && (gen & 1ull) == 0;
 	for (uint32_t t = 0; t < ticks; t += kGroupTicks) {
 		if (T::hasC && !T::hasP) xc.sync();  // the parallel side has finished this group
-		if (T::hasC && !T::hasP) {  // cascade warp of a pair: the eight ticks as a wavefront
-			float voice[kGroupTicks];
-			if (T::hasO) {
-#pragma unroll
-				for (int k = 0; k < kGroupTicks; ++k) voice[k] = oscillatorSide(S, C, srD, srInv);
-			}
-			cascadeGroup(S, C, xc, t, T::hasO ? voice : nullptr, out);
-		} else if (!T::hasP || evenPhilox) {  // straight-line group: one Philox block per two ticks
+		if (!T::hasP || evenPhilox) {  // straight-line group: one Philox block per two ticks
 #pragma unroll
 			for (int k = 0; k < kGroupTicks; k += 2) {
 				Philox4 blk;
