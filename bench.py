@@ -454,14 +454,17 @@ def main():
                        "host_enqueue_ms_per_step": round(1e3 * sum(enqueue_s) / max(len(enqueue_s), 1), 2)},
             "roofline": {"bound": "fp32_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
-                         # (klatt_f32_general_pair_kernel, one 256-tick round over ~47k streams), ncu --set full capture
-                         # summarised in profiles/r01_v3_ncu_summary.txt; algorithmic output of that launch: 24 MB
-                         "traffic": 87.4e6 if (prec == player.PRECISION_FP32 and S == 65536 and args.workload == "batch") else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (klatt_f32_sched_kernel:
+                         # one launch = one step of config 3), ncu --set full capture summarised in
+                         # profiles/r01_v4_ncu_summary.txt; algorithmic bytes of that launch: 36.6 GB (int16 out + queues + plans)
+                         "traffic": 72.2e9 if (prec == player.PRECISION_FP32 and S == 65536 and args.workload == "batch"
+                                               and os.environ.get("NVSP_SCHED") != "rounds") else None,
                          "peak_source": "FFMA loop measured on this GPU in this run (MEASURED_PEAKS.json has no FP32 entry)"
                                         if fp32_peak_measured > 0 else "SMs x 128 x 2 x max SM clock",
                          "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
-                         "kernel": "klatt_f32_hold_kernel + klatt_f32_general_pair_kernel (rounds)" if prec == player.PRECISION_FP32 else "klatt_batch_f64_kernel",
+                         "kernel": ("klatt_batch_f64_kernel" if prec != player.PRECISION_FP32 else
+                                    "klatt_f32_hold_kernel + klatt_f32_general_pair_kernel (rounds)" if os.environ.get("NVSP_SCHED") == "rounds"
+                                    else "klatt_f32_sched_kernel (persistent stream scheduler: hold and general chunks of all streams in one launch)"),
                          "flops_per_launch": rendered * flops_per_sample, "kernel_ms": kernel_ms,
                          "kernel_share_of_step": kernel_ms / ms_per_step},
             "roofline_hbm": {"bound": "hbm", "achieved": out_bytes_per_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -207,9 +207,9 @@ struct RoundsCtx {
 	static constexpr uint32_t kMaxGroups = 8;
 	DevBuf listHold, listGen, counters, scratchRow;
 	DevBuf ring, ctl;            // stream scheduler (persistent kernel, klatt_f32_sched.cu)
-	bool persistent = false;     // NVSP_SCHED=persistent selects it; the default is the round-based launch sequence
+	bool persistent = true;      // the default; NVSP_SCHED=rounds selects the round-based launch sequence instead
 	uint32_t *hostFault = nullptr;  // pinned: the scheduler watchdog's verdict of the last call
-	uint32_t schedHoldTicks = 256, schedGenTicks = 256, schedBlocks = 0;
+	uint32_t schedHoldTicks = 512, schedGenTicks = 640, schedBlocks = 0;
 	cudaStream_t lanes[2 * kMaxGroups] = {};
 	cudaEvent_t evStart = nullptr, evFork[kMaxGroups] = {}, evJoin[kMaxGroups] = {};
 	uint32_t holdTicks = 512, genTicks = 256, minStreams = 2048, groups = 4;
@@ -228,9 +228,9 @@ struct RoundsCtx {
 		groups = std::min<uint32_t>(std::max<uint32_t>(envU("NVSP_GROUPS", 4), 1), kMaxGroups);
 		{
 			const char *e = getenv("NVSP_SCHED");
-			persistent = e && strcmp(e, "persistent") == 0;
-			schedGenTicks = std::max<uint32_t>(envU("NVSP_SCHED_GEN_TICKS", 256) & ~63u, 64);
-			schedHoldTicks = std::max<uint32_t>(envU("NVSP_SCHED_HOLD_TICKS", 256) & ~63u, 64);
+			persistent = !(e && strcmp(e, "rounds") == 0);
+			schedGenTicks = std::max<uint32_t>(envU("NVSP_SCHED_GEN_TICKS", 640) & ~63u, 64);
+			schedHoldTicks = std::max<uint32_t>(envU("NVSP_SCHED_HOLD_TICKS", 512) & ~63u, 64);
 			int dev = 0, sms = 0;
 			cudaGetDevice(&dev);
 			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -1,5 +1,5 @@
-// The persistent stream scheduler of the FP32 batch path (opt-in: NVSP_SCHED=persistent; the default is the
-// round-based launch sequence of klatt_f32.cu -- measured equal in throughput on config 3).
+// The persistent stream scheduler of the FP32 batch path: the default for pre-queued batches (NVSP_SCHED=rounds selects
+// the round-based launch sequence of klatt_f32.cu instead; DESIGN.md section 5b has the measurements of both).
 // Same render bodies as the round kernels (klatt_f32_core.cuh), so the same bits.
 //
 // This translation unit is compiled with -fmad=false like klatt_f32.cu AND with -Xptxas -dlcm=cg: the kernel moves a

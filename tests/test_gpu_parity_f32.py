@@ -148,6 +148,8 @@ def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
         monkeypatch.setenv("NVSP_GROUPS", "3")
         monkeypatch.setenv("NVSP_SCHED", "persistent" if mode == "sched" else "rounds")
         monkeypatch.setenv("NVSP_SCHED_BLOCKS", "3")  # fewer workers than stream batches: streams queue up in the rings
+        monkeypatch.setenv("NVSP_SCHED_HOLD_TICKS", "256")  # several chunks of both classes per stream in a 1-s render
+        monkeypatch.setenv("NVSP_SCHED_GEN_TICKS", "128")
         b = player.Batch(sr, n, precision=player.PRECISION_FP32, seed=77, stream_ids=fb.stream_ids)
         b.set_frames_host(fb)
         parts, written = [], np.zeros(n, dtype=np.int64)
