@@ -165,6 +165,12 @@ KLATT_HD void plannedFrames(const double *prevReal, bool prevIsNull, const doubl
 // oscillators overlap with the cascade chain there, and the parallel side carries the Philox generator).
 enum Role : int { kRoleBoth = 0, kRoleCascade = 1, kRoleParallel = 2, kRoleCascadeOsc = 3, kRoleParallelOnly = 4 };
 constexpr int kGroupTicks = 8;  // hand-over granularity, and one 16-byte output store
+#ifndef KLATT_HOLD_UNROLL
+#define KLATT_HOLD_UNROLL 1
+#endif
+constexpr int kHoldUnroll = KLATT_HOLD_UNROLL;  // tick PAIRS of a hold group per loop body.  1, not the whole group (4): the hold loops
+                                                // were 21 KB of straight-line code and ncu showed 10 % of the stall samples waiting for
+                                                // instructions; measured 225.8 -> 221.9 ms (config 3), 175.0 -> 163.6 ms (config 5)
 
 template <int ROLE> struct RoleTraits {
 	static constexpr bool hasC = ROLE == kRoleBoth || ROLE == kRoleCascade || ROLE == kRoleCascadeOsc;      // cascade side
@@ -626,7 +632,7 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 	for (uint32_t t = 0; t < ticks; t += kGroupTicks) {
 		if (T::hasC && !T::hasP) xc.sync();  // the parallel side has finished this group
 		if (!T::hasP || evenPhilox) {  // straight-line group: one Philox block per two ticks
-#pragma unroll
+#pragma unroll(kHoldUnroll)
 			for (int k = 0; k < kGroupTicks; k += 2) {
 				Philox4 blk;
 				if (T::hasP) blk = noiseBlock(noise.seed, streamId, (gen + k) >> 1);
