@@ -34,6 +34,12 @@
 #include "klatt_common.h"
 #include "philox.cuh"
 
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define KLATT_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define KLATT_UNLIKELY(x) (x)
+#endif
+
 namespace klatt {
 
 // slots of GenStateF32::dir
@@ -758,7 +764,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 		if (active) {
 			// ================= frame manager, src/frame.cpp:41-80, entered only on event ticks =================
 			counter++;
-			if (counter >= nextEvent) {
+			if (KLATT_UNLIKELY(counter >= nextEvent)) {
 				if (hasNew) {
 					if (counter > newF) {  // :44-47 the fade is over: new becomes old; cur keeps its ratio-1 value
 						if (ROLE == kRoleBoth && !planned)
@@ -880,7 +886,7 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 			OscChain osc;
 			kf += kfStep;
 			if (T::hasO) S.vibInc += vibIncStep;
-			if ((gen & (uint64_t)(kCoarseTicks - 1)) == 0 && kfStep != 0.0f) {
+			if (KLATT_UNLIKELY((gen & (uint64_t)(kCoarseTicks - 1)) == 0 && kfStep != 0.0f)) {
 				// drift control, on a grid of ABSOLUTE sample indices (identical for every chunking of the render, and
 				// the same loop iteration for every lane of a batch that started together): the poles of this tick come
 				// from the coarse recurrence instead of the per-tick one
