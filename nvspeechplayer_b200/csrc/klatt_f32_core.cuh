@@ -65,15 +65,19 @@ KLATT_HD constexpr int directParam(int i) {
 // rewrites (src/frame.cpp:59-71).  NaN in a target keeps the old value (src/utils.h:21).  voicePitch is not
 // part of the plan (it is tracked in FP64 by the render kernels).
 // ---------------------------------------------------------------------------------------------------
+// 1 - exp(x + i*th) as (re, im), cancellation-free: 1 - r cos(th) = -expm1(x) + 2 r sin^2(th/2), r sin(th) = 2 r sin(th/2) cos(th/2).
+// One expm1 and one sincos (the plan kernel spends all its time in these: 4 per resonator per request).
+KLATT_HD void oneMinusExp(double x, double th, float &re, float &im) {
+	double em1 = expm1(x);  // r - 1
+	double r = 1.0 + em1;
+	double sh, ch;
+	sincos(0.5 * th, &sh, &ch);
+	re = (float)(-em1 + 2.0 * r * sh * sh);
+	im = (float)(-r * (2.0 * sh * ch));
+}
 KLATT_HD void poleTerms(double f, double bw, double srInv, float &zre, float &zim) {
 	const double PI = 3.14159265358979323846;
-	double x = -PI * bw * srInv;        // log of the pole radius
-	double th = 2.0 * PI * f * srInv;   // pole angle
-	double em1 = expm1(x);              // r - 1
-	double r = 1.0 + em1;
-	double sh = sin(0.5 * th);
-	zre = (float)(-em1 + 2.0 * r * sh * sh);  // 1 - r*cos(th), cancellation-free
-	zim = (float)(-r * sin(th));
+	oneMinusExp(-PI * bw * srInv /* log of the pole radius */, 2.0 * PI * f * srInv /* pole angle */, zre, zim);
 }
 
 // vibratoSpeed (Hz) -> phase increment per tick in 2^-64 cycles
@@ -114,17 +118,8 @@ KLATT_HD void planFade(const double *o, const double *n, uint32_t F, int sampleR
 		const double PI = 3.14159265358979323846;
 		double xs = -PI * (b1 - b0) * invF * srInv;
 		double dth = 2.0 * PI * (f1 - f0) * invF * srInv;
-		double qm1 = expm1(xs);
-		double q = 1.0 + qm1;
-		double sh = sin(0.5 * dth);
-		p.wre[r] = (float)(-qm1 + 2.0 * q * sh * sh);
-		p.wim[r] = (float)(-q * sin(dth));
-		{  // the same pole ratio over kCoarseTicks ticks
-			double xsA = xs * kCoarseTicks, dthA = dth * kCoarseTicks;
-			double QAm1 = expm1(xsA), QA = 1.0 + QAm1, shA = sin(0.5 * dthA);
-			p.Wre[r] = (float)(-QAm1 + 2.0 * QA * shA * shA);
-			p.Wim[r] = (float)(-QA * sin(dthA));
-		}
+		oneMinusExp(xs, dth, p.wre[r], p.wim[r]);
+		oneMinusExp(xs * kCoarseTicks, dth * kCoarseTicks, p.Wre[r], p.Wim[r]);  // the same pole ratio over kCoarseTicks ticks
 		if (r == kResN0) {
 			p.n0InvFade = !(f0 == 0 && f1 == 0);
 			p.n0InvFinal = (f0 + ((f1 - f0) * 1.0)) != 0;
