@@ -1,0 +1,143 @@
+// klatt_pull_kernel: one pull of one player in one thread block, parallel in time (see klatt_pull_core.cuh for the
+// scheme and for the per-thread passes; this file adds the block scans and the launcher).
+//
+// 512 threads; thread i owns ticks [i*L, (i+1)*L) of the pull.  The two signals every stage reads and rewrites in place
+// (cascade chain, parallel chain) and the per-tick phase increments live in dynamic shared memory, tick-major ([L][512]: the threads of a warp touch
+// consecutive banks).  Affine maps never leave registers: the scans are warp-shuffle scans (the pattern of
+// klatt_long_scan_kernel with one chunk per thread) with a 16-entry shared array for the warp totals, seeded with the
+// state the player carries from its previous pull.
+#include <cuda_runtime.h>
+#include "klatt_common.h"
+#include "klatt_pull_core.cuh"
+
+namespace klatt {
+
+namespace {
+
+constexpr int kPullWarps = kPullThreads / 32;
+
+__device__ __forceinline__ PullAffineD shflUpD(const PullAffineD &m, int delta) {
+	PullAffineD r;
+	r.p00 = __shfl_up_sync(0xffffffffu, m.p00, delta); r.p01 = __shfl_up_sync(0xffffffffu, m.p01, delta);
+	r.p10 = __shfl_up_sync(0xffffffffu, m.p10, delta); r.p11 = __shfl_up_sync(0xffffffffu, m.p11, delta);
+	r.zy = __shfl_up_sync(0xffffffffu, m.zy, delta); r.zd = __shfl_up_sync(0xffffffffu, m.zd, delta);
+	return r;
+}
+
+// Composition of `seed` and the maps of all threads before this one, in order.  Every thread of the block calls it.
+__device__ PullAffineD blockExclusive(const PullAffineD &own, const PullAffineD &seed, PullAffineD *warpTotal) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	PullAffineD inc = own;
+#pragma unroll
+	for (int delta = 1; delta < 32; delta <<= 1) {
+		PullAffineD up = shflUpD(inc, delta);
+		if (lane >= delta) inc = pullCompose(inc, up);
+	}
+	if (lane == 31) warpTotal[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		PullAffineD w = lane < kPullWarps ? warpTotal[lane] : pullIdentity();
+#pragma unroll
+		for (int delta = 1; delta < kPullWarps; delta <<= 1) {
+			PullAffineD up = shflUpD(w, delta);
+			if (lane >= delta) w = pullCompose(w, up);
+		}
+		if (lane < kPullWarps) warpTotal[lane] = w;
+	}
+	__syncthreads();
+	// exclusive prefix = (inclusive of the previous lane) after (inclusive total of the earlier warps) after the seed
+	PullAffineD prev = shflUpD(inc, 1);
+	PullAffineD pre = lane == 0 ? pullIdentity() : prev;
+	if (warp > 0) pre = pullCompose(pre, warpTotal[warp - 1]);
+	pre = pullCompose(pre, seed);
+	__syncthreads();  // warpTotal may be reused; every read of the carried state is behind us
+	return pre;
+}
+
+__device__ __forceinline__ PullAffineD seedOf(float y, float d) { return PullAffineD{1.0, 0.0, 0.0, 1.0, (double)y, (double)d}; }
+
+template <int STAGE>
+__device__ __forceinline__ void runStage(const PullCtx &X, uint32_t ch, int res, PullAffineD *warpTotal) {
+	constexpr int NR = PullStageTraits<STAGE>::NR;
+	PullAffine maps[NR];
+	PullStart st[NR];
+	float fir[2] = {0.0f, 0.0f};
+	pullStage<STAGE, 1>(X, ch, res, maps, nullptr, fir);
+#pragma unroll
+	for (int k = 0; k < NR; ++k) {
+		const int r = STAGE == kPullParallel ? kResParallel + k : res;
+		const PullAffineD pre = blockExclusive(pullToD(maps[k]), seedOf(X.state->y[r], X.state->d[r]), warpTotal);
+		st[k].y = (float)pre.zy;
+		st[k].d = (float)pre.zd;
+	}
+	pullStage<STAGE, 2>(X, ch, res, nullptr, st, fir);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kPullThreads)
+klatt_pull_kernel(PullCtx X) {
+	extern __shared__ float pullSignals[];
+	__shared__ PullAffineD warpTotal[kPullWarps];
+	X.sigA = pullSignals;
+	X.sigB = pullSignals + (size_t)X.L * kPullThreads;
+	X.inc = reinterpret_cast<double *>(X.sigB);  // 2 x the size of sigB; dead before sigB is first written
+	const uint32_t ch = threadIdx.x;
+
+	// source: phase increments and noise colouring per chunk, the phase recurrence by one thread, then the excitation
+	{
+		PullSourceSums sums;
+		pullSourcePass1(X, ch, sums);
+		const PullAffineD own{(double)sums.decay, 0.0, 0.0, (double)sums.decay, (double)sums.zAsp, (double)sums.zFric};
+		const PullAffineD pre = blockExclusive(own, seedOf(X.state->aspLast, X.state->fricLast), warpTotal);
+		if (ch == 0) pullPhaseSerial(X);
+		__syncthreads();
+		pullSourcePass2(X, ch, (float)pre.zy, (float)pre.zd);
+	}
+	__syncthreads();  // the FIR section of the nasal stage reads its neighbours' last two cascade inputs
+
+	runStage<kPullParallel>(X, ch, 0, warpTotal);
+	runStage<kPullNasal>(X, ch, kResNP, warpTotal);
+	for (int r = kResCascade; r < kResParallel - 1; ++r) runStage<kPullCascade>(X, ch, r, warpTotal);
+	runStage<kPullLast>(X, ch, kResParallel - 1, warpTotal);
+
+	__syncthreads();
+	if (ch == 0) X.state->generated += X.n;
+}
+
+__global__ void klatt_pull_init_kernel(PullState *s) {
+	// src/speechWaveGenerator.cpp:37,49,104-110: phases, noise memories and resonator histories start at zero
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		for (int r = 0; r < kNumResonators; ++r) { s->y[r] = 0.0f; s->d[r] = 0.0f; }
+		s->aspLast = 0.0f; s->fricLast = 0.0f; s->pitchPos = 0.0; s->generated = 0;
+	}
+}
+
+cudaError_t launchKlattPullInit(PullState *state, cudaStream_t stream) {
+	klatt_pull_init_kernel<<<1, 32, 0, stream>>>(state);
+	return cudaGetLastError();
+}
+
+// ctx.sigA / sigB / L are filled in here; everything else by the caller.  ctx.n <= kPullMaxTicks.
+cudaError_t launchKlattPull(PullCtx ctx, cudaStream_t stream) {
+	if (ctx.n == 0) return cudaSuccess;
+	if (ctx.n > kPullMaxTicks || ctx.nSeg == 0 || ctx.nSeg > kPullMaxSegs) return cudaErrorInvalidValue;
+	static bool attrSet[64] = {};
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	constexpr size_t kMaxSmem = 3 * (size_t)kPullMaxTicks * sizeof(float);  // sigA | sigB aliased by the first half of inc
+	if (dev >= 0 && dev < 64 && !attrSet[dev]) {
+		e = cudaFuncSetAttribute(klatt_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+		if (e != cudaSuccess) return e;
+		attrSet[dev] = true;
+	}
+	ctx.L = (ctx.n + kPullThreads - 1) / kPullThreads;
+	ctx.sigA = ctx.sigB = nullptr;
+	ctx.inc = nullptr;
+	const size_t smem = 3 * (size_t)ctx.L * kPullThreads * sizeof(float);
+	klatt_pull_kernel<<<1, kPullThreads, smem, stream>>>(ctx);
+	return cudaGetLastError();
+}
+
+}  // namespace klatt

@@ -1,0 +1,483 @@
+// klatt_pull: the low-latency path of the per-handle API: ONE pull of one player
+// (speechPlayer_synthesize(handle, n, buf), the call the NVDA audio thread makes, reference
+// nvdaAddon/synthDrivers/nvSpeechPlayer/__init__.py:56-82) rendered by ONE thread block, parallel in time, with the
+// state of the stream carried in and out.  It is klatt_long.cu's scheme (affine maps of the two-pole sections over a
+// chunk, composed by a scan) brought down to chunks of <= 16 ticks held in shared memory:
+//
+//   host   the frame manager runs at REQUEST granularity in FP64, exactly as reference src/frame.cpp:41-115 (pop,
+//          NULL-frame rewrites, swap, hold glide, drain, purge): pull_manager.h.  For a pull it emits the runs of ticks
+//          (PullSeg) the pull consists of, each with the fade plan of its request (planFade, klatt_f32_core.cuh) and the
+//          values in force on the pop tick.  Everything a tick needs is then a closed form of (segment, sampleCounter).
+//   device 512 threads, thread i renders ticks [i*L, (i+1)*L) of the pull, L = ceil(n / 512).  Source (vibrato, the two
+//          coloured noises; the glottal phase recurrence is the one serial step, see "source" below), parallel bank,
+//          rN0+rNP, r6 ... r1: per stage, pass 1 runs the chunk from zero state and accumulates its affine map, a block scan
+//          (warp shuffles, seeded with the carried-in state) gives every chunk its true start state, pass 2 renders the
+//          chunk in place in shared memory.  The last stage fuses mix, gain, clamp and the int16 store.
+//
+// The per-thread passes below are written against plain pointers (KLATT_HD) so that tests/hostsim can run the very
+// same arithmetic "thread by thread" on the host; only the block scans differ (shuffles on the device, a plain loop in
+// the test build).  The arithmetic of a tick is the FP32 formulation of klatt_f32_core.cuh; parity with the reference is
+// by the FP32 bar (<= 1 LSB on >= 99.9 %, >= 60 dB), not bit for bit (the scan re-associates).
+#pragma once
+#include "klatt_common.h"
+#include "klatt_f32_core.cuh"
+
+namespace klatt {
+
+constexpr int kPullThreads = 512;
+constexpr uint32_t kPullMaxTicks = 8192;  // per launch: <= 16 ticks per thread, two float signals = 64 KB of shared memory
+constexpr uint32_t kPullMaxSegs = 32;     // requests one launch may touch (a longer pull is cut into several launches)
+
+// One run of consecutive ticks of one request inside a pull.
+struct alignas(16) PullSeg {
+	FadePlanF32 plan;                       // fade old -> new of the request (src/frame.cpp:49-52), pitch excluded
+	double fb[kNumResonators][4];           // f0, f1, b0, b1 of each section (NaN targets resolved): exact pole on re-basing
+	double pitchStale, pitchOld, pitchNew;  // cur.voicePitch on the pop tick; end points of the fade (frame.cpp:61,71)
+	double pitchInc;                        // hold glide (frame.cpp:77,98)
+	uint64_t vibPosAtPop;                   // vibrato phase before the pop tick, 2^-64 cycles
+	int64_t vibIncStale;                    // vibrato increment on the pop tick
+	float dirStale[kNumDirect];             // direct params on the pop tick (curFrame is not touched there, frame.cpp:55-72)
+	float zStaleRe[kNumResonators], zStaleIm[kNumResonators];
+	uint32_t n0InvStale;
+	uint32_t F;          // numFadeSamples, >= 1 (reference src/speechPlayer.cpp:36)
+	uint32_t c0;         // sampleCounter on the run's first tick (0 = the pop tick)
+	uint32_t tickStart;  // first tick of the run, counted from the start of the pull
+	uint32_t count;
+	uint32_t pad[3];
+};
+static_assert(sizeof(PullSeg) % 16 == 0, "segments are copied as 16-byte words");
+
+// What a player carries from one pull to the next (device memory).
+struct PullState {
+	float y[kNumResonators];  // delta-form memories as in GenStateF32: last output; rN0: last INPUT
+	float d[kNumResonators];  //                                          last output difference; rN0: last input difference
+	float aspLast, fricLast;  // coloured-noise memories, units of 2^-23
+	double pitchPos;          // glottal phase in cycles, FP64 and accumulated exactly like the reference's (:55)
+	uint64_t generated;       // samples generated so far == noise draws consumed / 2
+};
+
+struct PullCtx {
+	const PullSeg *segs;
+	uint32_t nSeg, n, L;  // n ticks in this pull, L ticks per thread
+	int sampleRate;
+	float *sigA, *sigB;   // [L][kPullThreads]: tick t of the pull lives at (t % L) * kPullThreads + t / L
+	double *inc;          // same layout: glottal phase increment of every tick (dead once the sawtooth is in sigA: may
+	                      // share its storage with sigB)
+	PullState *state;
+	int noiseMode;
+	uint64_t seed, streamId;
+	const int32_t *draws;  // kNoiseGlibc / kNoiseReplay: rand() values, draw 2g = aspiration, 2g+1 = frication
+	uint64_t drawBase, drawLen;
+	int16_t *pcm;
+};
+
+// affine map of one section over one chunk, (y, d)_end = P (y, d)_start + z, row-major P
+struct PullAffine {
+	float p00, p01, p10, p11, zy, zd;
+};
+struct PullStart {
+	float y, d;
+};
+
+// vibrato: increment on tick (seg, c) and the sum of the increments of ticks [0, c) of the request
+KLATT_HD int64_t pullVibInc(const PullSeg &s, uint32_t c) {
+	return c == 0 ? s.vibIncStale : (c < s.F ? s.plan.vibInc0 + (int64_t)c * s.plan.vibIncStep : s.plan.vibIncFinal);
+}
+KLATT_HD uint64_t pullVibBefore(const PullSeg &s, uint32_t c) {
+	if (c == 0) return 0;
+	uint64_t sum = (uint64_t)s.vibIncStale;
+	const uint64_t kmax = (c - 1 < s.F - 1) ? c - 1 : s.F - 1;  // fade ticks 1 .. kmax are behind us
+	sum += kmax * (uint64_t)s.plan.vibInc0 + (uint64_t)s.plan.vibIncStep * (kmax * (kmax + 1) / 2);
+	if (c > s.F) sum += (uint64_t)(c - s.F) * (uint64_t)s.plan.vibIncFinal;
+	return sum;
+}
+
+// cur.voicePitch on tick (seg, c): stale on the pop tick, the fade (src/utils.h:20-23), the landing value on the landing
+// and the swap tick, then the hold glide (src/frame.cpp:77) as an arithmetic progression
+KLATT_HD double pullPitchAt(const PullSeg &s, uint32_t c) {
+	if (c == 0) return s.pitchStale;
+	const double o = s.pitchOld, n = s.pitchNew;
+	if (c < s.F) return (n != n) ? o : o + ((n - o) * ((double)c / (double)s.F));
+	const double landing = (n != n) ? o : o + ((n - o) * 1.0);
+	if (c <= s.F + 1) return landing;
+	return landing + (double)(c - s.F - 1) * s.pitchInc;
+}
+
+KLATT_HD float pullDirAt(const PullSeg &s, int slot, uint32_t c) {
+	return c == 0 ? s.dirStale[slot] : (c < s.F ? fmaf((float)c, s.plan.dirStep[slot], s.plan.dir0[slot]) : s.plan.dirFinal[slot]);
+}
+
+KLATT_HD bool pullN0InvAt(const PullSeg &s, uint32_t c) {
+	if (c == 0) return s.n0InvStale != 0;
+	return (c < s.F ? s.plan.n0InvFade : s.plan.n0InvFinal) != 0;
+}
+
+// where a tick sits: segment, sampleCounter value on that tick, ticks of the segment still to come (this one included)
+struct PullCursor {
+	uint32_t s, c, left;
+	KLATT_HD void seek(const PullCtx &X, uint32_t t) {
+		uint32_t lo = 0, hi = X.nSeg;  // last segment with tickStart <= t
+		while (hi - lo > 1) {
+			uint32_t mid = (lo + hi) >> 1;
+			if (X.segs[mid].tickStart <= t) lo = mid; else hi = mid;
+		}
+		s = lo;
+		c = X.segs[s].c0 + (t - X.segs[s].tickStart);
+		left = X.segs[s].count - (t - X.segs[s].tickStart);
+	}
+	KLATT_HD void next(const PullCtx &X) {
+		++c;
+		if (--left == 0 && s + 1 < X.nSeg) {
+			++s;
+			c = X.segs[s].c0;
+			left = X.segs[s].count;
+		}
+	}
+};
+
+// zeta = 1 - pole of one section along the pull (klatt_long.cu PoleWalk over segments)
+struct PullPole {
+	float zr, zi, wr, wi;
+	KLATT_HD void exact(const PullSeg &S, uint32_t k, int r, double srInv) {
+		const double ratio = (double)k / (double)S.F;
+		const double f0 = S.fb[r][0], f1 = S.fb[r][1], b0 = S.fb[r][2], b1 = S.fb[r][3];
+		poleTerms(f0 + ((f1 - f0) * ratio), b0 + ((b1 - b0) * ratio), srInv, zr, zi);
+	}
+	// state as it is AFTER the tick before (S, c)
+	KLATT_HD void seek(const PullSeg &S, uint32_t c, int r, double srInv) {
+		wr = wi = 0.0f;
+		if (c <= 1) {
+			zr = S.zStaleRe[r]; zi = S.zStaleIm[r];
+		} else if (c <= S.F) {  // ticks 1 .. c-1 of the fade are behind us
+			exact(S, c - 1, r, srInv);
+			wr = S.plan.wre[r]; wi = S.plan.wim[r];
+		} else {
+			zr = S.plan.zFre[r]; zi = S.plan.zFim[r];
+		}
+	}
+	// the update of tick (S, c): afterwards (zr, zi) is what the tick renders with
+	KLATT_HD void tick(const PullSeg &S, uint32_t c, int r, double srInv) {
+		if (c == 0) {  // pop tick: what was in force before
+			zr = S.zStaleRe[r]; zi = S.zStaleIm[r]; wr = wi = 0.0f;
+			return;
+		}
+		if (c > S.F) return;  // after the landing: constant
+		if (c == S.F) {
+			zr = S.plan.zFre[r]; zi = S.plan.zFim[r]; wr = wi = 0.0f;
+			return;
+		}
+		if (c == 1) {
+			zr = S.plan.z0re[r]; zi = S.plan.z0im[r]; wr = S.plan.wre[r]; wi = S.plan.wim[r];
+		}
+		if ((c & (uint32_t)(kCoarseTicks - 1)) == 0) {
+			exact(S, c, r, srInv);  // drift control: back onto the closed form
+			return;
+		}
+		float tr = fmaf(-zr, wr, wr);
+		tr = fmaf(zi, wi, tr);
+		float ti = fmaf(-zr, wi, wi);
+		ti = fmaf(-zi, wr, ti);
+		zr += tr;
+		zi += ti;
+	}
+	KLATT_HD void coef(float &a, float &rho) const {
+		a = fmaf(zr, zr, zi * zi);
+		rho = fmaf(2.0f, zr, -a);
+	}
+};
+
+KLATT_HD uint32_t pullIdx(const PullCtx &X, uint32_t t) { return (t % X.L) * (uint32_t)kPullThreads + t / X.L; }
+
+// the two noise words of generated sample g (word position: the 23 bits used are w >> 9)
+KLATT_HD void pullNoiseWords(const PullCtx &X, uint64_t g, Philox4 &blk, uint64_t &blkIndex, uint32_t &wA, uint32_t &wF) {
+	if (X.noiseMode == kNoisePhilox) {
+		const uint64_t b = g >> 1;
+		if (b != blkIndex) { blk = noiseBlock(X.seed, X.streamId, b); blkIndex = b; }
+		wA = (g & 1) ? blk.w[2] : blk.w[0];
+		wF = (g & 1) ? blk.w[3] : blk.w[1];
+	} else {  // rand() values (31 bits): shift into word position
+		const uint64_t d0 = 2 * g - X.drawBase;
+		wA = (d0 < X.drawLen) ? ((uint32_t)X.draws[d0] << 1) : 0u;
+		wF = (d0 + 1 < X.drawLen) ? ((uint32_t)X.draws[d0 + 1] << 1) : 0u;
+	}
+}
+KLATT_HD float pullDraw(uint32_t w) { return bitsToFloat(0x4B000000u | (w >> 9)) - 8388608.0f; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// source (reference src/speechWaveGenerator.cpp:32-88, :204-206)
+//
+// The glottal phase is the one quantity of the path that is NOT rendered in parallel: the reference accumulates it as
+// fmod(pos + f/sr, 1) in double (src/speechWaveGenerator.cpp:55), and a pitch whose period is a whole number of samples
+// (150 Hz at 22 050 Hz) makes the wrap instant a matter of the last bit of that running sum -- a wrap one sample apart
+// from the reference's is a full-scale error once per period (klatt_f32_core.cuh OscChain has the same concern).  No
+// associative reformulation reproduces a sequence of roundings, so: every thread prepares the per-tick increments of
+// its chunk in parallel (vibrato sine, pitch, the correctly rounded division -- the expensive part), and ONE thread then
+// runs the bare recurrence pos = frac(pos + inc[t]) over the pull, two dependent FP64 additions per tick.
+// ---------------------------------------------------------------------------------------------------------------
+struct PullSourceSums {
+	float zAsp, zFric;   // colouring filters at the end of the chunk when started from zero
+	float decay;         // 0.75 ^ (ticks in the chunk)
+};
+
+struct PullOsc {  // vibrato + pitch along the pull
+	PullCursor cur;
+	uint64_t vibPos;
+	KLATT_HD void seek(const PullCtx &X, uint32_t t) {
+		cur.seek(X, t);
+		const PullSeg &S = X.segs[cur.s];
+		vibPos = S.vibPosAtPop + pullVibBefore(S, cur.c);
+	}
+	// what this tick adds to the glottal phase, in cycles: (pitch * vibrato) / sampleRate as the reference rounds it
+	// (src/speechWaveGenerator.cpp:72-74, :55)
+	KLATT_HD double phaseInc(const PullCtx &X, double srD, double srInv) {
+		const PullSeg &S = X.segs[cur.s];
+		vibPos += (uint64_t)pullVibInc(S, cur.c);
+		float vph = (float)(int32_t)(uint32_t)(vibPos >> 32) * 2.3283064365386963e-10f;
+		float vib = (sinTurns(vph) * 0.06f) * pullDirAt(S, dVibratoPitchOffset, cur.c);
+		double m = pullPitchAt(S, cur.c) * ((double)vib + 1.0);
+		return divideBySampleRate(m, srD, srInv);
+	}
+	KLATT_HD void next(const PullCtx &X) {
+		const uint32_t was = cur.s;
+		cur.next(X);
+		if (cur.s != was) vibPos = X.segs[cur.s].vibPosAtPop + pullVibBefore(X.segs[cur.s], cur.c);
+	}
+};
+
+KLATT_HD void pullChunkRange(const PullCtx &X, uint32_t ch, uint32_t &t0, uint32_t &t1) {
+	const uint64_t a = (uint64_t)ch * X.L;
+	t0 = a < X.n ? (uint32_t)a : X.n;
+	t1 = (a + X.L < X.n) ? (uint32_t)(a + X.L) : X.n;
+}
+
+// pass 1: the phase increment of every tick of the chunk -> X.inc, and what the chunk adds to the two noise filters
+KLATT_HD void pullSourcePass1(const PullCtx &X, uint32_t ch, PullSourceSums &out) {
+	uint32_t t0, t1;
+	pullChunkRange(X, ch, t0, t1);
+	out.zAsp = 0.0f; out.zFric = 0.0f; out.decay = 1.0f;
+	if (t0 >= t1) return;
+	const double srD = (double)X.sampleRate, srInv = 1.0 / srD;
+	const uint64_t g0 = X.state->generated;
+	PullOsc w;
+	w.seek(X, t0);
+	Philox4 blk;
+	blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
+	uint64_t blkIndex = ~0ull;
+	uint32_t at = ch;
+	for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
+		uint32_t wA, wF;
+		pullNoiseWords(X, g0 + t, blk, blkIndex, wA, wF);
+		out.zAsp = fmaf(0.75f, out.zAsp, pullDraw(wA));
+		out.zFric = fmaf(0.75f, out.zFric, pullDraw(wF));
+		out.decay *= 0.75f;
+		X.inc[at] = w.phaseInc(X, srD, srInv);
+		w.next(X);
+	}
+}
+
+// the recurrence itself (one thread): the sawtooth value of every tick -> sigA (src/speechWaveGenerator.cpp:55, :74)
+KLATT_HD void pullPhaseSerial(const PullCtx &X) {
+	double pos = X.state->pitchPos;
+	for (uint32_t ch = 0; ch < (uint32_t)kPullThreads; ++ch) {
+		uint32_t t0, t1;
+		pullChunkRange(X, ch, t0, t1);
+		if (t0 >= t1) break;
+		uint32_t at = ch;
+		for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
+			pos = fracRef(X.inc[at] + pos);
+			X.sigA[at] = (float)pos;
+		}
+	}
+	X.state->pitchPos = pos;
+}
+
+// pass 2: the two excitation signals of every tick: cascade input -> sigA (:204, :148), parallel input -> sigB (:206, :171)
+KLATT_HD void pullSourcePass2(const PullCtx &X, uint32_t ch, float aspStart, float fricStart) {
+	uint32_t t0, t1;
+	pullChunkRange(X, ch, t0, t1);
+	if (t0 >= t1) return;
+	const uint64_t g0 = X.state->generated;
+	PullCursor cur;
+	cur.seek(X, t0);
+	float aspLast = aspStart, fricLast = fricStart;
+	Philox4 blk;
+	blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
+	uint64_t blkIndex = ~0ull;
+	uint32_t at = ch;
+	for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
+		uint32_t wA, wF;
+		pullNoiseWords(X, g0 + t, blk, blkIndex, wA, wF);
+		const PullSeg &S = X.segs[cur.s];
+		const uint32_t c = cur.c;
+		const float voice = X.sigA[at];
+		aspLast = fmaf(0.75f, aspLast, pullDraw(wA));
+		float asp = aspLast * (0.2f * kDrawScale);
+		float turb = asp * pullDirAt(S, dVoiceTurbulenceAmplitude, c);
+		if (voice < pullDirAt(S, dGlottalOpenQuotient, c)) turb *= 0.01f;
+		float v = (fmaf(voice, 2.0f, -1.0f) + turb) * pullDirAt(S, dVoiceAmplitude, c);
+		float src = fmaf(asp, pullDirAt(S, dAspirationAmplitude, c), v);
+		const float halfGain = pullDirAt(S, dPreFormantGain, c) * 0.5f;
+		X.sigA[at] = src * halfGain;
+		fricLast = fmaf(0.75f, fricLast, pullDraw(wF));
+		X.sigB[at] = fricLast * (((0.3f * kDrawScale) * pullDirAt(S, dFricationAmplitude, c)) * halfGain);
+		cur.next(X);
+	}
+	if (t1 == X.n) {  // the pull's last chunk leaves the carry
+		X.state->aspLast = aspLast;
+		X.state->fricLast = fricLast;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// resonator stages (reference src/speechWaveGenerator.cpp:112-182, :207-208)
+// ---------------------------------------------------------------------------------------------------------------
+enum PullStage : int { kPullParallel = 0, kPullNasal = 1, kPullCascade = 2, kPullLast = 3 };
+template <int STAGE> struct PullStageTraits {
+	static constexpr int NR = STAGE == kPullParallel ? 6 : 1;  // scanned sections
+};
+
+// input of the FIR section before tick t of the pull (t may reach 2 ticks into the previous pull)
+KLATT_HD float pullFirInput(const PullCtx &X, int64_t t) {
+	if (t >= 0) return X.sigA[pullIdx(X, (uint32_t)t)];
+	const float in1 = X.state->y[kResN0];
+	return t == -1 ? in1 : in1 - X.state->d[kResN0];
+}
+
+// One chunk of one stage.  PASS 1: from zero state, accumulate the affine map.  PASS 2: from the scanned start state,
+// overwrite the stage's input signal with its output (or, for the last stage, store the int16 samples).
+//   kPullParallel: sigB = frication input -> sections 8..13 -> parallel output (:170-180)
+//   kPullNasal   : sigA = cascade input -> rN0 (FIR) -> rNP (section 1) -> caNP mix (:148-150)
+//   kPullCascade : sigA -> section `res` (:151-155)
+//   kPullLast    : like kPullCascade for r1, then (x + par) * outputGain * 4000, clamp, truncate (:207-208)
+// fir[2]: the two inputs before the chunk, read in pass 1 (before any thread overwrites sigA) and handed to pass 2.
+template <int STAGE, int PASS>
+KLATT_HD void pullStage(const PullCtx &X, uint32_t ch, int res, PullAffine *maps, const PullStart *start, float *fir) {
+	constexpr int NR = PullStageTraits<STAGE>::NR;
+	uint32_t t0, t1;
+	pullChunkRange(X, ch, t0, t1);
+	if (PASS == 1) {
+#pragma unroll
+		for (int k = 0; k < NR; ++k) {
+			maps[k].p00 = 1.0f; maps[k].p01 = 0.0f; maps[k].p10 = 0.0f; maps[k].p11 = 1.0f; maps[k].zy = 0.0f; maps[k].zd = 0.0f;
+		}
+	}
+	if (t0 >= t1) return;
+	const double srInv = 1.0 / (double)X.sampleRate;
+	float *sig = STAGE == kPullParallel ? X.sigB : X.sigA;
+	PullCursor cur;
+	cur.seek(X, t0);
+	PullPole pw[NR], pw0;  // pw0: the FIR anti-resonator of the nasal stage
+	{
+		const PullSeg &S = X.segs[cur.s];
+#pragma unroll
+		for (int k = 0; k < NR; ++k) pw[k].seek(S, cur.c, STAGE == kPullParallel ? kResParallel + k : res, srInv);
+		if (STAGE == kPullNasal) pw0.seek(S, cur.c, kResN0, srInv);
+		else { pw0.zr = pw0.zi = pw0.wr = pw0.wi = 0.0f; }
+	}
+	float y[NR], d[NR];
+	float p00[NR], p01[NR], p10[NR], p11[NR];
+#pragma unroll
+	for (int k = 0; k < NR; ++k) {
+		if (PASS == 2) { y[k] = start[k].y; d[k] = start[k].d; }
+		else { y[k] = 0.0f; d[k] = 0.0f; }
+		p00[k] = 1.0f; p01[k] = 0.0f; p10[k] = 0.0f; p11[k] = 1.0f;
+	}
+	float in1 = 0.0f, in2 = 0.0f;
+	if (STAGE == kPullNasal) {
+		if (PASS == 1) {
+			fir[0] = pullFirInput(X, (int64_t)t0 - 1);
+			fir[1] = pullFirInput(X, (int64_t)t0 - 2);
+		}
+		in1 = fir[0]; in2 = fir[1];
+	}
+	uint32_t at = ch;
+	for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
+		const PullSeg &S = X.segs[cur.s];
+		const uint32_t c = cur.c;
+		float x = sig[at];
+		const float xin = x;
+		if (STAGE == kPullNasal) {  // rN0 on inputs: src/speechWaveGenerator.cpp:129-135 with anti == true
+			pw0.tick(S, c, kResN0, srInv);
+			float a0, rho0;
+			pw0.coef(a0, rho0);
+			const float dprev = in1 - in2;
+			const float dx = x - in1;
+			const float dx1 = fmaf(-rho0, dprev, dprev);
+			x = pullN0InvAt(S, c) ? fmaf(dx - dx1, fastRcp(a0), in1) : fmaf(a0, dx, dx1 + in1);
+			in2 = in1;
+			in1 = xin;
+		}
+		float acc = 0.0f;
+#pragma unroll
+		for (int k = 0; k < NR; ++k) {
+			pw[k].tick(S, c, STAGE == kPullParallel ? kResParallel + k : res, srInv);
+			float a, rho;
+			pw[k].coef(a, rho);
+			float w = fmaf(-rho, d[k], d[k]);
+			w = fmaf(-a, y[k], w);
+			const float dn = fmaf(a, x, w);
+			d[k] = dn;
+			y[k] += dn;
+			if (PASS == 1) {  // P <- A P with A = [[1-a, 1-rho], [-a, 1-rho]] acting on (y, d)
+				const float g = 1.0f - rho;
+				const float n10 = fmaf(-a, p00[k], g * p10[k]), n11 = fmaf(-a, p01[k], g * p11[k]);
+				p00[k] += n10; p01[k] += n11;
+				p10[k] = n10; p11[k] = n11;
+			}
+			if (STAGE == kPullParallel) acc = fmaf(y[k] - x, pullDirAt(S, dPa1 + k, c), acc);
+		}
+		if (PASS == 2) {
+			if (STAGE == kPullParallel) {
+				sig[at] = fmaf(x - acc, pullDirAt(S, dParallelBypass, c), acc);
+			} else if (STAGE == kPullNasal) {
+				sig[at] = fmaf(y[0] - xin, pullDirAt(S, dCaNP, c), xin);
+			} else if (STAGE == kPullCascade) {
+				sig[at] = y[0];
+			} else {
+				float s = (y[0] + X.sigB[at]) * (pullDirAt(S, dOutputGain, c) * 4000.0f);
+				s = fminf(s, 32000.0f);
+				s = fmaxf(s, -32000.0f);
+				X.pcm[t] = (int16_t)(int)s;
+			}
+		}
+		cur.next(X);
+	}
+	if (PASS == 1) {
+#pragma unroll
+		for (int k = 0; k < NR; ++k) {
+			maps[k].p00 = p00[k]; maps[k].p01 = p01[k]; maps[k].p10 = p10[k]; maps[k].p11 = p11[k];
+			maps[k].zy = y[k]; maps[k].zd = d[k];
+		}
+	} else if (t1 == X.n) {  // the pull's last chunk leaves the carry
+#pragma unroll
+		for (int k = 0; k < NR; ++k) {
+			const int r = STAGE == kPullParallel ? kResParallel + k : res;
+			X.state->y[r] = y[k];
+			X.state->d[r] = d[k];
+		}
+		if (STAGE == kPullNasal) {
+			X.state->y[kResN0] = in1;
+			X.state->d[kResN0] = in1 - in2;
+		}
+	}
+}
+
+// composition of affine maps, in double: it is cheap and keeps the scan out of the error budget
+struct PullAffineD {
+	double p00, p01, p10, p11, zy, zd;
+};
+KLATT_HD PullAffineD pullIdentity() { return PullAffineD{1.0, 0.0, 0.0, 1.0, 0.0, 0.0}; }
+KLATT_HD PullAffineD pullToD(const PullAffine &m) { return PullAffineD{m.p00, m.p01, m.p10, m.p11, m.zy, m.zd}; }
+// `second` after `first`
+KLATT_HD PullAffineD pullCompose(const PullAffineD &second, const PullAffineD &first) {
+	PullAffineD r;
+	r.p00 = second.p00 * first.p00 + second.p01 * first.p10;
+	r.p01 = second.p00 * first.p01 + second.p01 * first.p11;
+	r.p10 = second.p10 * first.p00 + second.p11 * first.p10;
+	r.p11 = second.p10 * first.p01 + second.p11 * first.p11;
+	r.zy = second.p00 * first.zy + second.p01 * first.zd + second.zy;
+	r.zd = second.p10 * first.zy + second.p11 * first.zd + second.zd;
+	return r;
+}
+
+}  // namespace klatt

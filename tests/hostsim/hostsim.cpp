@@ -81,3 +81,104 @@ extern "C" int hostsim_render_f32(int sampleRate, const double *frames, const ui
 	free(st);
 	return (int)total;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Low-latency pull path (nvspeechplayer_b200/csrc/klatt_pull_core.cuh + pull_manager.h): the host frame manager is
+// the product's own; the kernel is emulated "thread by thread" -- the same per-thread passes in the same order, the
+// block scans replaced by plain loops over the 512 chunks.
+// ---------------------------------------------------------------------------------------------------------------
+#include "../../nvspeechplayer_b200/csrc/pull_manager.h"
+
+namespace {
+struct HostPullPlayer {
+	PullManager mgr;
+	PullState state;
+	int sampleRate;
+	uint64_t seed, streamId;
+	HostPullPlayer(int sr, uint64_t sd, uint64_t sid) : mgr(sr), sampleRate(sr), seed(sd), streamId(sid) { memset(&state, 0, sizeof state); }
+};
+
+// exclusive prefixes of `maps` (one per chunk) seeded with (y0, d0): what blockExclusive() computes on the device
+void hostScan(const std::vector<PullAffine> &maps, int stride, int k, float y0, float d0, std::vector<PullStart> &out) {
+	PullAffineD pre = PullAffineD{1.0, 0.0, 0.0, 1.0, (double)y0, (double)d0};
+	for (int ch = 0; ch < kPullThreads; ++ch) {
+		out[(size_t)ch * stride + k].y = (float)pre.zy;
+		out[(size_t)ch * stride + k].d = (float)pre.zd;
+		pre = pullCompose(pullToD(maps[(size_t)ch * stride + k]), pre);
+	}
+}
+
+template <int STAGE> void hostStage(const PullCtx &X, int res) {
+	constexpr int NR = PullStageTraits<STAGE>::NR;
+	std::vector<PullAffine> maps((size_t)kPullThreads * NR);
+	std::vector<PullStart> st((size_t)kPullThreads * NR);
+	std::vector<float> fir((size_t)kPullThreads * 2, 0.0f);
+	for (int ch = 0; ch < kPullThreads; ++ch) pullStage<STAGE, 1>(X, ch, res, &maps[(size_t)ch * NR], nullptr, &fir[(size_t)ch * 2]);
+	for (int k = 0; k < NR; ++k) {
+		const int r = STAGE == kPullParallel ? kResParallel + k : res;
+		hostScan(maps, NR, k, X.state->y[r], X.state->d[r], st);
+	}
+	for (int ch = 0; ch < kPullThreads; ++ch) pullStage<STAGE, 2>(X, ch, res, nullptr, &st[(size_t)ch * NR], &fir[(size_t)ch * 2]);
+}
+
+void hostPullRender(PullCtx X) {
+	X.L = (X.n + kPullThreads - 1) / kPullThreads;
+	std::vector<float> sig((size_t)2 * X.L * kPullThreads, 0.0f);
+	X.sigA = sig.data();
+	X.sigB = sig.data() + (size_t)X.L * kPullThreads;
+	std::vector<double> inc((size_t)X.L * kPullThreads, 0.0);
+	X.inc = inc.data();
+	{
+		std::vector<PullSourceSums> sums(kPullThreads);
+		for (int ch = 0; ch < kPullThreads; ++ch) pullSourcePass1(X, ch, sums[ch]);
+		PullAffineD pre = PullAffineD{1.0, 0.0, 0.0, 1.0, (double)X.state->aspLast, (double)X.state->fricLast};
+		std::vector<float> a0(kPullThreads), f0(kPullThreads);
+		for (int ch = 0; ch < kPullThreads; ++ch) {
+			a0[ch] = (float)pre.zy; f0[ch] = (float)pre.zd;
+			PullAffineD own{(double)sums[ch].decay, 0.0, 0.0, (double)sums[ch].decay, (double)sums[ch].zAsp, (double)sums[ch].zFric};
+			pre = pullCompose(own, pre);
+		}
+		pullPhaseSerial(X);
+		for (int ch = 0; ch < kPullThreads; ++ch) pullSourcePass2(X, ch, a0[ch], f0[ch]);
+	}
+	hostStage<kPullParallel>(X, 0);
+	hostStage<kPullNasal>(X, kResNP);
+	for (int r = kResCascade; r < kResParallel - 1; ++r) hostStage<kPullCascade>(X, r);
+	hostStage<kPullLast>(X, kResParallel - 1);
+	X.state->generated += X.n;
+}
+}  // namespace
+
+extern "C" void *hostsim_pull_create(int sampleRate, uint64_t seed, uint64_t streamId) {
+	return new HostPullPlayer(sampleRate, seed, streamId);
+}
+extern "C" void hostsim_pull_destroy(void *h) { delete (HostPullPlayer *)h; }
+extern "C" void hostsim_pull_queue(void *h, const double *frame, uint32_t minDur, uint32_t fadeDur, int32_t userIndex, int purge) {
+	((HostPullPlayer *)h)->mgr.queueFrame(frame, minDur, fadeDur, userIndex, purge != 0);
+}
+extern "C" int hostsim_pull_last_index(void *h) { return ((HostPullPlayer *)h)->mgr.lastIndex(); }
+// maxTicks / maxSegs: per-"launch" limits (0: the product's)
+extern "C" int hostsim_pull_synthesize(void *h, uint32_t n, int16_t *out, uint32_t maxTicks, uint32_t maxSegs) {
+	HostPullPlayer *p = (HostPullPlayer *)h;
+	if (maxTicks == 0 || maxTicks > kPullMaxTicks) maxTicks = kPullMaxTicks;
+	if (maxSegs == 0 || maxSegs > kPullMaxSegs) maxSegs = kPullMaxSegs;
+	uint32_t total = 0;
+	std::vector<PullSeg> segs;
+	while (total < n) {
+		const uint32_t want = (n - total) < maxTicks ? (n - total) : maxTicks;
+		segs.clear();
+		bool drained = false;
+		const uint32_t got = p->mgr.advance(want, 0, maxSegs, segs, drained);
+		if (got) {
+			PullCtx X;
+			memset(&X, 0, sizeof X);
+			X.segs = segs.data(); X.nSeg = (uint32_t)segs.size(); X.n = got; X.sampleRate = p->sampleRate;
+			X.state = &p->state; X.noiseMode = kNoisePhilox; X.seed = p->seed; X.streamId = p->streamId;
+			X.pcm = out + total;
+			hostPullRender(X);
+		}
+		total += got;
+		if (drained) break;
+	}
+	return (int)total;
+}

@@ -58,3 +58,46 @@ def parity(got, want):
     err = float((d * d).sum())
     snr = float("inf") if err == 0 else 10 * np.log10(max(sig, 1e-30) / err)
     return float((np.abs(d) <= 1).mean()), float((d == 0).mean()), snr, float(np.abs(d).max())
+
+
+class PullPlayer:
+    """The low-latency pull path on the host: the product's request-level frame manager (pull_manager.h) driving a
+    thread-by-thread emulation of klatt_pull_kernel.  Same surface as the players `scenarios.run_script` drives."""
+
+    def __init__(self, sr, seed=0, stream=0, max_ticks=0, max_segs=0):
+        L = lib()
+        vp = ctypes.c_void_p
+        L.hostsim_pull_create.restype = vp
+        L.hostsim_pull_create.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64]
+        L.hostsim_pull_destroy.argtypes = [vp]
+        L.hostsim_pull_queue.argtypes = [vp, vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_int]
+        L.hostsim_pull_last_index.restype = ctypes.c_int
+        L.hostsim_pull_last_index.argtypes = [vp]
+        L.hostsim_pull_synthesize.restype = ctypes.c_int
+        L.hostsim_pull_synthesize.argtypes = [vp, ctypes.c_uint, vp, ctypes.c_uint, ctypes.c_uint]
+        self.L = L
+        self.h = L.hostsim_pull_create(sr, seed, stream)
+        self.max_ticks, self.max_segs = max_ticks, max_segs
+
+    def queue_frame(self, frame, min_dur, fade_dur, user_index=-1, purge=False):
+        if frame is None:
+            self.L.hostsim_pull_queue(self.h, None, int(min_dur), int(fade_dur), int(user_index), int(bool(purge)))
+        else:
+            fr = np.ascontiguousarray(frame, dtype=np.float64)
+            assert fr.size == 47
+            self.L.hostsim_pull_queue(self.h, fr.ctypes.data_as(ctypes.c_void_p), int(min_dur), int(fade_dur),
+                                      int(user_index), int(bool(purge)))
+
+    def synthesize(self, n):
+        out = np.zeros(max(int(n), 1), dtype=np.int16)
+        got = self.L.hostsim_pull_synthesize(self.h, int(n), out.ctypes.data_as(ctypes.c_void_p), self.max_ticks,
+                                             self.max_segs)
+        return out[:got]
+
+    def last_index(self):
+        return self.L.hostsim_pull_last_index(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.hostsim_pull_destroy(self.h)
+            self.h = None
