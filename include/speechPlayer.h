@@ -88,7 +88,9 @@ void speechPlayer_terminate(speechPlayer_handle_t playerHandle);
 
 enum { /* arithmetic the render kernel runs in */
 	SPEECHPLAYER_PRECISION_FP64 = 0, /* reference evaluation order in double: bit-exact int16 parity mode */
-	SPEECHPLAYER_PRECISION_FP32 = 1  /* production: FP32 DSP, FP64 pitch/phase */
+	SPEECHPLAYER_PRECISION_FP32 = 1, /* production: FP32 DSP, FP64 pitch/phase */
+	SPEECHPLAYER_PRECISION_STREAM = 2 /* low-latency pulls: the FP32 arithmetic, one pull rendered parallel in time by one
+	                                    * thread block with the player's state carried over (per-handle API only) */
 };
 enum { /* source of the two uniform draws per generated sample (reference rand(), speechWaveGenerator.cpp:40) */
 	SPEECHPLAYER_NOISE_PHILOX = 0, /* counter-based Philox4x32-10 keyed by (seed, stream id) */
@@ -97,7 +99,7 @@ enum { /* source of the two uniform draws per generated sample (reference rand()
 };
 
 /* Like speechPlayer_initialize with explicit modes.  speechPlayer_initialize itself reads the environment:
- * NVSP_PRECISION=fp64|fp32 (default fp64: faithful drop-in), NVSP_NOISE=glibc|philox (default glibc),
+ * NVSP_PRECISION=fp64|fp32|stream (default fp64: faithful drop-in), NVSP_NOISE=glibc|philox (default glibc),
  * NVSP_SEED, NVSP_DEVICE (CUDA ordinal; default LOCAL_RANK or 0). */
 speechPlayer_handle_t speechPlayer_initializeEx(int sampleRate, int precision, int noiseMode, uint64_t seed,
                                                 uint64_t streamId);

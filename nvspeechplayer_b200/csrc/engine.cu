@@ -8,6 +8,8 @@
 //        (sampleCounter / snapshot of curFrame, :105-111) runs as the prologue of the next launch
 //   LockableObject (queueFrame vs synthesize)        src/lock.h:25-53             -> Player::mu
 //   the per-sample loop                              src/speechWaveGenerator.cpp:197-214 -> klatt_f64.cu / klatt_f32.cu
+//   SPEECHPLAYER_PRECISION_STREAM handles: the whole FrameManagerImpl runs on the host at request granularity
+//        (pull_manager.h) and one pull is one launch of the time-parallel block kernel (klatt_pull.cu)
 //
 // There is no CPU synthesis path in this library: every sample comes out of a CUDA kernel.
 #include <cuda_runtime.h>
@@ -24,6 +26,7 @@
 #include "../../include/speechPlayer_batch.h"
 #include "glibc_rand.h"
 #include "klatt_common.h"
+#include "pull_manager.h"
 
 namespace klatt {
 cudaError_t launchKlattF64(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
@@ -64,6 +67,8 @@ struct LongStream {  // klatt_long.cu
 struct Affine {
 	float p00, p01, p10, p11, zy, zd;
 };
+cudaError_t launchKlattPullInit(PullState *state, cudaStream_t stream);  // klatt_pull.cu
+cudaError_t launchKlattPull(PullCtx ctx, cudaStream_t stream);
 cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream);
 cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
                                   uint64_t *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
@@ -485,6 +490,15 @@ struct Player {
 	uint64_t generated = 0;   // samples generated so far (== draws/2)
 	int lastIndex = -1;
 	HostPipe pipe;
+	// SPEECHPLAYER_PRECISION_STREAM: host frame manager, carried device state, staging for one launch
+	PullManager *pull = nullptr;
+	PullState *dPull = nullptr;
+	DevBuf dSegs, dPullPcm, dDraws;
+	unsigned char *hPullStage = nullptr;  // pinned: [segments | pcm | draws]
+	std::vector<PullSeg> pullSegs;
+	uint64_t pullLaunches = 0;
+	static constexpr size_t kStageSegs = sizeof(PullSeg) * kPullMaxSegs, kStagePcm = sizeof(int16_t) * kPullMaxTicks,
+	                        kStageDraws = sizeof(int32_t) * 2 * kPullMaxTicks;
 
 	size_t pending() const { return minDur.size(); }
 
@@ -574,6 +588,13 @@ struct Player {
 		DeviceGuard g(device);
 		pipe.destroy();
 		dFrames.release(); dMin.release(); dFade.release(); dUix.release(); dNull.release(); dReplay.release(); dDesc.release();
+		dSegs.release(); dPullPcm.release(); dDraws.release();
+		if (hPullStage) cudaFreeHost(hPullStage);
+		hPullStage = nullptr;
+		if (dPull) cudaFree(dPull);
+		dPull = nullptr;
+		delete pull;
+		pull = nullptr;
 		if (dState) cudaFree(dState);
 		dState = nullptr;
 	}
@@ -593,6 +614,7 @@ static Player *lookup(speechPlayer_handle_t h) {
 static int envPrecision() {
 	const char *e = getenv("NVSP_PRECISION");
 	if (e && (!strcmp(e, "fp32") || !strcmp(e, "f32") || !strcmp(e, "FP32"))) return kPrecisionF32;
+	if (e && (!strcmp(e, "stream") || !strcmp(e, "pull"))) return kPrecisionStream;
 	return kPrecisionF64;
 }
 static int envNoise() {
@@ -617,7 +639,10 @@ speechPlayer_handle_t speechPlayer_initializeEx(int sampleRate, int precision, i
                                                 uint64_t streamId) {
 	g_lastError.clear();
 	if (sampleRate <= 0) { fail("sampleRate must be positive"); return nullptr; }
-	if (precision != kPrecisionF64 && precision != kPrecisionF32) { fail("unknown precision"); return nullptr; }
+	if (precision != kPrecisionF64 && precision != kPrecisionF32 && precision != kPrecisionStream) {
+		fail("unknown precision");
+		return nullptr;
+	}
 	if (noiseMode < kNoisePhilox || noiseMode > kNoiseReplay) { fail("unknown noise mode"); return nullptr; }
 	int dev = pickDevice();
 	if (dev < 0) { fail("no usable CUDA device (this library has no CPU fallback)"); return nullptr; }
@@ -630,6 +655,19 @@ speechPlayer_handle_t speechPlayer_initializeEx(int sampleRate, int precision, i
 	    !cudaOk(cudaStreamSynchronize(nullptr), "init state sync")) {
 		delete p;
 		return nullptr;
+	}
+	if (precision == kPrecisionStream) {
+		p->pull = new PullManager(sampleRate);
+		if (!cudaOk(cudaMalloc((void **)&p->dPull, sizeof(PullState)), "cudaMalloc(pull state)") ||
+		    !cudaOk(launchKlattPullInit(p->dPull, nullptr), "init pull state") ||
+		    !cudaOk(cudaStreamSynchronize(nullptr), "init pull state sync") ||
+		    !cudaOk(cudaHostAlloc((void **)&p->hPullStage, Player::kStageSegs + Player::kStagePcm + Player::kStageDraws,
+		                          cudaHostAllocDefault), "cudaHostAlloc(pull staging)") ||
+		    !p->dSegs.reserve(Player::kStageSegs) || !p->dPullPcm.reserve(Player::kStagePcm)) {
+			p->destroy();
+			delete p;
+			return nullptr;
+		}
 	}
 	std::lock_guard<std::mutex> lk(g_tableMu);
 	for (size_t i = 0; i < g_players.size(); ++i)
@@ -655,6 +693,10 @@ void speechPlayer_queueFrame(speechPlayer_handle_t playerHandle, speechPlayer_fr
 	Player *p = lookup(playerHandle);
 	if (!p) return;
 	std::lock_guard<std::mutex> lk(p->mu);
+	if (p->pull) {
+		p->pull->queueFrame(reinterpret_cast<const double *>(framePtr), minFrameDuration, fadeDuration, userIndex, purgeQueue);
+		return;
+	}
 	if (purgeQueue) {  // src/frame.cpp:103-112: drop everything still queued; the rest happens on the device
 		p->clearQueue();
 		p->purgePending = true;
@@ -671,6 +713,11 @@ int speechPlayer_queueFrames(speechPlayer_handle_t playerHandle, const speechPla
 	std::lock_guard<std::mutex> lk(p->mu);
 	for (unsigned i = 0; i < n; ++i) {
 		bool null = (isNull && isNull[i]) || !frames;
+		if (p->pull) {
+			p->pull->queueFrame(null ? nullptr : reinterpret_cast<const double *>(frames + i), minFrameDuration[i], fadeDuration[i],
+			                    userIndex ? userIndex[i] : -1, false);
+			continue;
+		}
 		p->push(frames ? frames + i : nullptr, minFrameDuration[i], fadeDuration[i], userIndex ? userIndex[i] : -1, null);
 	}
 	return 0;
@@ -691,15 +738,89 @@ void speechPlayer_seedNoise(unsigned int seed) {
 	g_noise.seed(seed);
 }
 
+// One pull of a SPEECHPLAYER_PRECISION_STREAM player: the host manager describes the next ticks (src/frame.cpp:41-80 in
+// closed form), one launch of klatt_pull_kernel per kPullMaxTicks renders them, the samples come back through pinned memory.
+static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *out) {
+	std::lock_guard<std::mutex> lk(p->mu);
+	DeviceGuard g(p->device);
+	if (!p->pipe.init()) return -1;
+	cudaStream_t stream = p->pipe.compute;
+	PullSeg *hSegs = reinterpret_cast<PullSeg *>(p->hPullStage);
+	int16_t *hPcm = reinterpret_cast<int16_t *>(p->hPullStage + Player::kStageSegs);
+	int32_t *hDraws = reinterpret_cast<int32_t *>(p->hPullStage + Player::kStageSegs + Player::kStagePcm);
+	if (p->noiseMode == kNoiseReplay && p->replayDirty) {
+		if (!p->dReplay.reserve(std::max<size_t>(p->replayHost.size(), 1) * 4)) return -1;
+		CU(cudaMemcpyAsync(p->dReplay.p, p->replayHost.data(), p->replayHost.size() * 4, cudaMemcpyHostToDevice, stream));
+		CU(cudaStreamSynchronize(stream));
+		p->replayDirty = false;
+	}
+	unsigned int total = 0;
+	while (total < sampleCount) {
+		const uint32_t want = std::min<uint32_t>(sampleCount - total, kPullMaxTicks);
+		p->pullSegs.clear();
+		bool drained = false;
+		const uint32_t got = p->pull->advance(want, 0, kPullMaxSegs, p->pullSegs, drained);
+		if (got) {
+			const size_t nSeg = p->pullSegs.size();
+			memcpy(hSegs, p->pullSegs.data(), nSeg * sizeof(PullSeg));
+			CU(cudaMemcpyAsync(p->dSegs.p, hSegs, nSeg * sizeof(PullSeg), cudaMemcpyHostToDevice, stream));
+			PullCtx X;
+			memset(&X, 0, sizeof X);
+			X.segs = p->dSegs.as<PullSeg>(); X.nSeg = (uint32_t)nSeg; X.n = got; X.sampleRate = p->sampleRate;
+			X.state = p->dPull; X.noiseMode = p->noiseMode; X.seed = p->seed; X.streamId = p->streamId;
+			X.pcm = p->dPullPcm.as<int16_t>();
+			if (p->noiseMode == kNoiseGlibc) {  // the reference consumes exactly two rand() calls per generated sample
+				{
+					std::lock_guard<std::mutex> nl(g_noiseMu);
+					g_noise.fill(hDraws, (size_t)got * 2);
+				}
+				if (!p->dDraws.reserve(Player::kStageDraws)) return -1;
+				CU(cudaMemcpyAsync(p->dDraws.p, hDraws, (size_t)got * 2 * 4, cudaMemcpyHostToDevice, stream));
+				X.draws = p->dDraws.as<int32_t>(); X.drawBase = p->generated * 2; X.drawLen = (uint64_t)got * 2;
+			} else if (p->noiseMode == kNoiseReplay) {
+				X.draws = p->dReplay.as<int32_t>(); X.drawBase = 0; X.drawLen = p->replayHost.size();
+			}
+			CU(launchKlattPull(X, stream));
+			CU(cudaMemcpyAsync(hPcm, X.pcm, (size_t)got * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
+			CU(cudaStreamSynchronize(stream));
+			memcpy(out + total, hPcm, (size_t)got * sizeof(int16_t));
+			++p->pullLaunches;
+			p->generated += got;
+		}
+		total += got;
+		if (drained) break;
+	}
+	p->lastIndex = p->pull->lastIndex();
+	return (long long)total;
+}
+
 long long speechPlayer_synthesizeBatch(speechPlayer_handle_t *handles, unsigned int numHandles, unsigned int sampleCount,
                                        sample *sampleBuf, unsigned int *samplesWritten) {
 	g_lastError.clear();
 	if (numHandles == 0 || sampleCount == 0) return 0;
 	if (!handles || !sampleBuf) return fail("null argument");
 	std::vector<Player *> ps(numHandles);
+	bool anyPull = false;
 	for (unsigned i = 0; i < numHandles; ++i) {
 		ps[i] = lookup(handles[i]);
 		if (!ps[i]) return fail("bad handle in batch");
+		anyPull = anyPull || ps[i]->pull != nullptr;
+	}
+	if (anyPull) {  // low-latency players render one pull per launch each; a batch of them is a loop
+		std::vector<Player *> uniq(ps);
+		std::sort(uniq.begin(), uniq.end());
+		if (std::adjacent_find(uniq.begin(), uniq.end()) != uniq.end()) return fail("duplicate handle in batch");
+		long long total = 0;
+		for (unsigned i = 0; i < numHandles; ++i) {
+			if (!ps[i]->pull) return fail("handles of one batch must share device, sample rate, precision and noise mode");
+			long long w = synthesizePull(ps[i], sampleCount, reinterpret_cast<int16_t *>(sampleBuf) + (size_t)i * sampleCount);
+			if (w < 0) return -1;
+			if (samplesWritten) samplesWritten[i] = (unsigned int)w;
+			total += w;
+		}
+		return total;
+	}
+	for (unsigned i = 0; i < numHandles; ++i) {
 		if (ps[i]->precision != ps[0]->precision || ps[i]->sampleRate != ps[0]->sampleRate ||
 		    ps[i]->device != ps[0]->device || ps[i]->noiseMode != ps[0]->noiseMode || ps[i]->seed != ps[0]->seed)
 			return fail("handles of one batch must share device, sample rate, precision and noise mode");
@@ -892,7 +1013,10 @@ speechPlayer_batch_t *speechPlayer_batchCreate(int sampleRate, unsigned int numS
                                                uint64_t seed, const uint64_t *streamIds) {
 	g_lastError.clear();
 	if (sampleRate <= 0 || numStreams == 0) { fail("bad sampleRate / numStreams"); return nullptr; }
-	if (precision != kPrecisionF64 && precision != kPrecisionF32) { fail("unknown precision"); return nullptr; }
+	if (precision != kPrecisionF64 && precision != kPrecisionF32 && precision != kPrecisionStream) {
+		fail("unknown precision");
+		return nullptr;
+	}
 	if (noiseMode != kNoisePhilox && noiseMode != kNoiseReplay) { fail("batch noise mode must be PHILOX or REPLAY"); return nullptr; }
 	int dev = pickDevice();
 	if (dev < 0) { fail("no usable CUDA device (this library has no CPU fallback)"); return nullptr; }

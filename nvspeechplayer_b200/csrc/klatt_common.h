@@ -41,7 +41,9 @@ KLATT_HD constexpr int resBwParam(int r) {
 	return r == kResN0 ? kCbN0 : r == kResNP ? kCbNP : r < kResParallel ? (kCb6 - (r - kResCascade)) : (kPb1 + (r - kResParallel));
 }
 
-enum Precision : int { kPrecisionF64 = 0, kPrecisionF32 = 1 };
+// kPrecisionStream: per-handle API only -- FP32 arithmetic rendered one pull at a time by the time-parallel block
+// kernel (klatt_pull.cu) with the frame manager on the host (pull_manager.h): the low-latency path
+enum Precision : int { kPrecisionF64 = 0, kPrecisionF32 = 1, kPrecisionStream = 2 };
 enum NoiseMode : int { kNoisePhilox = 0, kNoiseGlibc = 1, kNoiseReplay = 2 };
 
 // ---------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ import numpy as np
 
 from .workloads import NUM_PARAMS, PARAM_NAMES
 
-PRECISION_FP64, PRECISION_FP32 = 0, 1
+PRECISION_FP64, PRECISION_FP32, PRECISION_STREAM = 0, 1, 2
 NOISE_PHILOX, NOISE_GLIBC, NOISE_REPLAY = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
