@@ -493,7 +493,7 @@ struct Player {
 	// SPEECHPLAYER_PRECISION_STREAM: host frame manager, carried device state, staging for one launch
 	PullManager *pull = nullptr;
 	PullState *dPull = nullptr;
-	DevBuf dSegs, dPullPcm, dDraws;
+	DevBuf dSegs, dPullPcm, dDraws, dPullDbg;
 	unsigned char *hPullStage = nullptr;  // pinned: [segments | pcm | draws]
 	std::vector<PullSeg> pullSegs;
 	uint64_t pullLaunches = 0;
@@ -588,7 +588,7 @@ struct Player {
 		DeviceGuard g(device);
 		pipe.destroy();
 		dFrames.release(); dMin.release(); dFade.release(); dUix.release(); dNull.release(); dReplay.release(); dDesc.release();
-		dSegs.release(); dPullPcm.release(); dDraws.release();
+		dSegs.release(); dPullPcm.release(); dDraws.release(); dPullDbg.release();
 		if (hPullStage) cudaFreeHost(hPullStage);
 		hPullStage = nullptr;
 		if (dPull) cudaFree(dPull);
@@ -780,10 +780,19 @@ static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *ou
 			} else if (p->noiseMode == kNoiseReplay) {
 				X.draws = p->dReplay.as<int32_t>(); X.drawBase = 0; X.drawLen = p->replayHost.size();
 			}
+			static const bool debugPhases = getenv("NVSP_PULL_DEBUG") != nullptr;
+			if (debugPhases && p->dPullDbg.reserve(16 * sizeof(long long))) X.dbg = p->dPullDbg.as<long long>();
 			CU(launchKlattPull(X, stream));
 			CU(cudaMemcpyAsync(hPcm, X.pcm, (size_t)got * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
 			CU(cudaStreamSynchronize(stream));
 			memcpy(out + total, hPcm, (size_t)got * sizeof(int16_t));
+			if (X.dbg) {  // SM cycles between the phase boundaries of the launch (tools/latency_probe.py reads these lines)
+				long long c[16];
+				CU(cudaMemcpy(c, X.dbg, sizeof c, cudaMemcpyDeviceToHost));
+				fprintf(stderr, "[pull] n=%u segs=%zu cycles: src1 %lld noise-scan %lld phase %lld src2 %lld parallel %lld nasal %lld "
+				        "r6-r2 %lld r1+out %lld total %lld in %lld ns\n", got, nSeg, c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3],
+				        c[5] - c[4], c[6] - c[5], c[7] - c[6], c[8] - c[7], c[8] - c[0], c[14] - c[15]);
+			}
 			++p->pullLaunches;
 			p->generated += got;
 		}

@@ -61,8 +61,9 @@ __device__ __forceinline__ void runStage(const PullCtx &X, uint32_t ch, int res,
 	constexpr int NR = PullStageTraits<STAGE>::NR;
 	PullAffine maps[NR];
 	PullStart st[NR];
+	PullPole poles[NR + 1];
 	float fir[2] = {0.0f, 0.0f};
-	pullStage<STAGE, 1>(X, ch, res, maps, nullptr, fir);
+	pullStage<STAGE, 1>(X, ch, res, maps, nullptr, fir, poles);
 #pragma unroll
 	for (int k = 0; k < NR; ++k) {
 		const int r = STAGE == kPullParallel ? kResParallel + k : res;
@@ -70,7 +71,11 @@ __device__ __forceinline__ void runStage(const PullCtx &X, uint32_t ch, int res,
 		st[k].y = (float)pre.zy;
 		st[k].d = (float)pre.zd;
 	}
-	pullStage<STAGE, 2>(X, ch, res, nullptr, st, fir);
+	pullStage<STAGE, 2>(X, ch, res, nullptr, st, fir, poles);
+}
+
+__device__ __forceinline__ void mark(const PullCtx &X, int slot) {
+	if (X.dbg && threadIdx.x == 0) X.dbg[slot] = clock64();
 }
 
 }  // namespace
@@ -83,26 +88,45 @@ klatt_pull_kernel(PullCtx X) {
 	X.sigB = pullSignals + (size_t)X.L * kPullThreads;
 	X.inc = reinterpret_cast<double *>(X.sigB);  // 2 x the size of sigB; dead before sigB is first written
 	const uint32_t ch = threadIdx.x;
+	if (X.dbg && ch == 0) {
+		unsigned long long ns;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+		X.dbg[15] = (long long)ns;
+	}
+	mark(X, 0);
 
 	// source: phase increments and noise colouring per chunk, the phase recurrence by one thread, then the excitation
 	{
 		PullSourceSums sums;
 		pullSourcePass1(X, ch, sums);
+		mark(X, 1);
 		const PullAffineD own{(double)sums.decay, 0.0, 0.0, (double)sums.decay, (double)sums.zAsp, (double)sums.zFric};
 		const PullAffineD pre = blockExclusive(own, seedOf(X.state->aspLast, X.state->fricLast), warpTotal);
+		mark(X, 2);
 		if (ch == 0) pullPhaseSerial(X);
 		__syncthreads();
+		mark(X, 3);
 		pullSourcePass2(X, ch, (float)pre.zy, (float)pre.zd);
 	}
 	__syncthreads();  // the FIR section of the nasal stage reads its neighbours' last two cascade inputs
+	mark(X, 4);
 
 	runStage<kPullParallel>(X, ch, 0, warpTotal);
+	mark(X, 5);
 	runStage<kPullNasal>(X, ch, kResNP, warpTotal);
+	mark(X, 6);
 	for (int r = kResCascade; r < kResParallel - 1; ++r) runStage<kPullCascade>(X, ch, r, warpTotal);
+	mark(X, 7);
 	runStage<kPullLast>(X, ch, kResParallel - 1, warpTotal);
 
 	__syncthreads();
+	mark(X, 8);
 	if (ch == 0) X.state->generated += X.n;
+	if (X.dbg && ch == 0) {
+		unsigned long long ns;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+		X.dbg[14] = (long long)ns;
+	}
 }
 
 __global__ void klatt_pull_init_kernel(PullState *s) {
@@ -118,7 +142,7 @@ cudaError_t launchKlattPullInit(PullState *state, cudaStream_t stream) {
 	return cudaGetLastError();
 }
 
-// ctx.sigA / sigB / L are filled in here; everything else by the caller.  ctx.n <= kPullMaxTicks.
+// ctx.sigA / sigB / inc / L are filled in here; everything else by the caller.  ctx.n <= kPullMaxTicks.
 cudaError_t launchKlattPull(PullCtx ctx, cudaStream_t stream) {
 	if (ctx.n == 0) return cudaSuccess;
 	if (ctx.n > kPullMaxTicks || ctx.nSeg == 0 || ctx.nSeg > kPullMaxSegs) return cudaErrorInvalidValue;
@@ -132,7 +156,7 @@ cudaError_t launchKlattPull(PullCtx ctx, cudaStream_t stream) {
 		if (e != cudaSuccess) return e;
 		attrSet[dev] = true;
 	}
-	ctx.L = (ctx.n + kPullThreads - 1) / kPullThreads;
+	ctx.L = pullTicksPerThread(ctx.n);  // 1, 2, 4, 8 or 16: the phase recurrence is unrolled for these
 	ctx.sigA = ctx.sigB = nullptr;
 	ctx.inc = nullptr;
 	const size_t smem = 3 * (size_t)ctx.L * kPullThreads * sizeof(float);

@@ -64,6 +64,7 @@ struct PullCtx {
 	double *inc;          // same layout: glottal phase increment of every tick (dead once the sawtooth is in sigA: may
 	                      // share its storage with sigB)
 	PullState *state;
+	long long *dbg;       // optional (NVSP_PULL_DEBUG): SM cycle counter at the phase boundaries of the launch
 	int noiseMode;
 	uint64_t seed, streamId;
 	const int32_t *draws;  // kNoiseGlibc / kNoiseReplay: rand() values, draw 2g = aspiration, 2g+1 = frication
@@ -138,10 +139,21 @@ struct PullCursor {
 // zeta = 1 - pole of one section along the pull (klatt_long.cu PoleWalk over segments)
 struct PullPole {
 	float zr, zi, wr, wi;
+	// zeta on fade tick k from the closed form of the pole.  The arguments are formed in double, the exponential and
+	// the sine / cosine in FP32 with the cancellation-free expressions of oneMinusExp(): zeta is kept in FP32 anyway, and
+	// 512 threads x 14 sections x (expm1 + sincos) in double was the largest fixed cost of a launch.
 	KLATT_HD void exact(const PullSeg &S, uint32_t k, int r, double srInv) {
-		const double ratio = (double)k / (double)S.F;
+		const double PI = 3.14159265358979323846;
+		const double ratio = (double)((float)k / (float)S.F);
 		const double f0 = S.fb[r][0], f1 = S.fb[r][1], b0 = S.fb[r][2], b1 = S.fb[r][3];
-		poleTerms(f0 + ((f1 - f0) * ratio), b0 + ((b1 - b0) * ratio), srInv, zr, zi);
+		const float x = (float)(-PI * (b0 + ((b1 - b0) * ratio)) * srInv);     // log of the pole radius
+		const float hth = (float)(PI * (f0 + ((f1 - f0) * ratio)) * srInv);    // half the pole angle
+		const float em1 = expm1f(x);
+		const float rad = 1.0f + em1;
+		float sh, ch;
+		sincosf(hth, &sh, &ch);
+		zr = fmaf((2.0f * rad) * sh, sh, -em1);
+		zi = -rad * ((2.0f * sh) * ch);
 	}
 	// state as it is AFTER the tick before (S, c)
 	KLATT_HD void seek(const PullSeg &S, uint32_t c, int r, double srInv) {
@@ -275,20 +287,76 @@ KLATT_HD void pullSourcePass1(const PullCtx &X, uint32_t ch, PullSourceSums &out
 	}
 }
 
-// the recurrence itself (one thread): the sawtooth value of every tick -> sigA (src/speechWaveGenerator.cpp:55, :74)
-KLATT_HD void pullPhaseSerial(const PullCtx &X) {
+// the recurrence itself (one thread): the sawtooth value of every tick -> sigA (src/speechWaveGenerator.cpp:55, :74).
+// A wrap happens once per pitch period, so the ticks are taken in groups of up to 8: the running sums of a group are
+// formed as if there were no wrap (one dependent FP64 addition per tick, nothing else on the chain), and only if one of
+// them left (-1, 1) is the group redone tick by tick with the reference's fmod.  Same roundings either way.
+KLATT_HD int32_t pullHiWord(double x) {
+#ifdef __CUDA_ARCH__
+	return __double2hiint(x);
+#else
+	int64_t b;
+	memcpy(&b, &x, 8);
+	return (int32_t)(b >> 32);
+#endif
+}
+template <int LL>
+KLATT_HD void pullPhaseSerialL(const PullCtx &X) {
+	constexpr int G = LL < 8 ? LL : 8;
 	double pos = X.state->pitchPos;
-	for (uint32_t ch = 0; ch < (uint32_t)kPullThreads; ++ch) {
-		uint32_t t0, t1;
-		pullChunkRange(X, ch, t0, t1);
-		if (t0 >= t1) break;
-		uint32_t at = ch;
-		for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
-			pos = fracRef(X.inc[at] + pos);
-			X.sigA[at] = (float)pos;
+	const uint32_t chunks = (X.n + LL - 1) / LL;
+	for (uint32_t ch = 0; ch < chunks; ++ch) {
+		const uint32_t t0 = ch * LL;
+		const uint32_t len = X.n - t0 < (uint32_t)LL ? X.n - t0 : (uint32_t)LL;
+		if (len == (uint32_t)LL) {
+#pragma unroll
+			for (int g0 = 0; g0 < LL; g0 += G) {
+				double a[G], sum[G];
+#pragma unroll
+				for (int k = 0; k < G; ++k) a[k] = X.inc[(uint32_t)(g0 + k) * kPullThreads + ch];
+				sum[0] = pos + a[0];
+#pragma unroll
+				for (int k = 1; k < G; ++k) sum[k] = sum[k - 1] + a[k];
+				int32_t top = 0;
+#pragma unroll
+				for (int k = 0; k < G; ++k) {
+					const int32_t h = pullHiWord(sum[k]) & 0x7fffffff;
+					top = h > top ? h : top;
+				}
+				if (top < 0x3ff00000) {  // every |sum| < 1: no wrap in this group
+#pragma unroll
+					for (int k = 0; k < G; ++k) X.sigA[(uint32_t)(g0 + k) * kPullThreads + ch] = (float)sum[k];
+					pos = sum[G - 1];
+				} else {
+#pragma unroll
+					for (int k = 0; k < G; ++k) {
+						pos = fracRef(a[k] + pos);
+						X.sigA[(uint32_t)(g0 + k) * kPullThreads + ch] = (float)pos;
+					}
+				}
+			}
+		} else {
+			for (uint32_t i = 0; i < len; ++i) {
+				pos = fracRef(X.inc[i * kPullThreads + ch] + pos);
+				X.sigA[i * kPullThreads + ch] = (float)pos;
+			}
 		}
 	}
 	X.state->pitchPos = pos;
+}
+KLATT_HD void pullPhaseSerial(const PullCtx &X) {  // X.L is one of the lengths launchKlattPull chooses from
+	switch (X.L) {
+		case 1: pullPhaseSerialL<1>(X); break;
+		case 2: pullPhaseSerialL<2>(X); break;
+		case 4: pullPhaseSerialL<4>(X); break;
+		case 8: pullPhaseSerialL<8>(X); break;
+		default: pullPhaseSerialL<16>(X); break;
+	}
+}
+KLATT_HD uint32_t pullTicksPerThread(uint32_t n) {
+	uint32_t L = 1;
+	while (L * (uint32_t)kPullThreads < n) L <<= 1;
+	return L;
 }
 
 // pass 2: the two excitation signals of every tick: cascade input -> sigA (:204, :148), parallel input -> sigB (:206, :171)
@@ -350,8 +418,11 @@ KLATT_HD float pullFirInput(const PullCtx &X, int64_t t) {
 //   kPullCascade : sigA -> section `res` (:151-155)
 //   kPullLast    : like kPullCascade for r1, then (x + par) * outputGain * 4000, clamp, truncate (:207-208)
 // fir[2]: the two inputs before the chunk, read in pass 1 (before any thread overwrites sigA) and handed to pass 2.
+// poles[NR + 1]: zeta of the sections at the start of the chunk (and of rN0 in the last slot), found in pass 1 -- inside
+// a fade that is an exponential and a sine / cosine per section -- and handed to pass 2.
 template <int STAGE, int PASS>
-KLATT_HD void pullStage(const PullCtx &X, uint32_t ch, int res, PullAffine *maps, const PullStart *start, float *fir) {
+KLATT_HD void pullStage(const PullCtx &X, uint32_t ch, int res, PullAffine *maps, const PullStart *start, float *fir,
+                        PullPole *poles) {
 	constexpr int NR = PullStageTraits<STAGE>::NR;
 	uint32_t t0, t1;
 	pullChunkRange(X, ch, t0, t1);
@@ -367,12 +438,19 @@ KLATT_HD void pullStage(const PullCtx &X, uint32_t ch, int res, PullAffine *maps
 	PullCursor cur;
 	cur.seek(X, t0);
 	PullPole pw[NR], pw0;  // pw0: the FIR anti-resonator of the nasal stage
-	{
+	if (PASS == 1) {
 		const PullSeg &S = X.segs[cur.s];
 #pragma unroll
 		for (int k = 0; k < NR; ++k) pw[k].seek(S, cur.c, STAGE == kPullParallel ? kResParallel + k : res, srInv);
 		if (STAGE == kPullNasal) pw0.seek(S, cur.c, kResN0, srInv);
 		else { pw0.zr = pw0.zi = pw0.wr = pw0.wi = 0.0f; }
+#pragma unroll
+		for (int k = 0; k < NR; ++k) poles[k] = pw[k];
+		poles[NR] = pw0;
+	} else {
+#pragma unroll
+		for (int k = 0; k < NR; ++k) pw[k] = poles[k];
+		pw0 = poles[NR];
 	}
 	float y[NR], d[NR];
 	float p00[NR], p01[NR], p10[NR], p11[NR];

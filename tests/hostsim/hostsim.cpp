@@ -113,16 +113,19 @@ template <int STAGE> void hostStage(const PullCtx &X, int res) {
 	std::vector<PullAffine> maps((size_t)kPullThreads * NR);
 	std::vector<PullStart> st((size_t)kPullThreads * NR);
 	std::vector<float> fir((size_t)kPullThreads * 2, 0.0f);
-	for (int ch = 0; ch < kPullThreads; ++ch) pullStage<STAGE, 1>(X, ch, res, &maps[(size_t)ch * NR], nullptr, &fir[(size_t)ch * 2]);
+	std::vector<PullPole> poles((size_t)kPullThreads * (NR + 1));
+	for (int ch = 0; ch < kPullThreads; ++ch)
+		pullStage<STAGE, 1>(X, ch, res, &maps[(size_t)ch * NR], nullptr, &fir[(size_t)ch * 2], &poles[(size_t)ch * (NR + 1)]);
 	for (int k = 0; k < NR; ++k) {
 		const int r = STAGE == kPullParallel ? kResParallel + k : res;
 		hostScan(maps, NR, k, X.state->y[r], X.state->d[r], st);
 	}
-	for (int ch = 0; ch < kPullThreads; ++ch) pullStage<STAGE, 2>(X, ch, res, nullptr, &st[(size_t)ch * NR], &fir[(size_t)ch * 2]);
+	for (int ch = 0; ch < kPullThreads; ++ch)
+		pullStage<STAGE, 2>(X, ch, res, nullptr, &st[(size_t)ch * NR], &fir[(size_t)ch * 2], &poles[(size_t)ch * (NR + 1)]);
 }
 
 void hostPullRender(PullCtx X) {
-	X.L = (X.n + kPullThreads - 1) / kPullThreads;
+	X.L = pullTicksPerThread(X.n);
 	std::vector<float> sig((size_t)2 * X.L * kPullThreads, 0.0f);
 	X.sigA = sig.data();
 	X.sigB = sig.data() + (size_t)X.L * kPullThreads;
