@@ -68,7 +68,7 @@ struct Affine {
 	float p00, p01, p10, p11, zy, zd;
 };
 cudaError_t launchKlattPullInit(PullState *state, cudaStream_t stream);  // klatt_pull.cu
-cudaError_t launchKlattPull(PullCtx ctx, cudaStream_t stream);
+cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut, cudaStream_t stream);
 cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream);
 cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
                                   uint64_t *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
@@ -494,7 +494,8 @@ struct Player {
 	PullManager *pull = nullptr;
 	PullState *dPull = nullptr;
 	DevBuf dSegs, dPullPcm, dDraws, dPullDbg;
-	unsigned char *hPullStage = nullptr;  // pinned: [segments | pcm | draws]
+	unsigned char *hPullStage = nullptr;  // pinned and mapped: [segments | pcm | draws]
+	unsigned char *dPullStage = nullptr;  // the same memory as the device sees it (zero-copy)
 	std::vector<PullSeg> pullSegs;
 	uint64_t pullLaunches = 0;
 	static constexpr size_t kStageSegs = sizeof(PullSeg) * kPullMaxSegs, kStagePcm = sizeof(int16_t) * kPullMaxTicks,
@@ -662,7 +663,8 @@ speechPlayer_handle_t speechPlayer_initializeEx(int sampleRate, int precision, i
 		    !cudaOk(launchKlattPullInit(p->dPull, nullptr), "init pull state") ||
 		    !cudaOk(cudaStreamSynchronize(nullptr), "init pull state sync") ||
 		    !cudaOk(cudaHostAlloc((void **)&p->hPullStage, Player::kStageSegs + Player::kStagePcm + Player::kStageDraws,
-		                          cudaHostAllocDefault), "cudaHostAlloc(pull staging)") ||
+		                          cudaHostAllocMapped), "cudaHostAlloc(pull staging)") ||
+		    !cudaOk(cudaHostGetDevicePointer((void **)&p->dPullStage, p->hPullStage, 0), "cudaHostGetDevicePointer") ||
 		    !p->dSegs.reserve(Player::kStageSegs) || !p->dPullPcm.reserve(Player::kStagePcm)) {
 			p->destroy();
 			delete p;
@@ -761,14 +763,22 @@ static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *ou
 		bool drained = false;
 		const uint32_t got = p->pull->advance(want, 0, kPullMaxSegs, p->pullSegs, drained);
 		if (got) {
+			// zero-copy (default): the kernel reads the segments from and writes the samples to the pinned staging itself, so a
+			// pull is one launch and one synchronize; NVSP_PULL_ZEROCOPY=0 goes through device buffers and two copies instead
+			static const bool zeroCopy = !(getenv("NVSP_PULL_ZEROCOPY") && atoi(getenv("NVSP_PULL_ZEROCOPY")) == 0);
 			const size_t nSeg = p->pullSegs.size();
 			memcpy(hSegs, p->pullSegs.data(), nSeg * sizeof(PullSeg));
-			CU(cudaMemcpyAsync(p->dSegs.p, hSegs, nSeg * sizeof(PullSeg), cudaMemcpyHostToDevice, stream));
+			const PullSeg *segSrc = reinterpret_cast<const PullSeg *>(p->dPullStage);
+			int16_t *pcmOut = reinterpret_cast<int16_t *>(p->dPullStage + Player::kStageSegs);
+			if (!zeroCopy) {
+				CU(cudaMemcpyAsync(p->dSegs.p, hSegs, nSeg * sizeof(PullSeg), cudaMemcpyHostToDevice, stream));
+				segSrc = p->dSegs.as<PullSeg>();
+				pcmOut = p->dPullPcm.as<int16_t>();
+			}
 			PullCtx X;
 			memset(&X, 0, sizeof X);
-			X.segs = p->dSegs.as<PullSeg>(); X.nSeg = (uint32_t)nSeg; X.n = got; X.sampleRate = p->sampleRate;
+			X.nSeg = (uint32_t)nSeg; X.n = got; X.sampleRate = p->sampleRate;
 			X.state = p->dPull; X.noiseMode = p->noiseMode; X.seed = p->seed; X.streamId = p->streamId;
-			X.pcm = p->dPullPcm.as<int16_t>();
 			if (p->noiseMode == kNoiseGlibc) {  // the reference consumes exactly two rand() calls per generated sample
 				{
 					std::lock_guard<std::mutex> nl(g_noiseMu);
@@ -782,8 +792,8 @@ static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *ou
 			}
 			static const bool debugPhases = getenv("NVSP_PULL_DEBUG") != nullptr;
 			if (debugPhases && p->dPullDbg.reserve(16 * sizeof(long long))) X.dbg = p->dPullDbg.as<long long>();
-			CU(launchKlattPull(X, stream));
-			CU(cudaMemcpyAsync(hPcm, X.pcm, (size_t)got * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
+			CU(launchKlattPull(X, segSrc, pcmOut, stream));
+			if (!zeroCopy) CU(cudaMemcpyAsync(hPcm, pcmOut, (size_t)got * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
 			CU(cudaStreamSynchronize(stream));
 			memcpy(out + total, hPcm, (size_t)got * sizeof(int16_t));
 			if (X.dbg) {  // SM cycles between the phase boundaries of the launch (tools/latency_probe.py reads these lines)

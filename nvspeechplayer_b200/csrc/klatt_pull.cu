@@ -54,7 +54,7 @@ __device__ PullAffineD blockExclusive(const PullAffineD &own, const PullAffineD 
 	return pre;
 }
 
-__device__ __forceinline__ PullAffineD seedOf(float y, float d) { return PullAffineD{1.0, 0.0, 0.0, 1.0, (double)y, (double)d}; }
+__device__ __forceinline__ PullAffineD seedOf(float y, float d) { return pullSeed(y, d); }
 
 template <int STAGE>
 __device__ __forceinline__ void runStage(const PullCtx &X, uint32_t ch, int res, PullAffineD *warpTotal) {
@@ -80,14 +80,29 @@ __device__ __forceinline__ void mark(const PullCtx &X, int slot) {
 
 }  // namespace
 
+// Shared memory: sigA | sigB | inc | the pull's segments | the pull's samples.  segSrc and pcmOut
+// may be pinned host memory (zero-copy): the segments come in and the samples go out in 16-byte words, coalesced, so a
+// pull is ONE launch with no copy before or after it.
 __global__ void __launch_bounds__(kPullThreads)
-klatt_pull_kernel(PullCtx X) {
-	extern __shared__ float pullSignals[];
+klatt_pull_kernel(PullCtx X, const PullSeg *__restrict__ segSrc, int16_t *__restrict__ pcmOut) {
+	extern __shared__ __align__(16) unsigned char pullSmem[];
 	__shared__ PullAffineD warpTotal[kPullWarps];
-	X.sigA = pullSignals;
-	X.sigB = pullSignals + (size_t)X.L * kPullThreads;
-	X.inc = reinterpret_cast<double *>(X.sigB);  // 2 x the size of sigB; dead before sigB is first written
+	const size_t sigBytes = (size_t)X.L * kPullThreads * sizeof(float);
+	X.sigA = reinterpret_cast<float *>(pullSmem);
+	X.sigB = reinterpret_cast<float *>(pullSmem + sigBytes);
+	X.inc = reinterpret_cast<double *>(pullSmem + 2 * sigBytes);
+	PullSeg *segS = reinterpret_cast<PullSeg *>(pullSmem + 4 * sigBytes);
+	int16_t *pcmS = reinterpret_cast<int16_t *>(pullSmem + 4 * sigBytes + (size_t)X.nSeg * sizeof(PullSeg));
 	const uint32_t ch = threadIdx.x;
+	{
+		const uint4 *src = reinterpret_cast<const uint4 *>(segSrc);
+		uint4 *dst = reinterpret_cast<uint4 *>(segS);
+		const uint32_t words = X.nSeg * (uint32_t)(sizeof(PullSeg) / 16);
+		for (uint32_t i = ch; i < words; i += kPullThreads) dst[i] = src[i];
+	}
+	__syncthreads();
+	X.segs = segS;
+	X.pcm = pcmS;
 	if (X.dbg && ch == 0) {
 		unsigned long long ns;
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
@@ -100,7 +115,7 @@ klatt_pull_kernel(PullCtx X) {
 		PullSourceSums sums;
 		pullSourcePass1(X, ch, sums);
 		mark(X, 1);
-		const PullAffineD own{(double)sums.decay, 0.0, 0.0, (double)sums.decay, (double)sums.zAsp, (double)sums.zFric};
+		const PullAffineD own{sums.decay, 0, 0, sums.decay, sums.zAsp, sums.zFric};
 		const PullAffineD pre = blockExclusive(own, seedOf(X.state->aspLast, X.state->fricLast), warpTotal);
 		mark(X, 2);
 		if (ch == 0) pullPhaseSerial(X);
@@ -120,6 +135,12 @@ klatt_pull_kernel(PullCtx X) {
 	runStage<kPullLast>(X, ch, kResParallel - 1, warpTotal);
 
 	__syncthreads();
+	{
+		const uint4 *src = reinterpret_cast<const uint4 *>(pcmS);
+		uint4 *dst = reinterpret_cast<uint4 *>(pcmOut);
+		const uint32_t words = (X.n * (uint32_t)sizeof(int16_t) + 15u) / 16u;
+		for (uint32_t i = ch; i < words; i += kPullThreads) dst[i] = src[i];
+	}
 	mark(X, 8);
 	if (ch == 0) X.state->generated += X.n;
 	if (X.dbg && ch == 0) {
@@ -142,15 +163,17 @@ cudaError_t launchKlattPullInit(PullState *state, cudaStream_t stream) {
 	return cudaGetLastError();
 }
 
-// ctx.sigA / sigB / inc / L are filled in here; everything else by the caller.  ctx.n <= kPullMaxTicks.
-cudaError_t launchKlattPull(PullCtx ctx, cudaStream_t stream) {
+// ctx.sigA / sigB / inc / L / segs / pcm are filled in by the launch; everything else by the caller.  ctx.n <= kPullMaxTicks.
+// segSrc: ctx.nSeg segments, pcmOut: room for ctx.n samples rounded up to 8 -- device memory or mapped pinned host memory.
+cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut, cudaStream_t stream) {
 	if (ctx.n == 0) return cudaSuccess;
 	if (ctx.n > kPullMaxTicks || ctx.nSeg == 0 || ctx.nSeg > kPullMaxSegs) return cudaErrorInvalidValue;
 	static bool attrSet[64] = {};
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess) return e;
-	constexpr size_t kMaxSmem = 3 * (size_t)kPullMaxTicks * sizeof(float);  // sigA | sigB aliased by the first half of inc
+	constexpr size_t kMaxSmem = 4 * (size_t)kPullMaxTicks * sizeof(float) + kPullMaxSegs * sizeof(PullSeg) +
+	                            kPullMaxTicks * sizeof(int16_t);
 	if (dev >= 0 && dev < 64 && !attrSet[dev]) {
 		e = cudaFuncSetAttribute(klatt_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
 		if (e != cudaSuccess) return e;
@@ -159,8 +182,11 @@ cudaError_t launchKlattPull(PullCtx ctx, cudaStream_t stream) {
 	ctx.L = pullTicksPerThread(ctx.n);  // 1, 2, 4, 8 or 16: the phase recurrence is unrolled for these
 	ctx.sigA = ctx.sigB = nullptr;
 	ctx.inc = nullptr;
-	const size_t smem = 3 * (size_t)ctx.L * kPullThreads * sizeof(float);
-	klatt_pull_kernel<<<1, kPullThreads, smem, stream>>>(ctx);
+	ctx.segs = nullptr;
+	ctx.pcm = nullptr;
+	const size_t smem = 4 * (size_t)ctx.L * kPullThreads * sizeof(float) + (size_t)ctx.nSeg * sizeof(PullSeg) +
+	                    (((size_t)ctx.n * sizeof(int16_t) + 15) & ~(size_t)15);
+	klatt_pull_kernel<<<1, kPullThreads, smem, stream>>>(ctx, segSrc, pcmOut);
 	return cudaGetLastError();
 }
 

@@ -61,8 +61,7 @@ struct PullCtx {
 	uint32_t nSeg, n, L;  // n ticks in this pull, L ticks per thread
 	int sampleRate;
 	float *sigA, *sigB;   // [L][kPullThreads]: tick t of the pull lives at (t % L) * kPullThreads + t / L
-	double *inc;          // same layout: glottal phase increment of every tick (dead once the sawtooth is in sigA: may
-	                      // share its storage with sigB)
+	double *inc;          // same layout: glottal phase increment of every tick, overwritten with the phase after the tick
 	PullState *state;
 	long long *dbg;       // optional (NVSP_PULL_DEBUG): SM cycle counter at the phase boundaries of the launch
 	int noiseMode;
@@ -287,7 +286,7 @@ KLATT_HD void pullSourcePass1(const PullCtx &X, uint32_t ch, PullSourceSums &out
 	}
 }
 
-// the recurrence itself (one thread): the sawtooth value of every tick -> sigA (src/speechWaveGenerator.cpp:55, :74).
+// the recurrence itself (one thread): X.inc[t] <- glottal phase after tick t (src/speechWaveGenerator.cpp:55, :74).
 // A wrap happens once per pitch period, so the ticks are taken in groups of up to 8: the running sums of a group are
 // formed as if there were no wrap (one dependent FP64 addition per tick, nothing else on the chain), and only if one of
 // them left (-1, 1) is the group redone tick by tick with the reference's fmod.  Same roundings either way.
@@ -303,44 +302,55 @@ KLATT_HD int32_t pullHiWord(double x) {
 template <int LL>
 KLATT_HD void pullPhaseSerialL(const PullCtx &X) {
 	constexpr int G = LL < 8 ? LL : 8;
+	constexpr uint32_t GP = LL / G;  // groups per chunk
 	double pos = X.state->pitchPos;
-	const uint32_t chunks = (X.n + LL - 1) / LL;
-	for (uint32_t ch = 0; ch < chunks; ++ch) {
-		const uint32_t t0 = ch * LL;
-		const uint32_t len = X.n - t0 < (uint32_t)LL ? X.n - t0 : (uint32_t)LL;
-		if (len == (uint32_t)LL) {
+	const uint32_t fullChunks = X.n / LL;
+	const uint32_t groups = fullChunks * GP;
+	// X.inc is overwritten in place with the phase after each tick (as a double: the conversion to the FP32 sawtooth value
+	// is left to the parallel pass that consumes it -- a conversion and a dependent store per tick in THIS loop cost more
+	// than the additions).  The increments of the next group are fetched while the current one is summed.
+	double a[G], nx[G];
 #pragma unroll
-			for (int g0 = 0; g0 < LL; g0 += G) {
-				double a[G], sum[G];
+	for (int k = 0; k < G; ++k) nx[k] = 0.0;
+	if (groups) {
 #pragma unroll
-				for (int k = 0; k < G; ++k) a[k] = X.inc[(uint32_t)(g0 + k) * kPullThreads + ch];
-				sum[0] = pos + a[0];
+		for (int k = 0; k < G; ++k) nx[k] = X.inc[(uint32_t)k * kPullThreads];
+	}
+	for (uint32_t gi = 0; gi < groups; ++gi) {
+		const uint32_t base = (gi % GP) * (uint32_t)(G * kPullThreads) + gi / GP;  // the group's first tick
 #pragma unroll
-				for (int k = 1; k < G; ++k) sum[k] = sum[k - 1] + a[k];
-				int32_t top = 0;
+		for (int k = 0; k < G; ++k) a[k] = nx[k];
+		if (gi + 1 < groups) {
+			const uint32_t nb = ((gi + 1) % GP) * (uint32_t)(G * kPullThreads) + (gi + 1) / GP;
 #pragma unroll
-				for (int k = 0; k < G; ++k) {
-					const int32_t h = pullHiWord(sum[k]) & 0x7fffffff;
-					top = h > top ? h : top;
-				}
-				if (top < 0x3ff00000) {  // every |sum| < 1: no wrap in this group
+			for (int k = 0; k < G; ++k) nx[k] = X.inc[nb + (uint32_t)k * kPullThreads];
+		}
+		double sum[G];
+		sum[0] = pos + a[0];
 #pragma unroll
-					for (int k = 0; k < G; ++k) X.sigA[(uint32_t)(g0 + k) * kPullThreads + ch] = (float)sum[k];
-					pos = sum[G - 1];
-				} else {
+		for (int k = 1; k < G; ++k) sum[k] = sum[k - 1] + a[k];
+		int32_t top = 0;
 #pragma unroll
-					for (int k = 0; k < G; ++k) {
-						pos = fracRef(a[k] + pos);
-						X.sigA[(uint32_t)(g0 + k) * kPullThreads + ch] = (float)pos;
-					}
-				}
-			}
+		for (int k = 0; k < G; ++k) {
+			const int32_t h = pullHiWord(sum[k]) & 0x7fffffff;
+			top = h > top ? h : top;
+		}
+		if (top < 0x3ff00000) {  // every |sum| < 1: no wrap in this group
+#pragma unroll
+			for (int k = 0; k < G; ++k) X.inc[base + (uint32_t)k * kPullThreads] = sum[k];
+			pos = sum[G - 1];
 		} else {
-			for (uint32_t i = 0; i < len; ++i) {
-				pos = fracRef(X.inc[i * kPullThreads + ch] + pos);
-				X.sigA[i * kPullThreads + ch] = (float)pos;
+#pragma unroll
+			for (int k = 0; k < G; ++k) {
+				pos = fracRef(a[k] + pos);
+				X.inc[base + (uint32_t)k * kPullThreads] = pos;
 			}
 		}
+	}
+	const uint32_t tail = X.n - fullChunks * LL;  // the last, shorter chunk
+	for (uint32_t i = 0; i < tail; ++i) {
+		pos = fracRef(X.inc[i * kPullThreads + fullChunks] + pos);
+		X.inc[i * kPullThreads + fullChunks] = pos;
 	}
 	X.state->pitchPos = pos;
 }
@@ -377,7 +387,7 @@ KLATT_HD void pullSourcePass2(const PullCtx &X, uint32_t ch, float aspStart, flo
 		pullNoiseWords(X, g0 + t, blk, blkIndex, wA, wF);
 		const PullSeg &S = X.segs[cur.s];
 		const uint32_t c = cur.c;
-		const float voice = X.sigA[at];
+		const float voice = (float)X.inc[at];
 		aspLast = fmaf(0.75f, aspLast, pullDraw(wA));
 		float asp = aspLast * (0.2f * kDrawScale);
 		float turb = asp * pullDirAt(S, dVoiceTurbulenceAmplitude, c);
@@ -540,22 +550,66 @@ KLATT_HD void pullStage(const PullCtx &X, uint32_t ch, int res, PullAffine *maps
 	}
 }
 
-// composition of affine maps, in double: it is cheap and keeps the scan out of the error budget
+// Composition of affine maps for the block scans.  FP32 with explicit fmaf (the same bits on the device and in the
+// host model below): a pull composes at most 512 maps in a tree of depth 9 + 4, so the scan adds a few 1e-7 relative to
+// the start states -- the size of one tick's own rounding.  (klatt_long.cu composes up to 1e5 maps and does it in
+// double.)  -DKLATT_PULL_SCAN_DOUBLE switches the scalar for A/B studies.
+#ifdef KLATT_PULL_SCAN_DOUBLE
+typedef double PullScalar;
+KLATT_HD PullScalar pullFma(PullScalar a, PullScalar b, PullScalar c) { return fma(a, b, c); }
+#else
+typedef float PullScalar;
+KLATT_HD PullScalar pullFma(PullScalar a, PullScalar b, PullScalar c) { return fmaf(a, b, c); }
+#endif
 struct PullAffineD {
-	double p00, p01, p10, p11, zy, zd;
+	PullScalar p00, p01, p10, p11, zy, zd;
 };
-KLATT_HD PullAffineD pullIdentity() { return PullAffineD{1.0, 0.0, 0.0, 1.0, 0.0, 0.0}; }
+KLATT_HD PullAffineD pullIdentity() { return PullAffineD{1, 0, 0, 1, 0, 0}; }
 KLATT_HD PullAffineD pullToD(const PullAffine &m) { return PullAffineD{m.p00, m.p01, m.p10, m.p11, m.zy, m.zd}; }
+KLATT_HD PullAffineD pullSeed(float y, float d) { return PullAffineD{1, 0, 0, 1, y, d}; }
 // `second` after `first`
 KLATT_HD PullAffineD pullCompose(const PullAffineD &second, const PullAffineD &first) {
 	PullAffineD r;
-	r.p00 = second.p00 * first.p00 + second.p01 * first.p10;
-	r.p01 = second.p00 * first.p01 + second.p01 * first.p11;
-	r.p10 = second.p10 * first.p00 + second.p11 * first.p10;
-	r.p11 = second.p10 * first.p01 + second.p11 * first.p11;
-	r.zy = second.p00 * first.zy + second.p01 * first.zd + second.zy;
-	r.zd = second.p10 * first.zy + second.p11 * first.zd + second.zd;
+	r.p00 = pullFma(second.p00, first.p00, second.p01 * first.p10);
+	r.p01 = pullFma(second.p00, first.p01, second.p01 * first.p11);
+	r.p10 = pullFma(second.p10, first.p00, second.p11 * first.p10);
+	r.p11 = pullFma(second.p10, first.p01, second.p11 * first.p11);
+	r.zy = pullFma(second.p00, first.zy, pullFma(second.p01, first.zd, second.zy));
+	r.zd = pullFma(second.p10, first.zy, pullFma(second.p11, first.zd, second.zd));
 	return r;
 }
+
+#ifndef __CUDACC__
+// Host model of klatt_pull.cu blockExclusive(): the same compositions in the same order (Kogge-Stone inside each warp of
+// 32 chunks, Kogge-Stone over the 16 warp totals, then previous lane -> earlier warps -> seed), so tests/hostsim sees the
+// start states the device computes.  own[kPullThreads] -> pre[kPullThreads].
+inline void pullBlockExclusiveModel(const PullAffineD *own, const PullAffineD &seed, PullAffineD *pre) {
+	constexpr int W = kPullThreads / 32;
+	PullAffineD inc[kPullThreads], tot[W];
+	for (int w = 0; w < W; ++w) {
+		PullAffineD cur[32], nxt[32];
+		for (int l = 0; l < 32; ++l) cur[l] = own[w * 32 + l];
+		for (int delta = 1; delta < 32; delta <<= 1) {
+			for (int l = 0; l < 32; ++l) nxt[l] = l >= delta ? pullCompose(cur[l], cur[l - delta]) : cur[l];
+			for (int l = 0; l < 32; ++l) cur[l] = nxt[l];
+		}
+		for (int l = 0; l < 32; ++l) inc[w * 32 + l] = cur[l];
+		tot[w] = cur[31];
+	}
+	{
+		PullAffineD nxt[W];
+		for (int delta = 1; delta < W; delta <<= 1) {
+			for (int l = 0; l < W; ++l) nxt[l] = l >= delta ? pullCompose(tot[l], tot[l - delta]) : tot[l];
+			for (int l = 0; l < W; ++l) tot[l] = nxt[l];
+		}
+	}
+	for (int t = 0; t < kPullThreads; ++t) {
+		const int w = t >> 5, l = t & 31;
+		PullAffineD p = l == 0 ? pullIdentity() : inc[t - 1];
+		if (w > 0) p = pullCompose(p, tot[w - 1]);
+		pre[t] = pullCompose(p, seed);
+	}
+}
+#endif
 
 }  // namespace klatt

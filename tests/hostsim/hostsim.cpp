@@ -100,11 +100,12 @@ struct HostPullPlayer {
 
 // exclusive prefixes of `maps` (one per chunk) seeded with (y0, d0): what blockExclusive() computes on the device
 void hostScan(const std::vector<PullAffine> &maps, int stride, int k, float y0, float d0, std::vector<PullStart> &out) {
-	PullAffineD pre = PullAffineD{1.0, 0.0, 0.0, 1.0, (double)y0, (double)d0};
+	std::vector<PullAffineD> own(kPullThreads), pre(kPullThreads);
+	for (int ch = 0; ch < kPullThreads; ++ch) own[ch] = pullToD(maps[(size_t)ch * stride + k]);
+	pullBlockExclusiveModel(own.data(), pullSeed(y0, d0), pre.data());
 	for (int ch = 0; ch < kPullThreads; ++ch) {
-		out[(size_t)ch * stride + k].y = (float)pre.zy;
-		out[(size_t)ch * stride + k].d = (float)pre.zd;
-		pre = pullCompose(pullToD(maps[(size_t)ch * stride + k]), pre);
+		out[(size_t)ch * stride + k].y = (float)pre[ch].zy;
+		out[(size_t)ch * stride + k].d = (float)pre[ch].zd;
 	}
 }
 
@@ -134,13 +135,11 @@ void hostPullRender(PullCtx X) {
 	{
 		std::vector<PullSourceSums> sums(kPullThreads);
 		for (int ch = 0; ch < kPullThreads; ++ch) pullSourcePass1(X, ch, sums[ch]);
-		PullAffineD pre = PullAffineD{1.0, 0.0, 0.0, 1.0, (double)X.state->aspLast, (double)X.state->fricLast};
+		std::vector<PullAffineD> own(kPullThreads), pre(kPullThreads);
+		for (int ch = 0; ch < kPullThreads; ++ch) own[ch] = PullAffineD{sums[ch].decay, 0, 0, sums[ch].decay, sums[ch].zAsp, sums[ch].zFric};
+		pullBlockExclusiveModel(own.data(), pullSeed(X.state->aspLast, X.state->fricLast), pre.data());
 		std::vector<float> a0(kPullThreads), f0(kPullThreads);
-		for (int ch = 0; ch < kPullThreads; ++ch) {
-			a0[ch] = (float)pre.zy; f0[ch] = (float)pre.zd;
-			PullAffineD own{(double)sums[ch].decay, 0.0, 0.0, (double)sums[ch].decay, (double)sums[ch].zAsp, (double)sums[ch].zFric};
-			pre = pullCompose(own, pre);
-		}
+		for (int ch = 0; ch < kPullThreads; ++ch) { a0[ch] = (float)pre[ch].zy; f0[ch] = (float)pre[ch].zd; }
 		pullPhaseSerial(X);
 		for (int ch = 0; ch < kPullThreads; ++ch) pullSourcePass2(X, ch, a0[ch], f0[ch]);
 	}
