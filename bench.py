@@ -52,12 +52,13 @@ def parse_args():
                          "consumer): 65536 x 2 s = 5.8 GB pinned per rank instead of 28.9 GB, so 8 ranks fit the host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-streams-per-core", type=int, default=16)
-    ap.add_argument("--workload", default="batch", choices=["batch", "vowel", "midi", "long"],
+    ap.add_argument("--workload", default="batch", choices=["batch", "vowel", "midi", "long", "pull"],
                     help="batch: BASELINE config 3 (default, the headline); vowel: config 2, vowel-chart pairs x --voices "
                          "voices at 16 kHz (one fresh player per (voice, pair)); midi: config 5, midi-sing style streams "
                          "(--streams per GPU x 5 s); long: config 4, ONE stream of --long-seconds at --long-rate through "
                          "the time-parallel kernel")
     ap.add_argument("--voices", type=int, default=1024, help="--workload vowel: voices per GPU (1369 pairs each)")
+    ap.add_argument("--pull-samples", type=int, default=8192, help="--workload pull: samples per speechPlayer_synthesize call")
     ap.add_argument("--long-seconds", type=float, default=3600.0)
     ap.add_argument("--long-rate", type=int, default=44100)
     return ap.parse_args()
@@ -246,6 +247,98 @@ def long_arm(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def pull_arm(args, rank, world, local_rank):
+    """ONE player driven like the NVDA audio thread drives the reference -- speechPlayer_synthesize pulls
+    of --pull-samples (8192) through the five-symbol C-ABI with host buffers -- on the low-latency path
+    (SPEECHPLAYER_PRECISION_STREAM: host frame manager + one time-parallel block launch per pull).  A step is one pull;
+    the number that matters is its latency.  One stream does not shard: N > 1 runs N replicas ("replicas only")."""
+    import numpy as np
+    import torch
+    from nvspeechplayer_b200 import player, workloads
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sr, pull = args.sample_rate, args.pull_samples
+    warm, steps = max(args.warmup, 3), max(args.steps, 50)
+    secs = (warm + steps + 2) * pull / sr
+    fr, m, f, nul, ux = workloads.random_stream(5_000_000 + rank, secs, sr, seed=args.seed)
+    fb = workloads._concat(sr, [(fr, m, f, nul, ux)], [5_000_000 + rank])
+    phi = fb.fade_fraction(int(secs * sr))
+    flops_per_sample = W_HOLD + W_FADE_EXTRA * phi
+    lib = player.load_library()
+    lib.speechPlayer_debugFp32PeakTflops.restype = __import__("ctypes").c_double
+    peak_tf = float(lib.speechPlayer_debugFp32PeakTflops())
+
+    def timed_pulls(make):
+        p = make()
+        p.queue_frames(fr, m, f, ux, nul) if hasattr(p, "queue_frames") else [
+            p.queue_frame(None if nul[j] else fr[j], int(m[j]), int(f[j]), int(ux[j])) for j in range(len(m))]
+        syn = p.synthesize_np if hasattr(p, "synthesize_np") else p.synthesize
+        ts = []
+        for i in range(warm + steps):
+            t0 = time.perf_counter()
+            c = syn(pull)
+            dt = time.perf_counter() - t0
+            assert len(c) == pull
+            if i >= warm:
+                ts.append(dt)
+        p.close()
+        return np.array(ts)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    res = {}
+    for name, prec in (("stream", player.PRECISION_STREAM), ("fp32_serial", player.PRECISION_FP32)):
+        res[name] = timed_pulls(lambda: player.SpeechPlayer(sr, precision=prec, noise=player.NOISE_PHILOX, seed=args.seed,
+                                                            streamId=5_000_000 + rank))
+    clocks = sampler.stop() if rank == 0 else None
+    ts = res["stream"]
+    total_s = float(ts.sum())
+    if world > 1:
+        t = torch.tensor([total_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_s = float(t[0])
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle
+            if oracle.have_ref():
+                ref = oracle.RefLib(philox=False)
+                rts = timed_pulls(lambda: ref.player(sr))
+                kind = "reference"
+            else:
+                port = oracle.PortLib()
+                rts = timed_pulls(lambda: port.player(sr))
+                kind = "port"
+            cpu = {"value": pull / sr / float(np.median(rts)), "unit": "audio-seconds/s", "cores": 1, "kind": kind,
+                   "sample": "the same %d pulls of %d samples on one player, one core" % (steps, pull),
+                   "ms_per_pull_median": float(np.median(rts)) * 1e3, "ms_per_pull_p95": float(np.percentile(rts, 95)) * 1e3}
+        value = world * steps * pull / sr / total_s
+        achieved = steps * pull * flops_per_sample / float(ts.sum()) / 1e12
+        e2e = {"value": value, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(fr.nbytes + m.nbytes + f.nbytes) // steps,
+               "d2h_bytes_per_step": pull * 2, "note": "the path is host-to-host by construction: value IS the end-to-end number"}
+        line = {"metric": "audio-seconds synthesized/sec (one handle, %d-sample pulls)" % pull, "value": value,
+                "unit": "audio-seconds/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": total_s / steps * 1e3,
+                "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "pull: one player, random frames @ %d Hz, speechPlayer_synthesize(%d) per step through the "
+                                       "five-symbol C-ABI, SPEECHPLAYER_PRECISION_STREAM" % (sr, pull),
+                           "fade_fraction_phi": round(phi, 4), "flops_per_sample_W": round(flops_per_sample, 1),
+                           "l2": "not applicable: one block, working set in shared memory"},
+                "latency_ms": {"median": float(np.median(ts)) * 1e3, "p95": float(np.percentile(ts, 95)) * 1e3, "max": float(ts.max()) * 1e3,
+                               "fp32_serial_kernel_median": float(np.median(res["fp32_serial"])) * 1e3},
+                "roofline": {"bound": "latency", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                             "traffic": None, "kernel": "klatt_pull_kernel (1 block of 512 threads per pull)",
+                             "note": "one SM of 148 and a serial FP64 phase recurrence: the bound is dependent-issue latency, "
+                                     "not a throughput roof; per-phase cycles: NVSP_PULL_DEBUG=1"},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": steps, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -253,6 +346,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.workload == "pull":
+        pull_arm(args, rank, world, local_rank)
         return
     if args.workload == "long":
         long_arm(args, rank, world, local_rank)

@@ -478,29 +478,47 @@ KLATT_HD void pullStage(const PullCtx &X, uint32_t ch, int res, PullAffine *maps
 		}
 		in1 = fir[0]; in2 = fir[1];
 	}
+	// What a tick reads besides its input and the section memories: coefficients and mixing gains, functions of
+	// (segment, counter).  Behind the landing tick of a request they are constants, so a chunk that lies inside one hold
+	// (most chunks do: a fade is a third of the ticks and 512 consecutive ticks share a warp) evaluates them once.
+	float ca[NR], crho[NR], cmix[NR], cextra = 0.0f, ca0 = 0.0f, crho0 = 0.0f, crcp0 = 0.0f;
+	bool cinv = false;
+	auto loadCoefs = [&](const PullSeg &S, uint32_t c) {
+		if (STAGE == kPullNasal) {
+			pw0.tick(S, c, kResN0, srInv);
+			pw0.coef(ca0, crho0);
+			cinv = pullN0InvAt(S, c);
+			crcp0 = cinv ? fastRcp(ca0) : 0.0f;
+			cextra = pullDirAt(S, dCaNP, c);
+		}
+#pragma unroll
+		for (int k = 0; k < NR; ++k) {
+			pw[k].tick(S, c, STAGE == kPullParallel ? kResParallel + k : res, srInv);
+			pw[k].coef(ca[k], crho[k]);
+			cmix[k] = STAGE == kPullParallel ? pullDirAt(S, dPa1 + k, c) : 0.0f;
+		}
+		if (STAGE == kPullParallel) cextra = pullDirAt(S, dParallelBypass, c);
+		if (STAGE == kPullLast) cextra = pullDirAt(S, dOutputGain, c) * 4000.0f;
+	};
+	const bool hold = cur.c > X.segs[cur.s].F && cur.left >= t1 - t0;
+	if (hold) loadCoefs(X.segs[cur.s], cur.c);
 	uint32_t at = ch;
 	for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
-		const PullSeg &S = X.segs[cur.s];
-		const uint32_t c = cur.c;
+		if (!hold) loadCoefs(X.segs[cur.s], cur.c);
 		float x = sig[at];
 		const float xin = x;
 		if (STAGE == kPullNasal) {  // rN0 on inputs: src/speechWaveGenerator.cpp:129-135 with anti == true
-			pw0.tick(S, c, kResN0, srInv);
-			float a0, rho0;
-			pw0.coef(a0, rho0);
 			const float dprev = in1 - in2;
 			const float dx = x - in1;
-			const float dx1 = fmaf(-rho0, dprev, dprev);
-			x = pullN0InvAt(S, c) ? fmaf(dx - dx1, fastRcp(a0), in1) : fmaf(a0, dx, dx1 + in1);
+			const float dx1 = fmaf(-crho0, dprev, dprev);
+			x = cinv ? fmaf(dx - dx1, crcp0, in1) : fmaf(ca0, dx, dx1 + in1);
 			in2 = in1;
 			in1 = xin;
 		}
 		float acc = 0.0f;
 #pragma unroll
 		for (int k = 0; k < NR; ++k) {
-			pw[k].tick(S, c, STAGE == kPullParallel ? kResParallel + k : res, srInv);
-			float a, rho;
-			pw[k].coef(a, rho);
+			const float a = ca[k], rho = crho[k];
 			float w = fmaf(-rho, d[k], d[k]);
 			w = fmaf(-a, y[k], w);
 			const float dn = fmaf(a, x, w);
@@ -512,23 +530,23 @@ KLATT_HD void pullStage(const PullCtx &X, uint32_t ch, int res, PullAffine *maps
 				p00[k] += n10; p01[k] += n11;
 				p10[k] = n10; p11[k] = n11;
 			}
-			if (STAGE == kPullParallel) acc = fmaf(y[k] - x, pullDirAt(S, dPa1 + k, c), acc);
+			if (STAGE == kPullParallel) acc = fmaf(y[k] - x, cmix[k], acc);
 		}
 		if (PASS == 2) {
 			if (STAGE == kPullParallel) {
-				sig[at] = fmaf(x - acc, pullDirAt(S, dParallelBypass, c), acc);
+				sig[at] = fmaf(x - acc, cextra, acc);
 			} else if (STAGE == kPullNasal) {
-				sig[at] = fmaf(y[0] - xin, pullDirAt(S, dCaNP, c), xin);
+				sig[at] = fmaf(y[0] - xin, cextra, xin);
 			} else if (STAGE == kPullCascade) {
 				sig[at] = y[0];
 			} else {
-				float s = (y[0] + X.sigB[at]) * (pullDirAt(S, dOutputGain, c) * 4000.0f);
+				float s = (y[0] + X.sigB[at]) * cextra;
 				s = fminf(s, 32000.0f);
 				s = fmaxf(s, -32000.0f);
 				X.pcm[t] = (int16_t)(int)s;
 			}
 		}
-		cur.next(X);
+		if (!hold) cur.next(X);
 	}
 	if (PASS == 1) {
 #pragma unroll
