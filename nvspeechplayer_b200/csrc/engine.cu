@@ -790,6 +790,10 @@ static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *ou
 			} else if (p->noiseMode == kNoiseReplay) {
 				X.draws = p->dReplay.as<int32_t>(); X.drawBase = 0; X.drawLen = p->replayHost.size();
 			}
+			// the glottal-phase recurrence: run decomposition (klatt_pull_core.cuh pullRuns*; bit-identical to the serial loop,
+			// 280 k -> 48 k cycles of an 8192-tick launch on B200) unless NVSP_PULL_PHASE=serial asks for the plain loop
+			static const bool phaseSerial = getenv("NVSP_PULL_PHASE") && !strcmp(getenv("NVSP_PULL_PHASE"), "serial");
+			X.phaseMode = phaseSerial ? 0 : 1;
 			static const bool debugPhases = getenv("NVSP_PULL_DEBUG") != nullptr;
 			if (debugPhases && p->dPullDbg.reserve(16 * sizeof(long long))) X.dbg = p->dPullDbg.as<long long>();
 			CU(launchKlattPull(X, segSrc, pcmOut, stream));

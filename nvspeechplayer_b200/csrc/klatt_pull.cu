@@ -56,6 +56,69 @@ __device__ PullAffineD blockExclusive(const PullAffineD &own, const PullAffineD 
 
 __device__ __forceinline__ PullAffineD seedOf(float y, float d) { return pullSeed(y, d); }
 
+// ---- scans of the run decomposition of the phase (phaseMode 1) ----
+__device__ __forceinline__ PullRunSum shflUpRun(const PullRunSum &m, int delta) {
+	PullRunSum r;
+	r.sum = __shfl_up_sync(0xffffffffu, m.sum, delta);
+	r.flag = __shfl_up_sync(0xffffffffu, m.flag, delta);
+	r.specials = __shfl_up_sync(0xffffffffu, m.specials, delta);
+	return r;
+}
+// exclusive segmented prefix over the block; total = the combination of all 512 elements
+__device__ PullRunSum blockExclusiveRuns(const PullRunSum &own, PullRunSum *warpTotal, PullRunSum &total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const PullRunSum zero{0, 0u, 0u};
+	PullRunSum inc = own;
+#pragma unroll
+	for (int delta = 1; delta < 32; delta <<= 1) {
+		PullRunSum up = shflUpRun(inc, delta);
+		if (lane >= delta) inc = pullRunCombine(up, inc);
+	}
+	if (lane == 31) warpTotal[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		PullRunSum w = lane < kPullWarps ? warpTotal[lane] : zero;
+#pragma unroll
+		for (int delta = 1; delta < kPullWarps; delta <<= 1) {
+			PullRunSum up = shflUpRun(w, delta);
+			if (lane >= delta) w = pullRunCombine(up, w);
+		}
+		if (lane < kPullWarps) warpTotal[lane] = w;
+	}
+	__syncthreads();
+	PullRunSum prev = shflUpRun(inc, 1);
+	PullRunSum pre = lane == 0 ? zero : prev;
+	if (warp > 0) pre = pullRunCombine(warpTotal[warp - 1], pre);
+	total = warpTotal[kPullWarps - 1];
+	__syncthreads();
+	return pre;
+}
+// exclusive sum modulo 2^64 (the approximate phase in 2^-64 cycles: exact and associative)
+__device__ uint64_t blockExclusiveU64(uint64_t own, uint64_t *warpSum) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint64_t inc = own;
+#pragma unroll
+	for (int delta = 1; delta < 32; delta <<= 1) {
+		uint64_t up = __shfl_up_sync(0xffffffffu, inc, delta);
+		if (lane >= delta) inc += up;
+	}
+	if (lane == 31) warpSum[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		uint64_t w = lane < kPullWarps ? warpSum[lane] : 0;
+#pragma unroll
+		for (int delta = 1; delta < kPullWarps; delta <<= 1) {
+			uint64_t up = __shfl_up_sync(0xffffffffu, w, delta);
+			if (lane >= delta) w += up;
+		}
+		if (lane < kPullWarps) warpSum[lane] = w;
+	}
+	__syncthreads();
+	const uint64_t pre = inc - own + (warp > 0 ? warpSum[warp - 1] : 0);
+	__syncthreads();
+	return pre;
+}
+
 template <int STAGE>
 __device__ __forceinline__ void runStage(const PullCtx &X, uint32_t ch, int res, PullAffineD *warpTotal) {
 	constexpr int NR = PullStageTraits<STAGE>::NR;
@@ -93,6 +156,10 @@ klatt_pull_kernel(PullCtx X, const PullSeg *__restrict__ segSrc, int16_t *__rest
 	X.inc = reinterpret_cast<double *>(pullSmem + 2 * sigBytes);
 	PullSeg *segS = reinterpret_cast<PullSeg *>(pullSmem + 4 * sigBytes);
 	int16_t *pcmS = reinterpret_cast<int16_t *>(pullSmem + 4 * sigBytes + (size_t)X.nSeg * sizeof(PullSeg));
+	X.runI = reinterpret_cast<int64_t *>(pullSmem);         // over sigA + sigB, both dead until source pass 2
+	X.runMeta = reinterpret_cast<uint16_t *>(pcmS);         // over the output staging, dead until the last stage
+	X.rec = reinterpret_cast<PullPhaseRec *>(pullSmem + 4 * sigBytes + (size_t)X.nSeg * sizeof(PullSeg) +
+	                                         (((size_t)X.n * sizeof(int16_t) + 15) & ~(size_t)15));
 	const uint32_t ch = threadIdx.x;
 	{
 		const uint4 *src = reinterpret_cast<const uint4 *>(segSrc);
@@ -118,7 +185,29 @@ klatt_pull_kernel(PullCtx X, const PullSeg *__restrict__ segSrc, int16_t *__rest
 		const PullAffineD own{sums.decay, 0, 0, sums.decay, sums.zAsp, sums.zFric};
 		const PullAffineD pre = blockExclusive(own, seedOf(X.state->aspLast, X.state->fricLast), warpTotal);
 		mark(X, 2);
-		if (ch == 0) pullPhaseSerial(X);
+		bool runsDone = false;
+		if (X.phaseMode) {  // run decomposition: the serial thread only visits the special ticks
+			__shared__ PullRunSum runTotal[kPullWarps];
+			__shared__ uint64_t warpSum[kPullWarps];
+			const double pos0 = X.state->pitchPos;
+			uint64_t fixed0;
+			const bool okStart = pullRunsStart(pos0, fixed0);
+			const uint64_t startFixed = fixed0 + blockExclusiveU64(sums.phaseFixed, warpSum);
+			PullRunSum mine;
+			pullRunsClassify(X, ch, startFixed, mine);
+			if (ch == 0 && !okStart) mine.specials += kPullMaxSpecial + 1;
+			PullRunSum total;
+			const PullRunSum before = blockExclusiveRuns(mine, runTotal, total);  // its barriers also publish runMeta / runI
+			if (total.specials <= kPullMaxSpecial) {  // uniform
+				pullRunsOffsets(X, ch, before);
+				__syncthreads();
+				if (ch == 0) pullRunsSerial(X, total.specials, pos0);
+				__syncthreads();
+				pullRunsFinish(X, ch, before.specials, pos0);
+				runsDone = true;
+			}
+		}
+		if (!runsDone && ch == 0) pullPhaseSerial(X);
 		__syncthreads();
 		mark(X, 3);
 		pullSourcePass2(X, ch, (float)pre.zy, (float)pre.zd);
@@ -173,7 +262,7 @@ cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut,
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess) return e;
 	constexpr size_t kMaxSmem = 4 * (size_t)kPullMaxTicks * sizeof(float) + kPullMaxSegs * sizeof(PullSeg) +
-	                            kPullMaxTicks * sizeof(int16_t);
+	                            kPullMaxTicks * sizeof(int16_t) + kPullMaxSpecial * sizeof(PullPhaseRec);
 	if (dev >= 0 && dev < 64 && !attrSet[dev]) {
 		e = cudaFuncSetAttribute(klatt_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
 		if (e != cudaSuccess) return e;
@@ -185,7 +274,11 @@ cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut,
 	ctx.segs = nullptr;
 	ctx.pcm = nullptr;
 	const size_t smem = 4 * (size_t)ctx.L * kPullThreads * sizeof(float) + (size_t)ctx.nSeg * sizeof(PullSeg) +
-	                    (((size_t)ctx.n * sizeof(int16_t) + 15) & ~(size_t)15);
+	                    (((size_t)ctx.n * sizeof(int16_t) + 15) & ~(size_t)15) +
+	                    (ctx.phaseMode ? kPullMaxSpecial * sizeof(PullPhaseRec) : 0);
+	ctx.runI = nullptr;
+	ctx.runMeta = nullptr;
+	ctx.rec = nullptr;
 	klatt_pull_kernel<<<1, kPullThreads, smem, stream>>>(ctx, segSrc, pcmOut);
 	return cudaGetLastError();
 }

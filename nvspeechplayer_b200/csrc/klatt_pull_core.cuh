@@ -56,12 +56,18 @@ struct PullState {
 	uint64_t generated;       // samples generated so far == noise draws consumed / 2
 };
 
+struct PullPhaseRec;
 struct PullCtx {
 	const PullSeg *segs;
 	uint32_t nSeg, n, L;  // n ticks in this pull, L ticks per thread
 	int sampleRate;
 	float *sigA, *sigB;   // [L][kPullThreads]: tick t of the pull lives at (t % L) * kPullThreads + t / L
 	double *inc;          // same layout: glottal phase increment of every tick, overwritten with the phase after the tick
+	// phaseMode 1 ("runs", the default): scratch of the run decomposition of the phase recurrence (see pullRuns*)
+	int phaseMode;
+	int64_t *runI;        // [L][kPullThreads], 8 bytes per tick: may share the storage of sigA + sigB (both dead until pass 2)
+	uint16_t *runMeta;    // [n], by tick: may share the storage of the int16 output (dead until the last stage)
+	struct PullPhaseRec *rec;  // [kPullMaxSpecial]
 	PullState *state;
 	long long *dbg;       // optional (NVSP_PULL_DEBUG): SM cycle counter at the phase boundaries of the launch
 	int noiseMode;
@@ -228,6 +234,8 @@ KLATT_HD float pullDraw(uint32_t w) { return bitsToFloat(0x4B000000u | (w >> 9))
 struct PullSourceSums {
 	float zAsp, zFric;   // colouring filters at the end of the chunk when started from zero
 	float decay;         // 0.75 ^ (ticks in the chunk)
+	uint64_t phaseFixed; // what the chunk adds to the phase in 2^-64 cycles (exact, associative: the APPROXIMATE phase
+	                     // the run decomposition classifies ticks with)
 };
 
 struct PullOsc {  // vibrato + pitch along the pull
@@ -265,7 +273,7 @@ KLATT_HD void pullChunkRange(const PullCtx &X, uint32_t ch, uint32_t &t0, uint32
 KLATT_HD void pullSourcePass1(const PullCtx &X, uint32_t ch, PullSourceSums &out) {
 	uint32_t t0, t1;
 	pullChunkRange(X, ch, t0, t1);
-	out.zAsp = 0.0f; out.zFric = 0.0f; out.decay = 1.0f;
+	out.zAsp = 0.0f; out.zFric = 0.0f; out.decay = 1.0f; out.phaseFixed = 0;
 	if (t0 >= t1) return;
 	const double srD = (double)X.sampleRate, srInv = 1.0 / srD;
 	const uint64_t g0 = X.state->generated;
@@ -281,7 +289,9 @@ KLATT_HD void pullSourcePass1(const PullCtx &X, uint32_t ch, PullSourceSums &out
 		out.zAsp = fmaf(0.75f, out.zAsp, pullDraw(wA));
 		out.zFric = fmaf(0.75f, out.zFric, pullDraw(wF));
 		out.decay *= 0.75f;
-		X.inc[at] = w.phaseInc(X, srD, srInv);
+		const double pinc = w.phaseInc(X, srD, srInv);
+		X.inc[at] = pinc;
+		if (X.phaseMode) out.phaseFixed += (uint64_t)cyclesToFixed(pinc);
 		w.next(X);
 	}
 }
@@ -367,6 +377,170 @@ KLATT_HD uint32_t pullTicksPerThread(uint32_t n) {
 	uint32_t L = 1;
 	while (L * (uint32_t)kPullThreads < n) L <<= 1;
 	return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Run decomposition of the phase recurrence (phaseMode 1, the default; NVSP_PULL_PHASE=serial selects the loop above).
+// While the phase stays inside one binade [2^k, 2^(k+1)) every value it takes is a multiple of that binade's ulp
+// u = 2^(k-52), so RN(pos + inc) = pos + RN_u(inc) unless inc/u lies exactly half-way: the rounded increments are
+// integers on a fixed grid and the recurrence is an integer prefix sum -- associative, scannable, and bit for bit what
+// the FP64 additions would have produced.  Only the SPECIAL ticks need the real FP64 addition, in order: wraps, binade
+// crossings, ties, non-positive or huge increments, and ticks whose approximate phase (the exact 2^-64 fixed-point
+// prefix sum, off by < 1e-12) is within 2^-30 of a binade boundary.  They are 1-20 % of the ticks
+// (tools/phase_runs_study.py, which also checks the decomposition bit for bit against the serial loop).
+//   classify   per tick, from the approximate phase: normal (k, I = RN_u(inc)/u) or special; per chunk: sum of I behind
+//              its last special tick, number of special ticks                       -> segmented block scan
+//   offsets    per normal tick: off = (sum of I since the last special tick) * u, exact in double; per special tick a
+//              record (off of the tick before, its increment), in order
+//   serial     ONE thread, over the special ticks only: pos = fmod((pos + offPrev) + inc, 1)
+//   finish     every tick: phase = (phase after the last special tick before it) + off
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kPullMaxSpecial = 2048;  // more special ticks than this in one launch: the plain serial loop takes over
+struct PullPhaseRec {
+	double offPrev;  // phase offset of the tick before this special tick from the previous special tick (0 if that is special too)
+	double v;        // increment of this tick; replaced by the phase after it
+};
+struct PullRunSum {   // summary of a chunk, and the element type of the segmented scan
+	int64_t sum;       // sum of I behind the last special tick (of everything if there is none)
+	uint32_t flag;     // a special tick inside
+	uint32_t specials;
+};
+KLATT_HD PullRunSum pullRunCombine(const PullRunSum &first, const PullRunSum &second) {
+	PullRunSum r;
+	r.specials = first.specials + second.specials;
+	r.flag = first.flag | second.flag;
+	r.sum = second.flag ? second.sum : first.sum + second.sum;
+	return r;
+}
+KLATT_HD double pullPow2(int e) {  // 2^e, -1022 <= e <= 1023
+	const uint64_t b = (uint64_t)(e + 1023) << 52;
+#ifdef __CUDA_ARCH__
+	return __longlong_as_double((long long)b);
+#else
+	double d;
+	memcpy(&d, &b, 8);
+	return d;
+#endif
+}
+KLATT_HD int pullBinade(double x) { return (int)((pullHiWord(x) >> 20) & 0x7ff) - 1023; }  // x in [2^k, 2^(k+1)), x > 0 normal
+KLATT_HD double pullFixedToCycles(uint64_t a) { return (double)(a >> 11) * 1.1102230246251565e-16; }  // top 53 bits * 2^-53
+
+// normal tick?  aPrev: approximate phase before the tick, x: its increment.  I: increment in ulps of binade k.
+KLATT_HD bool pullClassify(double aPrev, double x, int64_t &I, int &k) {
+	const double margin = 9.313225746154785e-10;  // 2^-30
+	if (!(x >= 0.0 && x < 0.5) || !(aPrev >= 9.094947017729282e-13 /* 2^-40 */)) return false;
+	const double s = aPrev + x;
+	if (!(s < 1.0 - margin)) return false;
+	k = pullBinade(s);
+	const double lo = pullPow2(k);
+	if (pullBinade(aPrev) != k || aPrev < lo * (1.0 + margin) || s > (2.0 * lo) * (1.0 - margin)) return false;
+	const double r = x * pullPow2(52 - k);  // x / u, exact
+	const double fl = floor(r);
+	const double fr = r - fl;               // exact
+	if (fr == 0.5) return false;            // tie: round-half-even looks at the parity of pos / u
+	I = (int64_t)fl + (fr > 0.5 ? 1 : 0);
+	return true;
+}
+
+KLATT_HD void pullRunsClassify(const PullCtx &X, uint32_t ch, uint64_t startFixed, PullRunSum &out) {
+	uint32_t t0, t1;
+	pullChunkRange(X, ch, t0, t1);
+	out.sum = 0; out.flag = 0; out.specials = 0;
+	uint64_t A = startFixed;
+	uint32_t at = ch;
+	for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
+		const double x = X.inc[at];
+		const double aPrev = pullFixedToCycles(A);
+		A += (uint64_t)cyclesToFixed(x);
+		int64_t I = 0;
+		int k = 0;
+		// a phase that may turn negative, or an increment the fixed-point approximation cannot hold (|pitch| >= sr/2):
+		// leave the whole pull to the serial loop
+		if (!(x >= 0.0 && x < 0.5)) out.specials += kPullMaxSpecial + 1;
+		if (pullClassify(aPrev, x, I, k)) {
+			X.runI[at] = I;
+			X.runMeta[t] = (uint16_t)(0x8000 | (k + 64));
+			out.sum += I;
+		} else {
+			X.runI[at] = 0;
+			X.runMeta[t] = 0;
+			out.sum = 0;
+			out.flag = 1;
+			out.specials += 1;
+		}
+	}
+}
+
+// before: the exclusive segmented prefix of the chunk (sum of I since the last special tick, special ticks so far)
+KLATT_HD void pullRunsOffsets(const PullCtx &X, uint32_t ch, const PullRunSum &before) {
+	uint32_t t0, t1;
+	pullChunkRange(X, ch, t0, t1);
+	if (t0 >= t1) return;
+	int64_t O = before.sum;
+	uint32_t j = before.specials;
+	double lastOff = 0.0;  // offset of the tick before, 0 when that tick is special (or belongs to the previous pull)
+	if (t0 > 0) {
+		const uint16_t m = X.runMeta[t0 - 1];
+		if (m & 0x8000) lastOff = (double)O * pullPow2((int)(m & 0x7fff) - 64 - 52);
+	}
+	double *off = reinterpret_cast<double *>(X.runI);
+	uint32_t at = ch;
+	for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
+		const uint16_t m = X.runMeta[t];
+		if (m & 0x8000) {
+			O += X.runI[at];
+			lastOff = (double)O * pullPow2((int)(m & 0x7fff) - 64 - 52);  // exact: |O| < 2^53, a power of two
+			off[at] = lastOff;
+		} else {
+			if (j < kPullMaxSpecial) {
+				X.rec[j].offPrev = lastOff;
+				X.rec[j].v = X.inc[at];
+			}
+			++j;
+			O = 0;
+			lastOff = 0.0;
+		}
+	}
+}
+
+// the carried phase as the start of the approximate (fixed-point) phase; negative (only after negative pitches): no runs
+KLATT_HD bool pullRunsStart(double pos0, uint64_t &fixed) {
+	if (!(pos0 >= 0.0 && pos0 < 1.0)) { fixed = 0; return false; }
+	fixed = (uint64_t)(pos0 * 18446744073709551616.0);
+	return true;
+}
+
+// one thread: the FP64 recurrence over the special ticks only; returns the phase after the last of them
+KLATT_HD double pullRunsSerial(const PullCtx &X, uint32_t specials, double pos0) {
+	double pos = pos0;
+	for (uint32_t j = 0; j < specials; ++j) {
+		const double s = (pos + X.rec[j].offPrev) + X.rec[j].v;  // the first addition is exact (same grid, same binade)
+		pos = ((pullHiWord(s) & 0x7fffffff) < 0x3ff00000) ? s : fracRef(s);
+		X.rec[j].v = pos;
+	}
+	return pos;
+}
+
+// X.inc[t] <- phase after tick t; the pull's last chunk leaves the carry
+KLATT_HD void pullRunsFinish(const PullCtx &X, uint32_t ch, uint32_t specialsBefore, double pos0) {
+	uint32_t t0, t1;
+	pullChunkRange(X, ch, t0, t1);
+	if (t0 >= t1) return;
+	uint32_t j = specialsBefore;
+	double base = j ? X.rec[j - 1].v : pos0;
+	const double *off = reinterpret_cast<const double *>(X.runI);
+	double p = base;
+	uint32_t at = ch;
+	for (uint32_t t = t0; t < t1; ++t, at += kPullThreads) {
+		if (X.runMeta[t] & 0x8000) {
+			p = base + off[at];  // exact
+		} else {
+			base = X.rec[j++].v;
+			p = base;
+		}
+		X.inc[at] = p;
+	}
+	if (t1 == X.n) X.state->pitchPos = p;
 }
 
 // pass 2: the two excitation signals of every tick: cascade input -> sigA (:204, :148), parallel input -> sigB (:206, :171)

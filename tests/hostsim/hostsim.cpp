@@ -8,6 +8,7 @@
 //   mode 0  one general-kernel pass per `chunk` ticks, plans made inline at the pop tick (per-handle API)
 //   mode 1  plans precomputed for the whole queue (klatt_plan_kernel), then ROUNDS: a stream with at least holdTicks
 //           pure hold ticks ahead runs renderHoldF32(holdTicks), otherwise renderGeneralF32(genTicks)
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -95,6 +96,7 @@ struct HostPullPlayer {
 	PullState state;
 	int sampleRate;
 	uint64_t seed, streamId;
+	int phaseMode = 0;
 	HostPullPlayer(int sr, uint64_t sd, uint64_t sid) : mgr(sr), sampleRate(sr), seed(sd), streamId(sid) { memset(&state, 0, sizeof state); }
 };
 
@@ -125,6 +127,8 @@ template <int STAGE> void hostStage(const PullCtx &X, int res) {
 		pullStage<STAGE, 2>(X, ch, res, nullptr, &st[(size_t)ch * NR], &fir[(size_t)ch * 2], &poles[(size_t)ch * (NR + 1)]);
 }
 
+unsigned long long g_runsLaunches = 0, g_runsSpecials = 0;
+
 void hostPullRender(PullCtx X) {
 	X.L = pullTicksPerThread(X.n);
 	std::vector<float> sig((size_t)2 * X.L * kPullThreads, 0.0f);
@@ -132,6 +136,10 @@ void hostPullRender(PullCtx X) {
 	X.sigB = sig.data() + (size_t)X.L * kPullThreads;
 	std::vector<double> inc((size_t)X.L * kPullThreads, 0.0);
 	X.inc = inc.data();
+	std::vector<int64_t> runI((size_t)X.L * kPullThreads, 0);
+	std::vector<uint16_t> runMeta(X.n + 8, 0);
+	std::vector<PullPhaseRec> rec(kPullMaxSpecial);
+	X.runI = runI.data(); X.runMeta = runMeta.data(); X.rec = rec.data();
 	{
 		std::vector<PullSourceSums> sums(kPullThreads);
 		for (int ch = 0; ch < kPullThreads; ++ch) pullSourcePass1(X, ch, sums[ch]);
@@ -140,7 +148,44 @@ void hostPullRender(PullCtx X) {
 		pullBlockExclusiveModel(own.data(), pullSeed(X.state->aspLast, X.state->fricLast), pre.data());
 		std::vector<float> a0(kPullThreads), f0(kPullThreads);
 		for (int ch = 0; ch < kPullThreads; ++ch) { a0[ch] = (float)pre[ch].zy; f0[ch] = (float)pre[ch].zd; }
-		pullPhaseSerial(X);
+		bool runsDone = false;
+		if (X.phaseMode) {  // the run decomposition, scans as plain loops (integer arithmetic: the order does not matter)
+			const double pos0 = X.state->pitchPos;
+			uint64_t fixed = 0;
+			const bool okStart = pullRunsStart(pos0, fixed);
+			std::vector<PullRunSum> mine(kPullThreads), before(kPullThreads);
+			for (int ch = 0; ch < kPullThreads; ++ch) {
+				pullRunsClassify(X, ch, fixed, mine[ch]);
+				fixed += sums[ch].phaseFixed;
+			}
+			if (!okStart) mine[0].specials += kPullMaxSpecial + 1;
+			PullRunSum acc{0, 0u, 0u};
+			for (int ch = 0; ch < kPullThreads; ++ch) { before[ch] = acc; acc = pullRunCombine(acc, mine[ch]); }
+			if (acc.specials <= kPullMaxSpecial) {
+				std::vector<double> incCopy;
+				if (getenv("HOSTSIM_CHECK_RUNS")) incCopy.assign(X.inc, X.inc + (size_t)X.L * kPullThreads);
+				for (int ch = 0; ch < kPullThreads; ++ch) pullRunsOffsets(X, ch, before[ch]);
+				pullRunsSerial(X, acc.specials, pos0);
+				for (int ch = 0; ch < kPullThreads; ++ch) pullRunsFinish(X, ch, before[ch].specials, pos0);
+				if (!incCopy.empty()) {  // debug: the plain recurrence on a copy, first mismatch reported
+					double pos = pos0;
+					for (uint32_t t = 0; t < X.n; ++t) {
+						const uint32_t at = pullIdx(X, t);
+						const double x = incCopy[at];
+						pos = fracRef(x + pos);
+						if (memcmp(&pos, &X.inc[at], 8) != 0) {
+							fprintf(stderr, "[runs mismatch] n=%u t=%u inc=%.17g want=%.17g got=%.17g meta=%04x prevmeta=%04x pos0=%.17g specials=%u\n",
+							        X.n, t, x, pos, X.inc[at], X.runMeta[t], t ? X.runMeta[t - 1] : 0, pos0, acc.specials);
+							break;
+						}
+					}
+				}
+				runsDone = true;
+				g_runsLaunches++;
+				g_runsSpecials += acc.specials;
+			}
+		}
+		if (!runsDone) pullPhaseSerial(X);
 		for (int ch = 0; ch < kPullThreads; ++ch) pullSourcePass2(X, ch, a0[ch], f0[ch]);
 	}
 	hostStage<kPullParallel>(X, 0);
@@ -153,6 +198,10 @@ void hostPullRender(PullCtx X) {
 
 extern "C" void *hostsim_pull_create(int sampleRate, uint64_t seed, uint64_t streamId) {
 	return new HostPullPlayer(sampleRate, seed, streamId);
+}
+extern "C" void hostsim_pull_phase_mode(void *h, int mode) { ((HostPullPlayer *)h)->phaseMode = mode; }
+extern "C" void hostsim_pull_runs_stats(unsigned long long *launches, unsigned long long *specials) {
+	*launches = g_runsLaunches; *specials = g_runsSpecials;
 }
 extern "C" void hostsim_pull_destroy(void *h) { delete (HostPullPlayer *)h; }
 extern "C" void hostsim_pull_queue(void *h, const double *frame, uint32_t minDur, uint32_t fadeDur, int32_t userIndex, int purge) {
@@ -177,6 +226,7 @@ extern "C" int hostsim_pull_synthesize(void *h, uint32_t n, int16_t *out, uint32
 			X.segs = segs.data(); X.nSeg = (uint32_t)segs.size(); X.n = got; X.sampleRate = p->sampleRate;
 			X.state = &p->state; X.noiseMode = kNoisePhilox; X.seed = p->seed; X.streamId = p->streamId;
 			X.pcm = out + total;
+			X.phaseMode = p->phaseMode;
 			hostPullRender(X);
 		}
 		total += got;

@@ -64,7 +64,7 @@ class PullPlayer:
     """The low-latency pull path on the host: the product's request-level frame manager (pull_manager.h) driving a
     thread-by-thread emulation of klatt_pull_kernel.  Same surface as the players `scenarios.run_script` drives."""
 
-    def __init__(self, sr, seed=0, stream=0, max_ticks=0, max_segs=0):
+    def __init__(self, sr, seed=0, stream=0, max_ticks=0, max_segs=0, phase_mode=1):
         L = lib()
         vp = ctypes.c_void_p
         L.hostsim_pull_create.restype = vp
@@ -76,7 +76,9 @@ class PullPlayer:
         L.hostsim_pull_synthesize.restype = ctypes.c_int
         L.hostsim_pull_synthesize.argtypes = [vp, ctypes.c_uint, vp, ctypes.c_uint, ctypes.c_uint]
         self.L = L
+        L.hostsim_pull_phase_mode.argtypes = [vp, ctypes.c_int]
         self.h = L.hostsim_pull_create(sr, seed, stream)
+        L.hostsim_pull_phase_mode(self.h, int(phase_mode))
         self.max_ticks, self.max_segs = max_ticks, max_segs
 
     def queue_frame(self, frame, min_dur, fade_dur, user_index=-1, purge=False):
@@ -101,3 +103,10 @@ class PullPlayer:
         if self.h:
             self.L.hostsim_pull_destroy(self.h)
             self.h = None
+
+
+def pull_runs_stats():
+    """(launches rendered with the run decomposition of the phase, special ticks in them) since the library was loaded"""
+    a, b = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    lib().hostsim_pull_runs_stats(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value

@@ -114,3 +114,43 @@ def test_pull_random_scripts_vs_oracle(port, seed):
     assert counts == wcounts
     assert idx == widx
     parity.assert_f32_parity(got, want, "random script %d" % seed, short_ok=3)
+
+
+def test_pull_phase_runs_bit_identical(golden_config1):
+    """The run decomposition of the glottal-phase recurrence (klatt_pull_core.cuh pullRuns*, the device's default) renders
+    the same bits as the plain serial FP64 loop -- on every scenario (whole-sample pitch periods, negative pitches that
+    hand the pull back to the serial loop, purges), on config 1 and on random frames -- while leaving only a fraction of
+    the ticks to the serial thread."""
+    def render_all(mode):
+        outs = []
+        for name, sc in sorted(scenarios.all_scenarios().items()):
+            pcm, _, _ = scenarios.run_script(lambda sr: _player(sr, phase_mode=mode), sc)
+            outs.append(pcm)
+        g = golden_config1
+        p = sim.PullPlayer(int(g["sample_rate"]), seed=int(g["philox_seed"]), stream=int(g["philox_stream"]), phase_mode=mode)
+        for j in range(len(g["min_dur"])):
+            p.queue_frame(None if g["is_null"][j] else g["frames"][j], int(g["min_dur"][j]), int(g["fade_dur"][j]))
+        while True:
+            c = p.synthesize(8192)
+            if c.size == 0:
+                break
+            outs.append(c.copy())
+        p.close()
+        for sr, pull in ((16000, 8192), (22050, 2048), (44100, 333)):
+            fr, m, f, nul, ux = workloads.random_stream(99, 1.5, sr)
+            p = sim.PullPlayer(sr, seed=3, stream=99, phase_mode=mode)
+            for j in range(len(m)):
+                p.queue_frame(None if nul[j] else fr[j], int(m[j]), int(f[j]), int(ux[j]))
+            for _ in range(int(1.5 * sr) // pull):
+                outs.append(p.synthesize(pull).copy())
+            p.close()
+        return np.concatenate(outs)
+
+    l0, s0 = sim.pull_runs_stats()
+    plain = render_all(0)
+    assert sim.pull_runs_stats() == (l0, s0)
+    runs = render_all(1)
+    l1, s1 = sim.pull_runs_stats()
+    np.testing.assert_array_equal(runs, plain)
+    assert l1 - l0 > 100                                  # the decomposition did render most launches ...
+    assert (s1 - s0) < 0.25 * plain.size                  # ... and left the serial thread a fraction of the ticks
