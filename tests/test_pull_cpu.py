@@ -154,3 +154,60 @@ def test_pull_phase_runs_bit_identical(golden_config1):
     np.testing.assert_array_equal(runs, plain)
     assert l1 - l0 > 100                                  # the decomposition did render most launches ...
     assert (s1 - s0) < 0.25 * plain.size                  # ... and left the serial thread a fraction of the ticks
+
+
+def _pull_stream(sr, fr, m, f, nul, ux, count, seed, stream, pull=8192):
+    p = sim.PullPlayer(sr, seed=seed, stream=stream)
+    for j in range(len(m)):
+        p.queue_frame(None if nul[j] else fr[j], int(m[j]), int(f[j]), int(ux[j]))
+    got = []
+    while sum(len(c) for c in got) < count:
+        c = p.synthesize(min(pull, count - sum(len(c) for c in got)))
+        if c.size == 0:
+            break
+        got.append(c.copy())
+    p.close()
+    return np.concatenate(got) if got else np.zeros(0, np.int16)
+
+
+def test_pull_config2_vowel_chart_streams(port):
+    """BASELINE config 2 recipe (16 kHz, vowel pair x voice, pitch sweeps 40 -> 300 -> 40 Hz) through pulls."""
+    fb = workloads.vowel_chart(2, pairs=6)
+    for s in range(fb.num_streams):
+        fr, m, f, nul, ux = fb.stream(s)
+        count = int(fb.timeline_samples()[s])
+        want = port.render(16000, fr, m, f, nul, ux, max_samples=count, noise=("philox", 8, int(fb.stream_ids[s])))
+        got = _pull_stream(16000, fr, m, f, nul, ux, count, 8, int(fb.stream_ids[s]))
+        parity.assert_f32_parity(got, want, "vowel chart stream %d via pulls" % s)
+
+
+def test_pull_config5_midi_sing_streams(port):
+    """BASELINE config 5 recipe (midi-sing note lists with pitch sweeps and vibrato) through pulls of 2048."""
+    sr, secs = 22050, 2.0
+    fb = workloads.midi_sing(4, seconds=secs, sample_rate=sr, first_stream=40)
+    count = int(secs * sr)
+    for s in range(fb.num_streams):
+        fr, m, f, nul, ux = fb.stream(s)
+        want = port.render(sr, fr, m, f, nul, ux, max_samples=count, noise=("philox", 5, int(fb.stream_ids[s])))
+        got = _pull_stream(sr, fr, m, f, nul, ux, len(want), 5, int(fb.stream_ids[s]), pull=2048)
+        parity.assert_f32_parity(got, want, "midi stream %d via pulls" % s)
+
+
+def test_pull_whole_sample_pitch_periods(port):
+    """150 Hz and 225 Hz at 22 050 Hz (periods of exactly 147 and 98 samples): the wrap instant hangs on the last bit of the
+    FP64 phase sum, and the run decomposition must reproduce it."""
+    sr, count = 22050, 22050
+    fr = np.zeros((2, 47))
+    for j, hz in enumerate((150.0, 225.0)):
+        fr[j, workloads.P["voicePitch"]] = fr[j, workloads.P["endVoicePitch"]] = hz
+        fr[j, workloads.P["voiceAmplitude"]] = 1.0
+        fr[j, workloads.P["preFormantGain"]] = 1.0
+        fr[j, workloads.P["outputGain"]] = 1.0
+        workloads.set_frame(fr[j], "a")
+    m = np.array([11025, 11025], dtype=np.uint32)
+    f = np.array([441, 441], dtype=np.uint32)
+    nul = np.zeros(2, dtype=np.uint8)
+    ux = np.array([0, 1], dtype=np.int32)
+    want = port.render(sr, fr, m, f, nul, ux, max_samples=count, noise=("philox", 2, 3))
+    got = _pull_stream(sr, fr, m, f, nul, ux, len(want), 2, 3)
+    parity.assert_f32_parity(got, want, "whole-sample periods via pulls")
