@@ -150,3 +150,19 @@ def test_pull_latency_smoke():
         assert c.size == 8192
     p.close()
     assert np.median(t) < 0.02, t   # 8192 samples are 372 ms of audio
+
+
+def test_pull_nvda_speak_cancel_speak(port):
+    """The NVDA driver's speak / cancel / speak with its audio thread pulling 8192 samples at a time (tests/nvda_flow.py,
+    reference nvdaAddon/synthDrivers/nvSpeechPlayer/__init__.py:56-82, :168-241) on the low-latency path."""
+    from tests import nvda_flow
+
+    def oracle_player(sr):
+        p = port.player(sr)
+        p.noise_philox(scenarios.SEED, scenarios.STREAM)
+        return p
+    want, wcounts, widx = nvda_flow.run(oracle_player)
+    got, counts, idx = nvda_flow.run(lambda sr: _PullAdapter(sr))
+    assert counts == wcounts
+    assert idx == widx
+    parity.assert_f32_parity(got, want, "NVDA speak / cancel / speak")

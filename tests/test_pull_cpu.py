@@ -211,3 +211,19 @@ def test_pull_whole_sample_pitch_periods(port):
     want = port.render(sr, fr, m, f, nul, ux, max_samples=count, noise=("philox", 2, 3))
     got = _pull_stream(sr, fr, m, f, nul, ux, len(want), 2, 3)
     parity.assert_f32_parity(got, want, "whole-sample periods via pulls")
+
+
+def test_pull_nvda_speak_cancel_speak(port):
+    """The NVDA driver's speak / cancel / speak with its audio thread pulling 8192 samples at a time (tests/nvda_flow.py):
+    same samples per pull, same getLastIndex after every pull, same audio as the reference's frame manager and generator."""
+    from tests import nvda_flow
+
+    def oracle_player(sr):
+        p = port.player(sr)
+        p.noise_philox(scenarios.SEED, scenarios.STREAM)
+        return p
+    want, wcounts, widx = nvda_flow.run(oracle_player)
+    got, counts, idx = nvda_flow.run(_player)
+    assert counts == wcounts and len(counts) > 8
+    assert idx == widx and max(idx) == 299
+    parity.assert_f32_parity(got, want, "NVDA speak / cancel / speak")
