@@ -227,3 +227,20 @@ def test_pull_nvda_speak_cancel_speak(port):
     assert counts == wcounts and len(counts) > 8
     assert idx == widx and max(idx) == 299
     parity.assert_f32_parity(got, want, "NVDA speak / cancel / speak")
+
+
+@pytest.mark.parametrize("flow", ["leap", "midi"])
+def test_pull_live_control_flows(port, flow):
+    """The reference's live-control demos (test_leap.py: purgeQueue on every tracking frame; test_midiSing.py: notes held
+    for 10^7 ms, purges on note / controller / pitch-bend events) while the audio thread keeps pulling."""
+    from tests import nvda_flow
+    run = nvda_flow.run_leap if flow == "leap" else nvda_flow.run_midi
+
+    def oracle_player(sr):
+        p = port.player(sr)
+        p.noise_philox(scenarios.SEED, scenarios.STREAM)
+        return p
+    want, wcounts = run(oracle_player)
+    got, counts = run(_player)
+    assert counts == wcounts
+    parity.assert_f32_parity(got, want, "live control: " + flow)
