@@ -234,3 +234,50 @@ extern "C" int hostsim_pull_synthesize(void *h, uint32_t n, int16_t *out, uint32
 	}
 	return (int)total;
 }
+
+// The two renditions of the glottal-phase recurrence on a caller-supplied increment sequence (n <= 8192 ticks):
+// out[0..n) = phase after every tick.  mode 0: the plain loop, mode 1: the run decomposition.  Returns the number of
+// special ticks the serial thread visited (mode 1), n (mode 0), or -1 when mode 1 handed the pull back to the plain loop.
+extern "C" int hostsim_phase(const double *incs, uint32_t n, double pos0, int mode, double *out, double *carry) {
+	PullState st;
+	memset(&st, 0, sizeof st);
+	st.pitchPos = pos0;
+	PullCtx X;
+	memset(&X, 0, sizeof X);
+	X.n = n; X.L = pullTicksPerThread(n); X.state = &st; X.phaseMode = mode;
+	std::vector<double> inc((size_t)X.L * kPullThreads, 0.0);
+	std::vector<int64_t> runI((size_t)X.L * kPullThreads, 0);
+	std::vector<uint16_t> runMeta(n + 8, 0);
+	std::vector<PullPhaseRec> rec(kPullMaxSpecial);
+	X.inc = inc.data(); X.runI = runI.data(); X.runMeta = runMeta.data(); X.rec = rec.data();
+	for (uint32_t t = 0; t < n; ++t) inc[pullIdx(X, t)] = incs[t];
+	int visited = (int)n;
+	bool done = false;
+	if (mode == 1) {
+		uint64_t fixed = 0;
+		const bool okStart = pullRunsStart(pos0, fixed);
+		std::vector<PullRunSum> mine(kPullThreads), before(kPullThreads);
+		for (int ch = 0; ch < kPullThreads; ++ch) {
+			pullRunsClassify(X, ch, fixed, mine[ch]);
+			uint32_t t0, t1;
+			pullChunkRange(X, ch, t0, t1);
+			for (uint32_t t = t0; t < t1; ++t) fixed += (uint64_t)cyclesToFixed(incs[t]);
+		}
+		if (!okStart) mine[0].specials += kPullMaxSpecial + 1;
+		PullRunSum acc{0, 0u, 0u};
+		for (int ch = 0; ch < kPullThreads; ++ch) { before[ch] = acc; acc = pullRunCombine(acc, mine[ch]); }
+		if (acc.specials <= kPullMaxSpecial) {
+			for (int ch = 0; ch < kPullThreads; ++ch) pullRunsOffsets(X, ch, before[ch]);
+			pullRunsSerial(X, acc.specials, pos0);
+			for (int ch = 0; ch < kPullThreads; ++ch) pullRunsFinish(X, ch, before[ch].specials, pos0);
+			visited = (int)acc.specials;
+			done = true;
+		} else {
+			visited = -1;
+		}
+	}
+	if (!done) pullPhaseSerial(X);
+	for (uint32_t t = 0; t < n; ++t) out[t] = inc[pullIdx(X, t)];
+	*carry = st.pitchPos;
+	return visited;
+}

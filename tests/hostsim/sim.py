@@ -110,3 +110,16 @@ def pull_runs_stats():
     a, b = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
     lib().hostsim_pull_runs_stats(ctypes.byref(a), ctypes.byref(b))
     return a.value, b.value
+
+
+def phase(inc, pos0, mode):
+    """The glottal-phase recurrence over an increment sequence (<= 8192 ticks): mode 0 the plain FP64 loop, mode 1 the run
+    decomposition.  Returns (phase after every tick, carried phase, special ticks visited | -1 = handed back to the loop)."""
+    L = lib()
+    L.hostsim_phase.restype = ctypes.c_int
+    L.hostsim_phase.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    inc = np.ascontiguousarray(inc, dtype=np.float64)
+    out = np.empty_like(inc)
+    carry = ctypes.c_double(0)
+    visited = L.hostsim_phase(inc.ctypes.data, len(inc), float(pos0), int(mode), out.ctypes.data, ctypes.byref(carry))
+    return out, carry.value, visited

@@ -244,3 +244,48 @@ def test_pull_live_control_flows(port, flow):
     got, counts = run(_player)
     assert counts == wcounts
     parity.assert_f32_parity(got, want, "live control: " + flow)
+
+
+def _adversarial_increments(rng, n):
+    sr = float(rng.choice([16000, 22050, 44100]))
+    kind = int(rng.integers(0, 12))
+    t = np.arange(n)
+    if kind == 0: return np.full(n, rng.uniform(40, 500) / sr)
+    if kind == 1: return np.full(n, 2.0 ** -float(rng.integers(2, 12)))                       # dyadic: rounding ties everywhere
+    if kind == 2: return np.full(n, float(rng.integers(1, 400)) / float(rng.integers(401, 4000)))
+    if kind == 3: return rng.uniform(0, 0.02, n)
+    if kind == 4: return rng.uniform(0, 0.49999, n)                                            # absurd pitches
+    if kind == 5: return np.where(rng.random(n) < 0.3, 0.0, rng.uniform(40, 500) / sr)         # zeros interspersed
+    if kind == 6: return (200 + 100 * np.sin(2 * np.pi * 5.5 * t / sr)) / sr                   # deep vibrato
+    if kind == 7: return np.full(n, rng.uniform(1e-9, 1e-5))                                   # almost no pitch
+    if kind == 8: return 2.0 ** -rng.integers(2, 30, n).astype(float)                          # random dyadics
+    if kind == 9: return np.full(n, 1.0 / float(rng.integers(2, 400)))                         # whole-sample periods
+    if kind == 10: return np.abs(rng.normal(0.01, 0.01, n))
+    return np.linspace(rng.uniform(40, 400), rng.uniform(40, 400), n) / sr                     # glide
+
+
+def test_pull_phase_runs_adversarial_increments():
+    """The run decomposition against the plain FP64 recurrence on increment sequences chosen to hurt: exact dyadics (every
+    addition a rounding tie), whole-sample periods, zeros, near-Nyquist pitches, starts on and next to binade boundaries.
+    Bit for bit, carry included; and the plain loop itself against Python's float arithmetic."""
+    import math
+    rng = np.random.default_rng(11)
+    ticks = visited = 0
+    for it in range(400):
+        n = int(rng.choice([1, 7, 333, 512, 2048, 4000, 8192]))
+        inc = _adversarial_increments(rng, n)
+        pos0 = float(rng.choice([0.0, rng.random(), 1 - 2.0 ** -53, 2.0 ** -45, 0.5, 0.25 - 2.0 ** -55]))
+        a, ca, _ = sim.phase(inc, pos0, 0)
+        b, cb, v = sim.phase(inc, pos0, 1)
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)) and ca == cb, (it, n, pos0)
+        if v >= 0:
+            ticks += n
+            visited += v
+        if it % 40 == 0:
+            pos = pos0
+            for k in range(n):
+                s = pos + float(inc[k])
+                pos = s - math.trunc(s)
+                assert pos == a[k]
+            assert pos == ca
+    assert visited < 0.2 * ticks
