@@ -51,6 +51,8 @@ def parse_args():
                     help="the e2e leg pulls the audio in slices of this length into ONE pinned host buffer (a streaming "
                          "consumer): 65536 x 2 s = 5.8 GB pinned per rank instead of 28.9 GB, so 8 ranks fit the host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run oracle check of random output rows")
+    ap.add_argument("--parity-streams", type=int, default=16)
     ap.add_argument("--cpu-streams-per-core", type=int, default=16)
     ap.add_argument("--workload", default="batch", choices=["batch", "vowel", "midi", "long", "pull"],
                     help="batch: BASELINE config 3 (default, the headline); vowel: config 2, vowel-chart pairs x --voices "
@@ -228,6 +230,26 @@ def long_arm(args, rank, world, local_rank):
             dt = time.perf_counter() - t0
             cpu = {"value": len(got_cpu) / sr / dt, "unit": "audio-seconds/s", "cores": 1, "kind": "reference" if ref else "port",
                    "sample": "first 30 s of the same stream incl. queueing its frames, one core"}
+        par = None
+        if not args.no_parity:
+            # the WHOLE stream on the oracle with the same Philox noise (one core, ~25 s for an hour at 44.1 kHz), compared over
+            # its final 10 s: drift of any scanned quantity over all chunks would show there
+            from oracle import oracle
+            from tests import parity as parity_mod
+            if not oracle.have_port():
+                oracle.build(quiet=True)
+            t0 = time.perf_counter()
+            want = oracle.PortLib().render(sr, fr, m, f, nul, ux, max_samples=n, noise=("philox", args.seed, 4_000_000 + rank))
+            t_or = time.perf_counter() - t0
+            tail = min(n, 10 * sr)
+            got_tail = d_out[n - tail:n].cpu().numpy()
+            w1_, ex_, snr_, mx_ = parity_mod.metrics(got_tail, want[n - tail:n])
+            w1_all = parity_mod.metrics(d_out[:n].cpu().numpy(), want)[0] if n <= 200_000_000 else None
+            lib.speechPlayer_debugLongSerialFallbacks.restype = __import__("ctypes").c_ulonglong
+            par = {"samples_checked": int(tail), "of": "the final 10 s of the stream", "within_1lsb": w1_, "snr_db": snr_,
+                   "max_abs_diff": mx_, "within_1lsb_whole_stream": w1_all, "oracle_seconds": round(t_or, 1),
+                   "oracle": "oracle/klatt_oracle.c (port) with the same Philox noise",
+                   "serial_phase_fallbacks": int(lib.speechPlayer_debugLongSerialFallbacks())}
         achieved = n * flops_per_sample / (ms * 1e-3) / 1e12
         line = {"metric": "audio-seconds synthesized/sec (single long stream)", "value": world * secs / (ms * 1e-3),
                 "unit": "audio-seconds/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -238,7 +260,7 @@ def long_arm(args, rank, world, local_rank):
                 "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                              "traffic": None, "kernel": "klatt_long_* (27 launches)",
                              "note": "algorithmic flops of the SERIAL path; the scan formulation executes about 3x of them"},
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu, "parity": par,
                 "e2e": {"value": world * secs / e2e_s, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(fr.nbytes + m.nbytes + f.nbytes + nul.nbytes),
                         "d2h_bytes_per_step": int(n * 2), "matches_device_path": same},
                 "gpu_launches": int(launches) * args.steps, "clocks": clocks}
@@ -527,6 +549,27 @@ def main():
                "kernel_launches_total": int(e2e_launches)}
         eb.close()
 
+    # ---- parity of what was just timed (outside the timed region): random rows of d_out against the oracle, whole length ----
+    par = None
+    if rank == 0 and not args.no_parity and args.workload == "batch":
+        from oracle import oracle
+        from tests import parity as parity_mod
+        if not oracle.have_port():
+            oracle.build(quiet=True)
+        port = oracle.PortLib()
+        rows = np.random.default_rng(args.seed).choice(S, size=min(args.parity_streams, S), replace=False)
+        w1s, snrs, exacts, worst = [], [], [], 0.0
+        for s_ in rows:
+            got = d_out[int(s_), :count].cpu().numpy()
+            fr_, m_, f_, nul_, ux_ = fb.stream(int(s_))
+            want = port.render(sr, fr_, m_, f_, nul_, ux_, max_samples=count, noise=("philox", args.seed, int(fb.stream_ids[int(s_)])))
+            w1_, ex_, snr_, mx_ = parity_mod.metrics(got, want)
+            assert len(want) == count
+            w1s.append(w1_); snrs.append(snr_); exacts.append(ex_); worst = max(worst, mx_)
+        par = {"streams": int(len(rows)), "samples_per_stream": count, "within_1lsb_min": min(w1s), "snr_db_min": min(snrs),
+               "exact_min": min(exacts), "max_abs_diff": worst, "oracle": "oracle/klatt_oracle.c (port, pinned to the compiled reference)",
+               "bar": "fp32: <=1 LSB on >= 99.9 % and >= 60 dB; fp64: exact on >= 99.99 %"}
+
     if rank == 0:
         peaks = measured_peaks()
         achieved_tf = rendered * flops_per_sample / (kernel_ms * 1e-3) / 1e12  # dominant kernel alone
@@ -568,6 +611,7 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_sample": 2.0},
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "ns_per_sample_core")} if cpu else None),
+            "parity": par,
             "e2e": e2e,
             "gpu_launches": int(launches1 - launches0),
             "clocks": clocks,

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <chrono>
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,7 @@
 #include "glibc_rand.h"
 #include "klatt_common.h"
 #include "pull_manager.h"
+#include "klatt_long_phase.cuh"
 
 namespace klatt {
 cudaError_t launchKlattF64(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
@@ -71,7 +73,8 @@ cudaError_t launchKlattPullInit(PullState *state, cudaStream_t stream);  // klat
 cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut, cudaStream_t stream);
 cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream);
 cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
-                                  uint64_t *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
+                                  uint64_t *startPhase, PhaseChunk *chunks, double *startP, uint32_t *fail, bool serialPhase,
+                                  float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
                                   float2 *startState, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream);
 }  // namespace klatt
 
@@ -490,6 +493,7 @@ struct Player {
 	uint64_t generated = 0;   // samples generated so far (== draws/2)
 	int lastIndex = -1;
 	HostPipe pipe;
+	std::vector<int16_t> hostScratch;  // rows of the last synthesize call before the written prefixes are handed out
 	// SPEECHPLAYER_PRECISION_STREAM: host frame manager, carried device state, staging for one launch
 	PullManager *pull = nullptr;
 	PullState *dPull = nullptr;
@@ -682,11 +686,10 @@ speechPlayer_handle_t speechPlayer_initializeEx(int sampleRate, int precision, i
 }
 
 speechPlayer_handle_t speechPlayer_initialize(int sampleRate) {
-	uint64_t sid;
-	{
-		std::lock_guard<std::mutex> lk(g_tableMu);
-		sid = g_players.size();
-	}
+	// Philox stream ids of the five-symbol API come from a process-wide counter, not from the handle table: slots are reused
+	// after terminate, and two live players must never share (seed, streamId)
+	static std::atomic<uint64_t> nextStreamId{0};
+	const uint64_t sid = nextStreamId.fetch_add(1);
 	return speechPlayer_initializeEx(sampleRate, envPrecision(), envNoise(), envSeed(), sid);
 }
 
@@ -877,13 +880,18 @@ long long speechPlayer_synthesizeBatch(speechPlayer_handle_t *handles, unsigned 
 	std::vector<uint32_t> written(numHandles);
 	std::vector<StreamResult> results(numHandles);
 	NoiseConfig nc{lead->noiseMode, lead->seed};
+	// The reference's generate() returns the count and leaves sampleBuf[count..] untouched (src/speechWaveGenerator.cpp:210),
+	// so the rows land in a scratch buffer first and only the written prefix of each row is handed to the caller.
+	std::vector<int16_t> &scratch = lead->hostScratch;
+	scratch.resize((size_t)numHandles * sampleCount);
 	long long total = renderToHost(lead->pipe, lead->precision, lead->dDesc.as<StreamDesc>(), numHandles, lead->sampleRate,
-	                               sampleCount, reinterpret_cast<int16_t *>(sampleBuf), written.data(), results.data(), nc,
-	                               nullptr);
+	                               sampleCount, scratch.data(), written.data(), results.data(), nc, nullptr);
 	if (total < 0) return -1;
 	for (unsigned i = 0; i < numHandles; ++i) {
 		ps[i]->absorb(results[i], written[i]);
 		if (samplesWritten) samplesWritten[i] = written[i];
+		memcpy(reinterpret_cast<int16_t *>(sampleBuf) + (size_t)i * sampleCount, scratch.data() + (size_t)i * sampleCount,
+		       sizeof(int16_t) * (size_t)written[i]);
 	}
 	if (lead->noiseMode == kNoiseGlibc && numHandles == 1) {
 		// the reference consumes exactly two rand() calls per generated sample: rewind to that point
@@ -1036,8 +1044,8 @@ speechPlayer_batch_t *speechPlayer_batchCreate(int sampleRate, unsigned int numS
                                                uint64_t seed, const uint64_t *streamIds) {
 	g_lastError.clear();
 	if (sampleRate <= 0 || numStreams == 0) { fail("bad sampleRate / numStreams"); return nullptr; }
-	if (precision != kPrecisionF64 && precision != kPrecisionF32 && precision != kPrecisionStream) {
-		fail("unknown precision");
+	if (precision != kPrecisionF64 && precision != kPrecisionF32) {
+		fail(precision == kPrecisionStream ? "SPEECHPLAYER_PRECISION_STREAM is a per-handle mode (speechPlayer_initializeEx)" : "unknown precision");
 		return nullptr;
 	}
 	if (noiseMode != kNoisePhilox && noiseMode != kNoiseReplay) { fail("batch noise mode must be PHILOX or REPLAY"); return nullptr; }
@@ -1179,7 +1187,11 @@ int speechPlayer_batchSetNoiseReplayDevice(speechPlayer_batch_t *b, const void *
 	DeviceGuard g(b->device);
 	b->dReplay = static_cast<const int32_t *>(dDraws);
 	b->drawsPerStream = drawsPerStream;
-	return b->rebuildDescs(nullptr, b->planned());
+	// the entry has no stream argument: the descriptor rewrite runs on the legacy default stream and is complete on return,
+	// so a synthesize on any (also non-blocking) stream afterwards sees whole descriptors
+	if (b->rebuildDescs(nullptr, b->planned()) != 0) return -1;
+	CU(cudaStreamSynchronize(nullptr));
+	return 0;
 }
 
 int speechPlayer_batchSynthesizeDevice(speechPlayer_batch_t *b, unsigned int sampleCount, void *dOut, size_t rowStride,
@@ -1237,6 +1249,10 @@ int speechPlayer_batchGetLaunchStats(speechPlayer_batch_t *b, unsigned long long
 // ------------------------------------------------------------------------------------------------
 // C-ABI: long-utterance path (klatt_long.cu)
 // ------------------------------------------------------------------------------------------------
+static std::atomic<unsigned long long> g_longSerialFallbacks{0};
+// how many speechPlayer_synthesizeLong calls of this process had to take the serial phase fallback (tests, bench)
+extern "C" unsigned long long speechPlayer_debugLongSerialFallbacks(void) { return g_longSerialFallbacks.load(); }
+
 extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPlayer_frame_t *frames,
                                                  const unsigned int *minFrameDuration, const unsigned int *fadeDuration,
                                                  const unsigned char *isNull, unsigned int numFrames, uint64_t seed,
@@ -1303,10 +1319,11 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 		const uint64_t numChunks = (ticks + chunkTicks - 1) / chunkTicks;
 		if (numChunks > 0x7fffffffull) return fail("stream too long for one call");
 		const size_t pad = ticks + 64;
-		DevBuf sig, maps, st, ph, pcm;
-		cleanup.bufs.insert(cleanup.bufs.end(), {&sig, &maps, &st, &ph, &pcm});
+		DevBuf sig, maps, st, ph, pcm, phChunks, phStart, phFail;
+		cleanup.bufs.insert(cleanup.bufs.end(), {&sig, &maps, &st, &ph, &pcm, &phChunks, &phStart, &phFail});
 		if (!sig.reserve(5 * pad * sizeof(float)) || !maps.reserve(numChunks * 6 * sizeof(Affine)) ||
-		    !st.reserve(numChunks * 6 * sizeof(float2)) || !ph.reserve(numChunks * 2 * sizeof(double)))
+		    !st.reserve(numChunks * 6 * sizeof(float2)) || !ph.reserve(numChunks * 2 * sizeof(double)) ||
+		    !phChunks.reserve(numChunks * sizeof(PhaseChunk)) || !phStart.reserve(numChunks * sizeof(double)) || !phFail.reserve(16))
 			return -1;
 		int16_t *dPcm = reinterpret_cast<int16_t *>(out);
 		if (!outOnDevice) {
@@ -1316,9 +1333,24 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 		float *f = sig.as<float>();
 		// the stream is rendered up to `ticks`: truncate the timeline by telling the kernels the shorter total
 		if (ticks < total) CU(cudaMemcpyAsync(L.start + n, &ticks, 8, cudaMemcpyHostToDevice, stream));
-		CU(launchKlattLongRender(L, ticks, chunkTicks, ph.as<uint64_t>(), ph.as<uint64_t>() + numChunks, f, f + pad, f + 2 * pad, f + 3 * pad,
-		                         f + 4 * pad, maps.as<Affine>(), st.as<float2>(), dPcm, &launches, stream));
-		CU(cudaEventRecord(cleanup.e1, stream));
+		// The glottal phase is the reference's FP64 recurrence, parallel in time by speculation + verification
+		// (klatt_long_phase.cuh).  A render whose check failed -- or NVSP_LONG_PHASE=serial -- is repeated with the plain
+		// recurrence on one thread: slow, exact by definition.
+		static const bool forceSerial = getenv("NVSP_LONG_PHASE") && !strcmp(getenv("NVSP_LONG_PHASE"), "serial");
+		bool serialPhase = forceSerial;
+		for (;;) {
+			CU(launchKlattLongRender(L, ticks, chunkTicks, ph.as<uint64_t>(), ph.as<uint64_t>() + numChunks, phChunks.as<PhaseChunk>(),
+			                         phStart.as<double>(), phFail.as<uint32_t>(), serialPhase, f, f + pad, f + 2 * pad, f + 3 * pad,
+			                         f + 4 * pad, maps.as<Affine>(), st.as<float2>(), dPcm, &launches, stream));
+			CU(cudaEventRecord(cleanup.e1, stream));
+			uint32_t failed = 0;
+			CU(cudaMemcpyAsync(&failed, phFail.p, sizeof failed, cudaMemcpyDeviceToHost, stream));
+			CU(cudaStreamSynchronize(stream));
+			if (!failed || serialPhase) break;
+			if (getenv("NVSP_VERBOSE")) fprintf(stderr, "[nvspeechplayer_b200] long path: speculative phase not verified, serial fallback\n");
+			serialPhase = true;
+		}
+		g_longSerialFallbacks += serialPhase && !forceSerial ? 1 : 0;
 		if (!outOnDevice) CU(cudaMemcpyAsync(out, dPcm, ticks * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
 		CU(cudaStreamSynchronize(stream));
 		if (renderMs) {

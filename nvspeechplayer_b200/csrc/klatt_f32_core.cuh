@@ -423,6 +423,52 @@ KLATT_HD double fracRef(double x) {
 #endif
 }
 
+// n successive FP64 additions  p = p + inc  (round to nearest even), bit for bit, in O(binades crossed) steps: the reference's
+// hold glide `curFrame.voicePitch += oldFrameRequest->voicePitchInc` once per tick (src/frame.cpp:77), needed in the middle of
+// a hold by the time-parallel paths.  While p stays inside one binade every value it takes lies on that binade's grid (ulp
+// u), so RN(p + inc) = p + RN_u(inc): a constant step (a tie inc/u = k + 1/2 rounds to even once and is stationary from the
+// second addition on).  Two real additions give the stationary step, whole-grid integer arithmetic covers the rest of the
+// binade (stopping one step short of either edge, where the ulp changes), and the crossing is done with real additions again.
+KLATT_HD double glideExact(double p, double inc, uint64_t n) {
+	if (n == 0) return p;
+	if (!(inc == inc) || !(p == p) || inc == 0.0) return p + inc;  // NaN propagates; +0 is the identity (the sign of zero never matters here)
+	while (n > 0) {
+		// three real additions: p1 may still come from the neighbouring binade's grid; p2 = RN(p1 + inc) is then a value this
+		// binade's rounding produced (even after a tie), so p2 -> p3 is the stationary step
+		const double p1 = p + inc;
+		if (--n == 0) return p1;
+		const double p2 = p1 + inc;
+		if (--n == 0) return p2;
+		const double p3 = p2 + inc;
+		--n;
+		p = p3;
+		if (n == 0) return p3;
+		const double step = p3 - p2;  // exact (neighbouring values)
+		if (step == 0.0) return p3;   // inc is below half an ulp from here on: every further addition is the identity
+		const double a1 = p1 < 0 ? -p1 : p1, a2 = p2 < 0 ? -p2 : p2, a3 = p3 < 0 ? -p3 : p3;
+		if (!(a3 >= 1e-290 && a3 <= 1e290) || !(a2 >= 1e-290) || !(a1 >= 1e-290)) continue;  // zero, denormal, huge, inf: plain additions
+		int e1, e2, e3;
+		(void)frexp(a1, &e1);
+		(void)frexp(a2, &e2);
+		const double f3 = frexp(a3, &e3);  // a3 = f3 * 2^e3, f3 in [0.5, 1)
+		if (e1 != e3 || e2 != e3 || (p1 < 0) != (p3 < 0) || (p2 < 0) != (p3 < 0)) continue;  // straddles a binade edge (or zero)
+		// grid units: P = a3 / u in [2^52, 2^53), S = signed step of |p| per addition
+		const int64_t P = (int64_t)ldexp(f3, 53);
+		const double sMag = ldexp(step, 53 - e3);  // exact integer: step is a multiple of u
+		const int64_t S = (p3 < 0) ? -(int64_t)sMag : (int64_t)sMag;
+		if (S == 0) continue;
+		const int64_t lo = (int64_t)1 << 52, hi = (int64_t)1 << 53;
+		int64_t room = S > 0 ? (hi - P) / S : (P - lo) / (-S);
+		room -= 1;  // stay one step clear of the edge: the addition that reaches it is a real one
+		if (room <= 0) continue;
+		const uint64_t k = (uint64_t)room < n ? (uint64_t)room : n;
+		const double mag = ldexp((double)(P + (int64_t)k * S), e3 - 53);
+		p = (p3 < 0) ? -mag : mag;
+		n -= k;
+	}
+	return p;
+}
+
 // parallel side of one generated sample (reference src/speechWaveGenerator.cpp:205-206, :170-180): wF is the
 // frication noise word (the reference's rand() value is word>>1; the top 23 bits are used).  The six sections run as
 // three pairs; the weighted sum is accumulated per half and folded at the end.

@@ -41,7 +41,11 @@ struct NullOut {
 // give two schedulers of an SM nothing but the (lighter, latency-bound) cascade warps and the other two nothing but the
 // (heavier) parallel warps; flipping the assignment on a hash of the block index mixes both kinds on every scheduler.
 __device__ __forceinline__ bool cascadeRole(uint32_t warp) {
+#ifdef KLATT_NO_ROLE_FLIP  // A/B: cascade warps on schedulers 0,1 and parallel warps on 2,3 of every SM (one loop per instruction cache)
+	const uint32_t flip = 0;
+#else
 	const uint32_t flip = (blockIdx.x * 0x9E3779B9u) >> 31;
+#endif
 	return ((warp >> 1) ^ flip) == 0;
 }
 

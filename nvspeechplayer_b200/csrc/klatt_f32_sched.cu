@@ -7,6 +7,7 @@
 // line.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "klatt_common.h"
 #include "klatt_f32_core.cuh"
 #include "out_writer.cuh"
@@ -128,7 +129,9 @@ __device__ __forceinline__ void schedPush(SchedCtl *ctl, uint32_t *ring, uint32_
 // kClassExit when the call is complete; s = the lane's stream, or kRingEmpty for a lane that got none.
 // Tickets are only taken from a ring that shows a backlog, so consumers run ahead of the producers by at most the
 // workers that raced for the same entries; those wait for the next pushes.
-__device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, uint32_t ringCap, uint32_t &s) {
+// pref: kClassHold / kClassGen = this SM's workers take that class whenever it has a backlog (SM roles: every warp of an SM
+// then runs the same two loops, which is what its instruction caches hold); kClassExit = no preference.
+__device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, uint32_t ringCap, uint32_t &s, uint32_t pref) {
 	const unsigned lane = threadIdx.x & 31u;
 	const uint32_t mask = ringCap - 1u;
 	for (;;) {
@@ -141,7 +144,9 @@ __device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, ui
 				const int32_t b1 = (int32_t)(ldVolatile(&ctl->tail1) - ldVolatile(&ctl->head1));
 				if (b0 > 0 || b1 > 0) {
 					cls = (2 * b1 >= b0) ? kClassGen : kClassHold;
+					if (pref != kClassExit) cls = pref;
 					if ((cls == kClassGen ? b1 : b0) < 32 && (cls == kClassGen ? b0 : b1) >= 32) cls ^= 1u;  // a full warp beats the weights
+					if ((cls == kClassGen ? b1 : b0) <= 0) cls ^= 1u;
 					base = atomicAdd(ctl->head(cls), 32u);
 					break;
 				}
@@ -223,7 +228,8 @@ klatt_sched_seed_kernel(const StreamDesc *__restrict__ descs, uint32_t numStream
 __global__ void __launch_bounds__(kPairBlock, KLATT_SCHED_MINB)
 klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                        uint32_t holdTicks, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,
-                       int16_t *__restrict__ scratchRow, NoiseConfig noise, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap) {
+                       int16_t *__restrict__ scratchRow, NoiseConfig noise, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap,
+                       uint32_t holdSms) {
 	__shared__ uint4 xbuf[2][2 * kGroupTicks * 32];
 	__shared__ uint32_t work[2][34];  // per worker: 32 stream indices, class
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, pair = warp & 1u;
@@ -233,10 +239,17 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams
 	long long tClaim = 0, tHold = 0, tGen = 0, tPush = 0, nHold = 0, nGen = 0, nLanes = 0;
 	long long t0 = clock64();
 #endif
+	uint32_t pref = kClassExit;
+	if (holdSms) {  // SM roles: the first holdSms SMs (spread evenly over the SM ids) prefer hold chunks, the others general chunks
+		uint32_t smid, nsm;
+		asm("mov.u32 %0, %%smid;" : "=r"(smid));
+		asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+		pref = ((smid + 1) * holdSms / nsm != smid * holdSms / nsm) ? kClassHold : kClassGen;
+	}
 	for (;;) {
 		if (cascade) {
 			uint32_t s = kRingEmpty;
-			const uint32_t cls = schedClaim(ctl, ring, ringCap, s);
+			const uint32_t cls = schedClaim(ctl, ring, ringCap, s, pref);
 			if (s == kRingEmpty) s = numStreams;  // idle lanes run the dummy stream
 			__threadfence();
 			work[pair][lane] = s;
@@ -318,8 +331,9 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
 	const uint32_t batches = (numStreams + 31) / 32;
 	// paired workers: two warps per batch, two batches per block
 	const uint32_t blocksWanted = (batches + 1) / 2, grid = blocksWanted < numBlocks ? blocksWanted : numBlocks;
+	static const uint32_t holdSms = getenv("NVSP_SCHED_HOLD_SMS") ? (uint32_t)atoi(getenv("NVSP_SCHED_HOLD_SMS")) : 0u;
 	klatt_f32_sched_kernel<<<grid, kPairBlock, 0, stream>>>(descs, numStreams, sampleRate, sampleCount, holdTicks, genTicks, out,
-	                                                         rowStride, scratchRow, noise, ctl, ring, ringCap);
+	                                                         rowStride, scratchRow, noise, ctl, ring, ringCap, holdSms);
 	// the watchdog's verdict travels to a pinned host word; the engine reads it at its next synchronisation point
 	if (hostFault && (e = cudaMemcpyAsync(hostFault, &ctl->fault, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
 	if ((e = launchKlattFinalize(descs, numStreams, samplesWritten, results, stream)) != cudaSuccess) return e;

@@ -7,10 +7,14 @@
 //                   from the tick index.  Interpolated parameters are a function of that position (src/frame.cpp:49-52),
 //                   the hold-phase pitch glide is an arithmetic progression (src/frame.cpp:77).
 //   vibrato phase   64-bit fixed point and piecewise-linear increments: an exact arithmetic series per request.
-//   glottal phase   needs the sum of all earlier per-tick increments (src/speechWaveGenerator.cpp:55,74), which has no
-//                   closed form under vibrato: every chunk sums its own increments (FP64 arithmetic per tick, converted to
-//                   2^-64-cycle fixed point, so the sums are exact and associative: klatt_long_phase_kernel) and an
-//                   exclusive scan over chunks (warp shuffles) gives the phase each chunk starts from.
+//   glottal phase   the reference's own FP64 recurrence pos = fmod(pos + quot, 1) (src/speechWaveGenerator.cpp:55,74), bit
+//                   for bit and parallel in time (klatt_long_phase.cuh): an exact 2^-64 fixed-point prefix sum of the
+//                   increments locates an anchor per chunk, every chunk runs the plain recurrence speculatively from its
+//                   anchor (two runs, one grid step apart), the chain of roundings is translation-equivariant on the 2^-53
+//                   grid so a scan of small integer maps turns the guesses into the true start values, and the source pass
+//                   re-runs the plain recurrence from those and CHECKS that every run ends on the next one's start (a miss,
+//                   or a stretch of zero / negative pitch without anchors, takes the serial fallback).  The hold glide of
+//                   the pitch is the reference's repeated addition (src/frame.cpp:77), seeked in closed form (glideExact).
 //   noise           Philox is random access; the 0.75-pole colouring filter (src/speechWaveGenerator.cpp:40) forgets its
 //                   past within 64 ticks (0.75^64 = 1e-8), so a chunk warms it up on the 64 ticks before its first one.
 //   resonators      each two-pole section is LINEAR in its state for a given input: over a chunk,
@@ -29,6 +33,7 @@
 #include <cuda_runtime.h>
 #include "klatt_common.h"
 #include "klatt_f32_core.cuh"
+#include "klatt_long_phase.cuh"
 
 namespace klatt {
 
@@ -239,7 +244,7 @@ __global__ void klatt_long_timeline_kernel(LongStream L) {
 		L.pitchOld[j] = pOld; L.pitchNew[j] = pNew; L.pitchInc[j] = inc;
 		const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
 		const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
-		pitchCur = landing + (double)(occ - F - 2) * inc;  // hold ticks F+2 .. occ-1 (src/frame.cpp:77)
+		pitchCur = glideExact(landing, inc, occ - F - 2);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
 		L.vibPosStart[j] = vibPos;
 		const FadePlanF32 &p = L.plans[j];
 		uint64_t s = (uint64_t)vPrev + (F - 1) * (uint64_t)p.vibInc0 + (uint64_t)p.vibIncStep * ((F - 1) * F / 2) +
@@ -262,6 +267,8 @@ struct SourceWalk {
 	DirWalk vpo, vta, goq, va, aa, fa, pfg;
 	uint64_t vibPos;
 	uint32_t loaded;
+	double pPop, pOld, pNew, pInc;  // pitch of the request in force: stale pop-tick value, fade end points, hold glide
+	double pitchHold;               // cur.voicePitch while holding, accumulated like the reference does (src/frame.cpp:77)
 	__device__ void loadReq(const LongStream &L, bool full) {
 		vw.load(L, cur.j);
 		vpo.load(L, cur.j, dVibratoPitchOffset);
@@ -270,20 +277,35 @@ struct SourceWalk {
 			va.load(L, cur.j, dVoiceAmplitude); aa.load(L, cur.j, dAspirationAmplitude);
 			fa.load(L, cur.j, dFricationAmplitude); pfg.load(L, cur.j, dPreFormantGain);
 		}
+		pPop = L.pitchPop[cur.j]; pOld = L.pitchOld[cur.j]; pNew = L.pitchNew[cur.j]; pInc = L.pitchInc[cur.j];
 		loaded = cur.j;
 	}
+	__device__ __forceinline__ double landing() const { return (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0); }
 	__device__ void seek(const LongStream &L, uint64_t t, bool full) {
 		cur.seek(L, t);
+		pitchHold = 0.0;
+		if (cur.j >= L.nReq) { loaded = cur.j; return; }
 		loadReq(L, full);
 		vibPos = L.vibPosStart[cur.j] + vw.before(cur.c, cur.F);
+		// in the middle of a hold: the value the previous tick used, (c-1) - F - 1 additions after the landing
+		if (cur.c >= cur.F + 2) pitchHold = glideExact(landing(), pInc, (uint64_t)(cur.c - cur.F - 2));
 	}
-	// phase increment of this tick, 2^-64 cycles (FP64 arithmetic, exact integer from there on)
-	__device__ __forceinline__ uint64_t phaseInc(const LongStream &L, double srInv) {
-		vibPos += (uint64_t)vw.inc(cur.c, cur.F);
+	// The increment of the glottal phase on this tick, exactly the double the serial kernel adds (klatt_f32_core.cuh OscChain:
+	// vibrato sine in FP32, pitch * (1 + vibrato) and the correctly rounded division by the sample rate in FP64; reference
+	// src/speechWaveGenerator.cpp:73-74).  cur.voicePitch: stale on the pop tick, old+(new-old)*ratio in the fade
+	// (src/frame.cpp:49-52), the landing value on the landing and swap ticks, then += inc per tick (:77).
+	__device__ __forceinline__ double quotOfTick(double srD, double srInv) {
+		const uint32_t c = cur.c, F = cur.F;
+		vibPos += (uint64_t)vw.inc(c, F);
 		float vph = (float)(int32_t)(uint32_t)(vibPos >> 32) * 2.3283064365386963e-10f;
-		float vib = (sinTurns(vph) * 0.06f) * vpo.at(cur.c, cur.F);
-		double base = pitchAt(L, cur.j, cur.c, cur.F) * srInv;
-		return (uint64_t)cyclesToFixed(fma(base, (double)vib, base));
+		float vib = (sinTurns(vph) * 0.06f) * vpo.at(c, F);
+		double pitch;
+		if (c == 0) pitch = pPop;
+		else if (c < F) pitch = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * ((double)c / (double)F));
+		else if (c <= F + 1) { pitch = landing(); pitchHold = pitch; }
+		else { pitchHold += pInc; pitch = pitchHold; }
+		const double m = pitch * ((double)vib + 1.0);
+		return divideBySampleRate(m, srD, srInv);
 	}
 	__device__ __forceinline__ void next(const LongStream &L, bool full) {
 		cur.next(L);
@@ -291,7 +313,23 @@ struct SourceWalk {
 	}
 };
 
-// pass 1: the phase every chunk advances by (fraction of a cycle)
+// SourceWalk as the increment source of phaseSpeculateChunk
+struct PhaseSrc {
+	SourceWalk w;
+	const LongStream &L;
+	double srD, srInv;
+	__device__ PhaseSrc(const LongStream &L_, uint64_t t) : L(L_) {
+		srD = (double)L.sampleRate; srInv = 1.0 / srD;
+		w.seek(L, t, false);
+	}
+	__device__ __forceinline__ void tick(double &quot, uint64_t &fixedInc) {
+		quot = w.quotOfTick(srD, srInv);
+		fixedInc = (uint64_t)cyclesToFixed(quot);
+		w.next(L, false);
+	}
+};
+
+// pass 1: the phase every chunk advances by (fraction of a cycle, 2^-64 fixed point: exact sums, used to LOCATE the anchors)
 __global__ void __launch_bounds__(128)
 klatt_long_phase_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, uint64_t *__restrict__ advance) {
 	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,13 +337,12 @@ klatt_long_phase_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, u
 	const uint64_t total = L.start[L.nReq];
 	const uint64_t t0 = (uint64_t)ch * chunkTicks;
 	const uint64_t t1 = (t0 + chunkTicks < total) ? t0 + chunkTicks : total;
-	const double srInv = 1.0 / (double)L.sampleRate;
-	SourceWalk w;
-	w.seek(L, t0, false);
-	uint64_t pos = 0;
+	PhaseSrc src(L, t0);
+	uint64_t pos = 0, fi;
+	double quot;
 	for (uint64_t t = t0; t < t1; ++t) {
-		pos += w.phaseInc(L, srInv);
-		w.next(L, false);
+		src.tick(quot, fi);
+		pos += fi;
 	}
 	advance[ch] = pos;
 }
@@ -346,17 +383,102 @@ klatt_long_phase_scan_kernel(const uint64_t *__restrict__ advance, uint32_t numC
 	}
 }
 
-// pass 2: the two excitation signals of every tick: cascade input ci (:204, :148) and parallel input pin (:206, :171)
+// speculative pass: anchors, the two runs per chunk, the offset map of every chunk (klatt_long_phase.cuh)
 __global__ void __launch_bounds__(128)
-klatt_long_source_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, const uint64_t *__restrict__ startPhase,
-                         float *__restrict__ ci, float *__restrict__ pin) {
+klatt_long_spec_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, const uint64_t *__restrict__ startPhase,
+                       PhaseChunk *__restrict__ chunks, uint32_t *__restrict__ fail) {
 	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
 	if (ch >= numChunks) return;
 	const uint64_t total = L.start[L.nReq];
-	const uint64_t t0 = (uint64_t)ch * chunkTicks;
-	const uint64_t t1 = (t0 + chunkTicks < total) ? t0 + chunkTicks : total;
-	const double srInv = 1.0 / (double)L.sampleRate;
-	// warm the two noise colouring filters up on the ticks before the chunk
+	PhaseSrc src(L, (uint64_t)ch * chunkTicks);
+	PhaseChunk pc;
+	// a run may extend over up to 15 anchorless chunks (zero pitch, silence); beyond that the call takes the fallback
+	if (!phaseSpeculateChunk(src, ch, chunkTicks, total, startPhase[ch], 16ull * chunkTicks, pc)) atomicOr(fail, 1u);
+	chunks[ch] = pc;
+}
+
+// exclusive scan of the offset maps in chunk order: startP[c] = the TRUE phase entering tick chunks[c].anchor
+__global__ void __launch_bounds__(1024)
+klatt_long_phase_map_scan_kernel(const PhaseChunk *__restrict__ chunks, uint32_t numChunks, double *__restrict__ startP) {
+	__shared__ PhaseMap warpTotal[32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t per = (numChunks + 1023) / 1024;
+	const uint32_t c0 = (uint32_t)tid * per < numChunks ? (uint32_t)tid * per : numChunks;
+	const uint32_t c1 = c0 + per < numChunks ? c0 + per : numChunks;
+	PhaseMap run = phaseMapIdentity();
+	for (uint32_t c = c0; c < c1; ++c) run = phaseMapCompose(chunks[c].map, run);
+	auto shfl = [](const PhaseMap &m, int delta) {
+		PhaseMap r;
+#pragma unroll
+		for (int i = 0; i < kPhaseRuns; ++i) r.a[i] = __shfl_up_sync(0xffffffffu, m.a[i], delta);
+		return r;
+	};
+	PhaseMap inc = run;
+#pragma unroll
+	for (int delta = 1; delta < 32; delta <<= 1) {
+		PhaseMap up = shfl(inc, delta);
+		if (lane >= delta) inc = phaseMapCompose(inc, up);
+	}
+	if (lane == 31) warpTotal[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		PhaseMap w = warpTotal[lane];
+#pragma unroll
+		for (int delta = 1; delta < 32; delta <<= 1) {
+			PhaseMap up = shfl(w, delta);
+			if (lane >= delta) w = phaseMapCompose(w, up);
+		}
+		warpTotal[lane] = w;
+	}
+	__syncthreads();
+	PhaseMap prev = shfl(inc, 1);
+	PhaseMap pre = lane == 0 ? phaseMapIdentity() : prev;
+	if (warp > 0) pre = phaseMapCompose(pre, warpTotal[warp - 1]);
+	// the stream starts at offset 0 of chunk 0's anchor (phase 0 exactly): the offset at chunk c's anchor is pre(0)
+	for (uint32_t c = c0; c < c1; ++c) {
+		const PhaseChunk pc = chunks[c];
+		startP[c] = pc.anchor == kNoAnchor ? 0.0 : phaseFromOffset(pc.s0, phaseMapApply(pre, 0));
+		pre = phaseMapCompose(pc.map, pre);
+	}
+}
+
+// serial fallback: ONE thread runs the plain recurrence over the whole stream and hands every chunk its true start (slow:
+// one tick after the other; taken only when the speculative pass could not anchor a chunk or failed its own check)
+__global__ void klatt_long_phase_serial_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, PhaseChunk *__restrict__ chunks,
+                                               double *__restrict__ startP) {
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	const uint64_t total = L.start[L.nReq];
+	PhaseSrc src(L, 0);
+	double pos = 0.0, quot;
+	uint64_t fi;
+	for (uint32_t c = 0; c < numChunks; ++c) {
+		const uint64_t t0 = (uint64_t)c * chunkTicks, t1 = (t0 + chunkTicks < total) ? t0 + chunkTicks : total;
+		PhaseChunk pc;
+		pc.anchor = t0; pc.next = t1; pc.s0 = pos; pc.map = phaseMapIdentity();
+		chunks[c] = pc;
+		startP[c] = pos;
+		for (uint64_t t = t0; t < t1; ++t) {
+			src.tick(quot, fi);
+			pos = phaseStep(pos, quot);
+		}
+	}
+}
+
+// pass 2: the two excitation signals of every tick: cascade input ci (:204, :148) and parallel input pin (:206, :171).
+// Chunk ch owns the ticks [anchor, next) of its phase run and renders them from the true start phase; the run must end on
+// the next run's start, bit for bit, or `fail` is raised (the construction is verified, not trusted).
+__global__ void __launch_bounds__(128)
+klatt_long_source_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, const PhaseChunk *__restrict__ chunks,
+                         const double *__restrict__ startP, uint32_t *__restrict__ fail, float *__restrict__ ci,
+                         float *__restrict__ pin) {
+	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ch >= numChunks) return;
+	const PhaseChunk pc = chunks[ch];
+	if (pc.anchor == kNoAnchor) return;
+	const uint64_t total = L.start[L.nReq];
+	const uint64_t t0 = pc.anchor, t1 = pc.next;
+	const double srD = (double)L.sampleRate, srInv = 1.0 / srD;
+	// warm the two noise colouring filters up on the ticks before the run
 	float aspLast = 0.0f, fricLast = 0.0f;
 	for (uint64_t g = (t0 > (uint64_t)kWarmTicks ? t0 - kWarmTicks : 0); g < t0; ++g) {
 		Philox4 b = noiseBlock(L.seed, L.streamId, g >> 1);
@@ -366,15 +488,15 @@ klatt_long_source_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, 
 	}
 	SourceWalk w;
 	w.seek(L, t0, true);
-	uint64_t pos = startPhase[ch];
+	double pos = startP[ch];
 	Philox4 blk;
 	blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
 	for (uint64_t t = t0; t < t1; ++t) {
 		if ((t & 1) == 0 || t == t0) blk = noiseBlock(L.seed, L.streamId, t >> 1);
 		const uint32_t wA = (t & 1) ? blk.w[2] : blk.w[0], wF = (t & 1) ? blk.w[3] : blk.w[1];
-		pos += w.phaseInc(L, srInv);
 		const uint32_t c = w.cur.c, F = w.cur.F;
-		const float voice = bitsToFloat(0x3F800000u | (uint32_t)(pos >> 41)) - 1.0f;
+		pos = phaseStep(pos, w.quotOfTick(srD, srInv));
+		const float voice = (float)pos;
 		aspLast = fmaf(0.75f, aspLast, bitsToFloat(0x4B000000u | (wA >> 9)) - 8388608.0f);
 		float asp = aspLast * (0.2f * kDrawScale);
 		float turb = asp * w.vta.at(c, F);
@@ -386,6 +508,10 @@ klatt_long_source_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, 
 		fricLast = fmaf(0.75f, fricLast, bitsToFloat(0x4B000000u | (wF >> 9)) - 8388608.0f);
 		pin[t] = fricLast * (((0.3f * kDrawScale) * w.fa.at(c, F)) * halfGain);
 		w.next(L, true);
+	}
+	if (t1 < total) {  // the chunk whose run starts at t1 must have been handed exactly the value this run arrives with
+		const uint32_t nx = (uint32_t)(t1 / chunkTicks);
+		if (nx >= numChunks || chunks[nx].anchor != t1 || startP[nx] != pos) atomicOr(fail, 1u);
 	}
 }
 
@@ -603,15 +729,28 @@ cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream) {
 }
 
 // signals: five float arrays of totalTicks (+ padding): ci, pin, par, xa, xb.  maps / startState: numChunks * 6.
+// phase scratch: advance / startPhase [numChunks] u64, chunks [numChunks] PhaseChunk, startP [numChunks] double, fail u32.
+// serialPhase: skip the speculative passes and run the plain recurrence on one thread (the fallback).
 cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
-                                  uint64_t *startPhase, float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
+                                  uint64_t *startPhase, PhaseChunk *chunks, double *startP, uint32_t *fail, bool serialPhase,
+                                  float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
                                   float2 *startState, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream) {
 	if (totalTicks == 0) return cudaSuccess;
 	const uint32_t numChunks = (uint32_t)((totalTicks + chunkTicks - 1) / chunkTicks);
 	const dim3 grid((numChunks + 127) / 128), block(128);
-	klatt_long_phase_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, advance);
-	klatt_long_phase_scan_kernel<<<1, 1024, 0, stream>>>(advance, numChunks, startPhase);
-	klatt_long_source_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, startPhase, ci, pin);
+	cudaError_t e = cudaMemsetAsync(fail, 0, sizeof(uint32_t), stream);
+	if (e != cudaSuccess) return e;
+	if (serialPhase) {
+		klatt_long_phase_serial_kernel<<<1, 1, 0, stream>>>(L, chunkTicks, numChunks, chunks, startP);
+		if (launchCounter) *launchCounter += 1;
+	} else {
+		klatt_long_phase_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, advance);
+		klatt_long_phase_scan_kernel<<<1, 1024, 0, stream>>>(advance, numChunks, startPhase);
+		klatt_long_spec_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, startPhase, chunks, fail);
+		klatt_long_phase_map_scan_kernel<<<1, 1024, 0, stream>>>(chunks, numChunks, startP);
+		if (launchCounter) *launchCounter += 4;
+	}
+	klatt_long_source_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, chunks, startP, fail, ci, pin);
 	// parallel bank
 	klatt_long_stage_kernel<kStageParallel, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, maps, nullptr, nullptr, nullptr);
 	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 6, startState);
@@ -632,7 +771,7 @@ cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint
 	klatt_long_stage_kernel<kStageLast, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, maps, nullptr, nullptr, nullptr);
 	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
 	klatt_long_stage_kernel<kStageLast, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, nullptr, startState, nullptr, pcm);
-	if (launchCounter) *launchCounter += 3 + 3 * 8;
+	if (launchCounter) *launchCounter += 1 + 3 * 8;
 	return cudaGetLastError();
 }
 

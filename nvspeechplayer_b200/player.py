@@ -20,7 +20,8 @@ PRECISION_FP64, PRECISION_FP32, PRECISION_STREAM = 0, 1, 2
 NOISE_PHILOX, NOISE_GLIBC, NOISE_REPLAY = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspeechPlayer.so")
+# NVSP_LIB: an A/B build of the same library (tools/_variants/, csrc/Makefile LIB=...); never anything but this engine
+LIB_PATH = os.environ.get("NVSP_LIB") or os.path.join(_HERE, "libspeechPlayer.so")
 dllPath = os.path.join(_HERE, "speechPlayer.dll")  # the name the reference wrapper loads (speechPlayer.py:42)
 
 speechPlayer_frameParam_t = ctypes.c_double

@@ -89,6 +89,8 @@ extern "C" int hostsim_render_f32(int sampleRate, const double *frames, const ui
 // block scans replaced by plain loops over the 512 chunks.
 // ---------------------------------------------------------------------------------------------------------------
 #include "../../nvspeechplayer_b200/csrc/pull_manager.h"
+#include "../../nvspeechplayer_b200/csrc/klatt_long_phase.cuh"
+#include <algorithm>
 
 namespace {
 struct HostPullPlayer {
@@ -280,4 +282,54 @@ extern "C" int hostsim_phase(const double *incs, uint32_t n, double pos0, int mo
 	for (uint32_t t = 0; t < n; ++t) out[t] = inc[pullIdx(X, t)];
 	*carry = st.pitchPos;
 	return visited;
+}
+
+// n-fold FP64 accumulation in closed form per binade (klatt_f32_core.cuh glideExact) -- compared with the plain loop by
+// tests/test_long_phase_cpu.py
+extern "C" double hostsim_glide(double p, double inc, uint64_t n) { return glideExact(p, inc, n); }
+
+// The exact parallel phase of the long-utterance path (klatt_long_phase.cuh) on a caller-supplied increment sequence, chunk
+// by chunk in the kernels' order: fixed-point prefix -> speculative runs -> scan of the offset maps -> true runs + check.
+// out[t] = phase after tick t.  Returns 1 when every run ended on the next run's start (the device's condition for keeping
+// the result), 0 when the check failed or a chunk could not be anchored (the device then takes the serial fallback).
+namespace {
+struct ArraySrc {
+	const double *q;
+	uint64_t t;
+	void tick(double &quot, uint64_t &fi) { quot = q[t]; fi = (uint64_t)cyclesToFixed(quot); ++t; }
+};
+}
+extern "C" int hostsim_long_phase(const double *quot, uint64_t n, uint32_t L, double *out, uint64_t *anchoredOut) {
+	const uint64_t numChunks = (n + L - 1) / L;
+	std::vector<uint64_t> startPhase(numChunks);
+	uint64_t phi = 0;
+	for (uint64_t c = 0; c < numChunks; ++c) {
+		startPhase[c] = phi;
+		for (uint64_t t = c * L; t < std::min<uint64_t>((c + 1) * L, n); ++t) phi += (uint64_t)cyclesToFixed(quot[t]);
+	}
+	std::vector<PhaseChunk> chunks(numChunks);
+	bool ok = true;
+	uint64_t anchored = 0;
+	for (uint64_t c = 0; c < numChunks; ++c) {
+		ArraySrc src{quot, c * L};
+		ok = phaseSpeculateChunk(src, c, L, n, startPhase[c], 16ull * L, chunks[c]) && ok;
+		anchored += chunks[c].anchor != kNoAnchor;
+	}
+	if (anchoredOut) *anchoredOut = anchored;
+	std::vector<double> startP(numChunks, 0.0);
+	PhaseMap pre = phaseMapIdentity();
+	for (uint64_t c = 0; c < numChunks; ++c) {
+		if (chunks[c].anchor != kNoAnchor) startP[c] = phaseFromOffset(chunks[c].s0, phaseMapApply(pre, 0));
+		pre = phaseMapCompose(chunks[c].map, pre);
+	}
+	for (uint64_t c = 0; c < numChunks; ++c) {
+		if (chunks[c].anchor == kNoAnchor) continue;
+		double pos = startP[c];
+		for (uint64_t t = chunks[c].anchor; t < chunks[c].next; ++t) { pos = phaseStep(pos, quot[t]); out[t] = pos; }
+		if (chunks[c].next < n) {
+			const uint64_t nx = chunks[c].next / L;
+			if (nx >= numChunks || chunks[nx].anchor != chunks[c].next || startP[nx] != pos) ok = false;
+		}
+	}
+	return ok ? 1 : 0;
 }

@@ -1,0 +1,39 @@
+#!/bin/bash
+# GPU box helper: tools/gpu_run.sh <stage> [args].  One script for every gpurun call of the round; outputs under gpurun_out/<stage>/.
+#   try "<env>" [bench args]   one compact line for a short bench run (A/B of builds: NVSP_LIB=tools/_variants/libX.so)
+cd "$(dirname "$0")/.."
+stage="$1"; shift
+O=gpurun_out/$stage
+mkdir -p $O
+try() {  # try "<env assignments>" [bench args...]
+	local envs="$1"; shift
+	local out
+	out=$(env $envs timeout 300 python bench.py --no-cpu-baseline --no-e2e --steps 3 --warmup 3 "$@" 2>$O/try_err.txt)
+	echo "$envs $* :: $(echo "$out" | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); print('ms/step %.2f  audio-s/s %.0f  frac %.4f  launches %d' % (d['ms_per_step'], d['value'], d['roofline']['frac'], d['gpu_launches']))
+except Exception as e:
+    print('FAILED', e)
+")"
+	grep -h "sched profile\|rror" $O/try_err.txt | head -4
+}
+case "$stage" in
+c1)  # baseline data of round 2: GPU suite, A/B of cheap scheduler variants, ncu source-level capture, kernel (b) captures, D2H probe
+	timeout 400 python -m pytest tests -q -m gpu -x > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -3 $O/pytest_gpu.log
+	try "NVSP_X=base"
+	try "NVSP_LIB=$PWD/tools/_variants/libnoflip.so"
+	try "NVSP_SCHED_HOLD_SMS=44"
+	try "NVSP_SCHED_HOLD_SMS=52"
+	try "NVSP_SCHED_HOLD_SMS=60"
+	try "NVSP_LIB=$PWD/tools/_variants/libprof.so"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_f32_sched_kernel -s 3 -c 1 -f -o $O/prof_sched \
+		python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_sched.log 2>&1; echo "ncu sched rc=$?"; ls -la $O/prof_sched.ncu-rep
+	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/long_launches.csv \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline > $O/long_launches.log 2>&1; echo "ncu long list rc=$?"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_long_stage -s 40 -c 3 -f -o $O/prof_long \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline > $O/ncu_long.log 2>&1; echo "ncu long rc=$?"; ls -la $O/prof_long.ncu-rep
+	timeout 120 tools/d2h_probe 1 1024 6 > $O/d2h_1gpu.json 2>&1; cat $O/d2h_1gpu.json
+	;;
+*) echo "unknown stage $stage"; exit 2;;
+esac
