@@ -49,6 +49,12 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
                                 int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, cudaStream_t stream,
                                 unsigned long long *launchCounter);
 int klattF32SchedBlocksPerSm();
+cudaError_t launchKlattF32Block(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount, uint32_t holdTicks,
+                                int16_t *out, size_t rowStride, uint32_t *samplesWritten, StreamResult *results, NoiseConfig noise,
+                                void *liteMem, int16_t *scratchRow, uint32_t numBlocks, void *profMem, uint32_t *hostFault,
+                                cudaStream_t stream, unsigned long long *launchCounter);
+bool klattF32BlockCanTake(uint32_t numStreams, uint32_t numBlocks);
+size_t klattF32BlockLiteBytes(uint32_t numStreams, uint32_t numBlocks);
 cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_t totalRequests, const double *frames,
                             const uint32_t *fadeDur, const uint8_t *isNull, int sampleRate, FadePlanF32 *plans,
                             cudaStream_t stream);
@@ -215,7 +221,11 @@ struct RoundsCtx {
 	static constexpr uint32_t kMaxGroups = 8;
 	DevBuf listHold, listGen, counters, scratchRow;
 	DevBuf ring, ctl;            // stream scheduler (persistent kernel, klatt_f32_sched.cu)
-	bool persistent = true;      // the default; NVSP_SCHED=rounds selects the round-based launch sequence instead
+	bool persistent = true;      // NVSP_SCHED=rounds selects the round-based launch sequence instead
+	// block scheduler (klatt_f32_block.cu): the default for large batches; NVSP_SCHED=rings (or persistent) keeps the ring scheduler
+	DevBuf lite, blockProf;
+	bool blockSched = true;
+	uint32_t blockHoldTicks = 128, blockMinStreams = 16384, blockBlocks = 0;
 	uint32_t *hostFault = nullptr;  // pinned: the scheduler watchdog's verdict of the last call
 	uint32_t schedHoldTicks = 512, schedGenTicks = 640, schedBlocks = 0;
 	cudaStream_t lanes[2 * kMaxGroups] = {};
@@ -237,6 +247,9 @@ struct RoundsCtx {
 		{
 			const char *e = getenv("NVSP_SCHED");
 			persistent = !(e && strcmp(e, "rounds") == 0);
+			blockSched = !(e && (strcmp(e, "rounds") == 0 || strcmp(e, "rings") == 0 || strcmp(e, "persistent") == 0));
+			blockHoldTicks = std::max<uint32_t>(envU("NVSP_BLOCK_HOLD_TICKS", 128) & ~63u, 64);
+			blockMinStreams = envU("NVSP_BLOCK_MIN_STREAMS", 16384);
 			schedGenTicks = std::max<uint32_t>(envU("NVSP_SCHED_GEN_TICKS", 640) & ~63u, 64);
 			schedHoldTicks = std::max<uint32_t>(envU("NVSP_SCHED_HOLD_TICKS", 512) & ~63u, 64);
 			int dev = 0, sms = 0;
@@ -244,6 +257,7 @@ struct RoundsCtx {
 			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 			const int perSm = klattF32SchedBlocksPerSm();
 			schedBlocks = envU("NVSP_SCHED_BLOCKS", (uint32_t)(sms * std::max(perSm, 1)));
+			blockBlocks = std::max<uint32_t>(envU("NVSP_BLOCK_BLOCKS", (uint32_t)sms), 1);
 			if (getenv("NVSP_VERBOSE"))
 				fprintf(stderr, "[nvspeechplayer_b200] scheduler: %d SMs x %d blocks, %u blocks, hold %u / general %u ticks\n", sms, perSm,
 				        schedBlocks, schedHoldTicks, schedGenTicks);
@@ -260,6 +274,7 @@ struct RoundsCtx {
 	}
 	void destroy() {
 		listHold.release(); listGen.release(); counters.release(); scratchRow.release(); ring.release(); ctl.release();
+		lite.release(); blockProf.release();
 		if (hostFault) cudaFreeHost(hostFault);
 		hostFault = nullptr;
 		if (evStart) cudaEventDestroy(evStart);
@@ -284,6 +299,23 @@ static cudaError_t launchRender(int precision, const StreamDesc *descs, uint32_t
 	if (precision == kPrecisionF64) {
 		if (launchCounter) ++*launchCounter;
 		return launchKlattF64(descs, n, sampleRate, sampleCount, out, rowStride, written, results, noise, stream);
+	}
+	if (rc && planned && rc->init() && rc->blockSched && n >= rc->blockMinStreams && klattF32BlockCanTake(n, rc->blockBlocks)) {
+		if (!rc->lite.reserve(klattF32BlockLiteBytes(n, rc->blockBlocks)) ||
+		    !rc->scratchRow.reserve(sizeof(int16_t) * (size_t)std::max<uint32_t>(std::max(rc->schedHoldTicks, rc->holdTicks), rc->blockHoldTicks)))
+			return cudaErrorMemoryAllocation;
+		if (!rc->blockProf.p) {
+			if (!rc->blockProf.reserve(256)) return cudaErrorMemoryAllocation;
+			cudaMemsetAsync(rc->blockProf.p, 0, 256, stream);
+		}
+		if (!rc->hostFault) {
+			if (cudaMallocHost((void **)&rc->hostFault, sizeof(uint32_t)) != cudaSuccess) return cudaErrorMemoryAllocation;
+			*rc->hostFault = 0;
+		}
+		if (*rc->hostFault) return cudaErrorLaunchTimeout;  // an earlier call of this batch tripped the watchdog
+		return launchKlattF32Block(descs, n, sampleRate, sampleCount, rc->blockHoldTicks, out, rowStride, written, results, noise,
+		                           rc->lite.p, rc->scratchRow.as<int16_t>(), rc->blockBlocks, rc->blockProf.p, rc->hostFault, stream,
+		                           launchCounter);
 	}
 	if (rc && planned && rc->init() && rc->persistent && n >= rc->minStreams && sampleCount > rc->schedGenTicks) {
 		uint32_t cap = 64;
@@ -1273,6 +1305,7 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 	chunkTicks = std::max(chunkTicks, 64u);
 	const size_t n = numFrames;
 	DevBuf dFrames, dMin, dFade, dNull, dOff, dPlans, dStart, dPrev, dPitch, dVib;
+	DevBuf sig, maps, st, ph, pcm, phChunks, phStart, phFail;  // (function scope: `cleanup` below releases them at exit)
 	struct Cleanup {
 		std::vector<DevBuf *> bufs;
 		cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1319,7 +1352,6 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 		const uint64_t numChunks = (ticks + chunkTicks - 1) / chunkTicks;
 		if (numChunks > 0x7fffffffull) return fail("stream too long for one call");
 		const size_t pad = ticks + 64;
-		DevBuf sig, maps, st, ph, pcm, phChunks, phStart, phFail;
 		cleanup.bufs.insert(cleanup.bufs.end(), {&sig, &maps, &st, &ph, &pcm, &phChunks, &phStart, &phFail});
 		if (!sig.reserve(5 * pad * sizeof(float)) || !maps.reserve(numChunks * 6 * sizeof(Affine)) ||
 		    !st.reserve(numChunks * 6 * sizeof(float2)) || !ph.reserve(numChunks * 2 * sizeof(double)) ||

@@ -129,6 +129,33 @@ struct GenStateF32 {
 	FadePlanF32 plan;              // plan of the fade in progress when it was made inline (no precomputed plans)
 };
 
+// The same two blocks WITHOUT what a pre-queued (planned) FP32 stream never touches -- the three 47-double frames of the
+// frame manager and the inline fade plan: 472 bytes instead of 2.4 KB.  The block scheduler (klatt_f32_block.cu) keeps the
+// streams of a call in a dense array of these (65 536 streams: 31 MB, resident in the 126 MB L2) and switches a stream
+// between the hold, fade and general loops every 64..128 ticks; members keep the names of the full structures so the
+// render bodies of klatt_f32_core.cuh work on either.
+struct FrameMgrLite {
+	int32_t lastUserIndex;
+	uint32_t qHead, counter;
+	uint8_t hasNew, curIsNull, oldIsNull, newIsNull;
+	uint32_t oldM, newM, newF, purgePending;
+	double oldInc, newInc;
+};
+struct GenStateF32Lite {
+	double pitchPos, pitch, pitchInc, pitchOld, pitchNew;
+	uint64_t samplesGenerated, vibratoPos;
+	int64_t vibInc;
+	float aspLast, fricLast;
+	uint32_t n0Inv, holdArmed, nextEvent, coarseAt, callPos, callDrained;
+	float y[kNumResonators], d[kNumResonators], zre[kNumResonators], zim[kNumResonators];
+	float dir[kNumDirect];
+	float zc[2 * kNumResonators];
+};
+struct alignas(16) StreamStateLite {
+	FrameMgrLite fm;
+	GenStateF32Lite f32;
+};
+
 struct StreamState {
 	FrameMgrState fm;
 	union {

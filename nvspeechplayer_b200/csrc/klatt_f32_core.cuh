@@ -31,6 +31,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <type_traits>
 #include "klatt_common.h"
 #include "philox.cuh"
 
@@ -616,8 +617,8 @@ struct NoiseSource {
 	}
 };
 
-template <int ROLE>
-KLATT_HD void loadDspState(DspState &S, const GenStateF32 &gs) {
+template <int ROLE, class GS>
+KLATT_HD void loadDspState(DspState &S, const GS &gs) {
 	using T = RoleTraits<ROLE>;
 #pragma unroll
 	for (int r = T::R0; r < T::R1; ++r) { half(S.ny, r) = (r == kResN0) ? gs.y[r] : -gs.y[r]; half(S.d, r) = gs.d[r]; }
@@ -628,8 +629,8 @@ KLATT_HD void loadDspState(DspState &S, const GenStateF32 &gs) {
 		S.pitchPos = gs.pitchPos; S.pitch = gs.pitch; S.pitchInc = gs.pitchInc;
 	}
 }
-template <int ROLE>
-KLATT_HD void storeDspState(GenStateF32 &gs, const DspState &S) {
+template <int ROLE, class GS>
+KLATT_HD void storeDspState(GS &gs, const DspState &S) {
 	using T = RoleTraits<ROLE>;
 #pragma unroll
 	for (int r = T::R0; r < T::R1; ++r) { gs.y[r] = (r == kResN0) ? half(S.ny, r) : -half(S.ny, r); gs.d[r] = half(S.d, r); }
@@ -646,18 +647,23 @@ KLATT_HD void storeDspState(GenStateF32 &gs, const DspState &S) {
 // The caller guarantees (canHoldF32) that no frame-manager event falls inside: coefficients are built once.
 // `ticks` is a multiple of kGroupTicks.  Only the cascade side owns the frame-manager counters.
 // ---------------------------------------------------------------------------------------------------
-KLATT_HD bool canHoldF32(const StreamState &st, uint32_t ticks) {
-	const FrameMgrState &fm = st.fm;
-	return !fm.hasNew && !fm.curIsNull && !fm.purgePending && st.gen.f32.holdArmed &&
-	       (uint64_t)fm.counter + ticks <= (uint64_t)fm.oldM;
+template <class FM, class GS>
+KLATT_HD bool canHoldF32T(const FM &fm, const GS &gs, uint32_t ticks) {
+	return !fm.hasNew && !fm.curIsNull && !fm.purgePending && gs.holdArmed && (uint64_t)fm.counter + ticks <= (uint64_t)fm.oldM;
+}
+KLATT_HD bool canHoldF32(const StreamState &st, uint32_t ticks) { return canHoldF32T(st.fm, st.gen.f32, ticks); }
+// `ticks` ticks ahead are all INTERIOR fade ticks (frame.cpp:49-52 with 1 <= sampleCounter < fade length, no event among
+// them) and the first of them falls on the 64-sample grid of the drift control: renderFadeF32T may run them
+template <class FM, class GS>
+KLATT_HD bool canFadeF32T(const FM &fm, const GS &gs, uint32_t ticks) {
+	return fm.hasNew && !fm.purgePending && fm.counter >= 1 && (uint64_t)fm.counter + ticks < (uint64_t)fm.newF &&
+	       (gs.samplesGenerated & (uint64_t)(kCoarseTicks - 1)) == 0;
 }
 
-template <int ROLE, class Out, class Xchg>
-KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t ticks, Out &out, const NoiseConfig &noise,
-                            Xchg &xc) {
+template <int ROLE, class Out, class Xchg, class FM, class GS>
+KLATT_HD void renderHoldF32T(FM &fm, GS &gs, const StreamDesc &desc, int sampleRate, uint32_t ticks, Out &out, const NoiseConfig &noise,
+                             Xchg &xc) {
 	using T = RoleTraits<ROLE>;
-	StreamState *st = desc.state;
-	GenStateF32 &gs = st->gen.f32;
 	const double srD = (double)sampleRate, srInv = 1.0 / (double)sampleRate;
 	DspState S;
 	loadDspState<ROLE>(S, gs);
@@ -716,9 +722,13 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 	storeDspState<ROLE>(gs, S);
 	if (T::hasC) {
 		gs.samplesGenerated = gen;
-		st->fm.counter += ticks;
+		fm.counter += ticks;
 		gs.callPos += ticks;
 	}
+}
+template <int ROLE, class Out, class Xchg>
+KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t ticks, Out &out, const NoiseConfig &noise, Xchg &xc) {
+	renderHoldF32T<ROLE>(desc.state->fm, desc.state->gen.f32, desc, sampleRate, ticks, out, noise, xc);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -728,13 +738,12 @@ KLATT_HD void renderHoldF32(const StreamDesc &desc, int sampleRate, uint32_t tic
 // desc.plans (may be null, kRoleBoth only) holds precomputed FadePlanF32 for requests [qBase, qBase+qCount);
 // without it the plan is made inline at the pop tick from the frame manager's own frames (per-handle API, purge).
 // ---------------------------------------------------------------------------------------------------
-template <int ROLE, class Out, class Xchg>
-KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint32_t myTicks, uint32_t loopTicks, Out &out,
-                                   const NoiseConfig &noise, Xchg &xc, int32_t *lastUserIndexOut, uint32_t *qHeadOut) {
+template <int ROLE, class Out, class Xchg, class FM, class GS>
+KLATT_HD uint32_t renderGeneralF32T(FM &fm, GS &gs, const StreamDesc &desc, int sampleRate, uint32_t myTicks, uint32_t loopTicks, Out &out,
+                                    const NoiseConfig &noise, Xchg &xc, int32_t *lastUserIndexOut, uint32_t *qHeadOut) {
 	using T = RoleTraits<ROLE>;
-	StreamState *st = desc.state;
-	FrameMgrState &fm = st->fm;
-	GenStateF32 &gs = st->gen.f32;
+	// inline planning (per-handle API, purge) needs the frame manager's three frames and the plan slot of the full state
+	constexpr bool kInline = ROLE == kRoleBoth && std::is_same<FM, FrameMgrState>::value;
 	const double srD = (double)sampleRate, srInv = 1.0 / (double)sampleRate;
 	const bool planned = desc.plans != nullptr;  // always true for the split roles
 
@@ -766,21 +775,24 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 	// purge prologue, src/frame.cpp:103-112 (the dropped requests were removed on the host).  fm.curFrame is kept
 	// current at every exit in inline mode, so the snapshot is available here; the working set simply stays where
 	// the interrupted fade left it.
-	if (ROLE == kRoleBoth && fm.purgePending) {
-		fm.purgePending = 0;
-		counter = oldM;
-		if (hasNew) {
-			oldIsNull = newIsNull;
-			for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.curFrame[i];
-			hasNew = false;
+	if constexpr (kInline) {
+		if (fm.purgePending) {
+			fm.purgePending = 0;
+			counter = oldM;
+			if (hasNew) {
+				oldIsNull = newIsNull;
+				for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.curFrame[i];
+				hasNew = false;
+			}
+			S.pitchInc = 0.0;
+			holdArmed = false;
+			nextEvent = oldM + 1;
 		}
-		S.pitchInc = 0.0;
-		holdArmed = false;
-		nextEvent = oldM + 1;
 	}
 	const FadePlanF32 *plan = nullptr;
 	if (hasNew) {
-		plan = planned ? desc.plans + (qHead - 1 - desc.qBase) : &gs.plan;
+		if constexpr (kInline) plan = planned ? desc.plans + (qHead - 1 - desc.qBase) : &gs.plan;
+		else plan = desc.plans + (qHead - 1 - desc.qBase);
 		if (counter >= 1 && counter < newF) {  // resuming in the middle of a fade: the increments are in force
 #pragma unroll
 			for (int r = T::R0; r < T::R1; ++r) { half(wr, r) = plan->wre[r]; half(wi, r) = plan->wim[r]; }
@@ -808,8 +820,10 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 			if (KLATT_UNLIKELY(counter >= nextEvent)) {
 				if (hasNew) {
 					if (counter > newF) {  // :44-47 the fade is over: new becomes old; cur keeps its ratio-1 value
-						if (ROLE == kRoleBoth && !planned)
-							for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
+						if constexpr (kInline) {
+							if (!planned)
+								for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
+						}
 						oldM = newM; oldIsNull = newIsNull;
 						if (T::hasO) fm.oldInc = fm.newInc;
 						hasNew = false;
@@ -865,14 +879,18 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						qHead++;
 						hasNew = true;
 						double pitchOld = S.pitch, pitchNew, newInc;  // old.frame.voicePitch follows the glide (:78)
-						if (ROLE == kRoleBoth && !planned) {
-							fm.oldFrame[kVoicePitch] = S.pitch;
-							for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
+						if constexpr (kInline) {
+							if (!planned) {
+								fm.oldFrame[kVoicePitch] = S.pitch;
+								for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
+							}
 						}
 						if (newIsNull) {  // :59-63
-							if (ROLE == kRoleBoth && !planned) {
-								for (int i = 0; i < kNumParams; ++i) fm.newFrame[i] = fm.oldFrame[i];
-								fm.newFrame[kPreFormantGain] = 0;
+							if constexpr (kInline) {
+								if (!planned) {
+									for (int i = 0; i < kNumParams; ++i) fm.newFrame[i] = fm.oldFrame[i];
+									fm.newFrame[kPreFormantGain] = 0;
+								}
 							}
 							pitchNew = S.pitch;
 							newInc = 0;
@@ -880,13 +898,17 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 							const double *fr = desc.frames + (size_t)rel * kNumParams;
 							pitchNew = fr[kVoicePitch];
 							newInc = (fr[kEndVoicePitch] - fr[kVoicePitch]) / (double)newM;  // src/frame.cpp:98
-							if (ROLE == kRoleBoth && !planned)
-								for (int i = 0; i < kNumParams; ++i) fm.newFrame[i] = fr[i];
+							if constexpr (kInline) {
+								if (!planned)
+									for (int i = 0; i < kNumParams; ++i) fm.newFrame[i] = fr[i];
+							}
 							if (oldIsNull) {  // :64-67
 								pitchOld = pitchNew;
-								if (ROLE == kRoleBoth && !planned) {
-									for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
-									fm.oldFrame[kPreFormantGain] = 0;
+								if constexpr (kInline) {
+									if (!planned) {
+										for (int i = 0; i < kNumParams; ++i) fm.oldFrame[i] = fm.newFrame[i];
+										fm.oldFrame[kPreFormantGain] = 0;
+									}
 								}
 							}
 						}
@@ -896,11 +918,13 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 						if (T::hasO) { gs.pitchOld = pitchOld; gs.pitchNew = pitchNew; fm.newInc = newInc; }
 						if (planned) {
 							plan = desc.plans + rel;
-						} else if (ROLE == kRoleBoth) {  // plan the fade here (double precision, once per request)
-							fm.newFrame[kVoicePitch] = pitchNew;
-							fm.oldFrame[kVoicePitch] = pitchOld;
-							planFade(fm.oldFrame, fm.newFrame, newF, sampleRate, gs.plan);
-							plan = &gs.plan;
+						} else {
+							if constexpr (kInline) {  // plan the fade here (double precision, once per request)
+								fm.newFrame[kVoicePitch] = pitchNew;
+								fm.oldFrame[kVoicePitch] = pitchOld;
+								planFade(fm.oldFrame, fm.newFrame, newF, sampleRate, gs.plan);
+								plan = &gs.plan;
+							}
 						}
 						S.pitchInc = 0.0;
 						holdArmed = false;
@@ -986,20 +1010,22 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 	}
 
 	// ---- store the stream back ----
-	if (ROLE == kRoleBoth && !planned) {  // keep fm.curFrame / fm.oldFrame meaningful for purge and for the next inline plan
-		if (hasNew) {
-			if (counter >= 1) {
-				double ratio = (double)counter / (double)newF;
-				for (int i = 0; i < kNumParams; ++i) {
-					double o = fm.oldFrame[i], n = fm.newFrame[i];
-					fm.curFrame[i] = (n != n) ? o : o + ((n - o) * ratio);
+	if constexpr (kInline) {
+		if (!planned) {  // keep fm.curFrame / fm.oldFrame meaningful for purge and for the next inline plan
+			if (hasNew) {
+				if (counter >= 1) {
+					double ratio = (double)counter / (double)newF;
+					for (int i = 0; i < kNumParams; ++i) {
+						double o = fm.oldFrame[i], n = fm.newFrame[i];
+						fm.curFrame[i] = (n != n) ? o : o + ((n - o) * ratio);
+					}
 				}
+			} else {
+				for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
+				fm.oldFrame[kVoicePitch] = S.pitch;
 			}
-		} else {
-			for (int i = 0; i < kNumParams; ++i) fm.curFrame[i] = fm.oldFrame[i];
-			fm.oldFrame[kVoicePitch] = S.pitch;
+			fm.curFrame[kVoicePitch] = S.pitch;
 		}
-		fm.curFrame[kVoicePitch] = S.pitch;
 	}
 	storeDspState<ROLE>(gs, S);
 #pragma unroll
@@ -1022,6 +1048,126 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 	*lastUserIndexOut = lastUserIndex;
 	*qHeadOut = qHead;
 	return produced;
+}
+template <int ROLE, class Out, class Xchg>
+KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint32_t myTicks, uint32_t loopTicks, Out &out,
+                                   const NoiseConfig &noise, Xchg &xc, int32_t *lastUserIndexOut, uint32_t *qHeadOut) {
+	return renderGeneralF32T<ROLE>(desc.state->fm, desc.state->gen.f32, desc, sampleRate, myTicks, loopTicks, out, noise, xc,
+	                               lastUserIndexOut, qHeadOut);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// renderFadeF32T: `ticks` INTERIOR fade ticks of one pre-queued stream (reference src/frame.cpp:49-52 feeding
+// src/speechWaveGenerator.cpp:113-125 on every tick), straight-line: the caller guarantees (canFadeF32T) that no
+// frame-manager event falls inside and that the first tick sits on the 64-sample grid of the drift control, so the coarse
+// re-basing happens before the loop and a tick is pole recurrences -> coefficients -> the DSP with no branch.  The
+// arithmetic of every tick is renderGeneralF32T's, operation for operation: a stream may change between the two (and the
+// hold loop) at any chunk boundary without changing an output bit.  ticks is a multiple of kGroupTicks and at most
+// kCoarseTicks; Philox noise only (pre-queued batches); even `samplesGenerated` follows from the grid condition.
+// ---------------------------------------------------------------------------------------------------
+template <int ROLE, class Out, class Xchg, class FM, class GS>
+KLATT_HD void renderFadeF32T(FM &fm, GS &gs, const StreamDesc &desc, int sampleRate, uint32_t ticks, Out &out, const NoiseConfig &noise,
+                             Xchg &xc) {
+	using T = RoleTraits<ROLE>;
+	const double srD = (double)sampleRate, srInv = 1.0 / (double)sampleRate;
+	const uint32_t rel = fm.qHead - 1u - desc.qBase;
+	const FadePlanF32 *plan = desc.plans + (rel < desc.qCount ? rel : 0u);  // (idle lanes run a dummy stream with an empty queue)
+	uint32_t counter = fm.counter;
+	DspState S;
+	loadDspState<ROLE>(S, gs);
+	F2 u[kNumPairs], v[kNumPairs], wr[kNumPairs], wi[kNumPairs];
+	F2 dir0[kNumDirectPairs], dstep[kNumDirectPairs];
+#pragma unroll
+	for (int r = T::R0; r < T::R1; ++r) { half(u, r) = -gs.zre[r]; half(v, r) = -gs.zim[r]; half(wr, r) = plan->wre[r]; half(wi, r) = plan->wim[r]; }
+#pragma unroll
+	for (int i = 0; i < kNumDirect; ++i)
+		if (roleUsesDirectPair<ROLE>(i / 2)) {
+			half(dir0, i) = roleUsesDirect<ROLE>(i) ? plan->dir0[i] : 0.0f;
+			half(dstep, i) = roleUsesDirect<ROLE>(i) ? plan->dirStep[i] : 0.0f;
+		}
+	float kf = (float)counter;
+	const int64_t vibIncStep = plan->vibIncStep;
+	const bool n0Inv = gs.n0Inv != 0;
+	uint64_t gen = gs.samplesGenerated;
+	const uint64_t streamId = desc.streamId;
+	// the first tick lies on the drift-control grid: its poles come from the coarse recurrence when the previous grid point
+	// of this fade was recorded, from the per-tick one otherwise; either way they become the new record
+	{
+		if (counter + 1u - gs.coarseAt == (uint32_t)kCoarseTicks) {
+#pragma unroll
+			for (int r = T::R0; r < T::R1; ++r) {
+				float zr = gs.zc[r], zi = gs.zc[kNumResonators + r], Wr = plan->Wre[r], Wi = plan->Wim[r];
+				float tr = fmaf(-zr, Wr, Wr);
+				tr = fmaf(zi, Wi, tr);
+				float ti = fmaf(-zr, Wi, Wi);
+				ti = fmaf(-zi, Wr, ti);
+				half(u, r) = -(zr + tr);
+				half(v, r) = -(zi + ti);
+			}
+		} else {
+			stepPoles<ROLE>(u, v, wr, wi);
+		}
+#pragma unroll
+		for (int r = T::R0; r < T::R1; ++r) { gs.zc[r] = -half(u, r); gs.zc[kNumResonators + r] = -half(v, r); }
+	}
+	const uint32_t coarseAt = counter + 1u;
+	for (uint32_t t = 0; t < ticks; t += kGroupTicks) {
+		if (T::hasC && !T::hasP) xc.sync();  // the parallel side has finished this group
+#pragma unroll 1
+		for (int k = 0; k < kGroupTicks; k += 2) {
+			Philox4 blk;
+			if (T::hasP) blk = noiseBlock(noise.seed, streamId, (gen + k) >> 1);
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const bool oscHere = T::hasO && !T::hasC;
+				OscChain osc;
+				counter++;
+				kf += 1.0f;
+				if (T::hasO) S.vibInc += vibIncStep;
+				if (t + k + h != 0) stepPoles<ROLE>(u, v, wr, wi);
+				if (oscHere) { osc.seg1(S); osc.seg2(); }
+				CoefF32 C;
+				{
+					F2 dir[kNumDirectPairs];
+					const F2 kf2 = f2s(kf);
+#pragma unroll
+					for (int q = 0; q < kNumDirectPairs; ++q)
+						if (roleUsesDirectPair<ROLE>(q)) dir[q] = fma2(kf2, dstep[q], dir0[q]);
+					if (oscHere) osc.seg3(S, half(dir, dVibratoPitchOffset));
+					buildCoef<ROLE>(C, u, v, dir, n0Inv);
+				}
+				if (oscHere) osc.seg4(srD, srInv);
+				uint32_t wA = 0;
+				float par = 0.0f, voice = 0.0f;
+				if (T::hasP) {
+					wA = blk.w[2 * h];
+					if (oscHere) osc.seg5(S);
+					par = parallelSide(S, C, blk.w[2 * h + 1]);
+					if (oscHere) voice = osc.seg6();
+					if (!T::hasC) xc.put(t + k + h, wA, par, voice);
+				}
+				if (T::hasC) {
+					if (!T::hasP) xc.get(t + k + h, wA, par, voice);
+					if (T::hasO) voice = oscillatorSide(S, C, srD, srInv);
+					out.push(cascadeSide(S, C, wA, par, voice));
+				}
+			}
+		}
+		gen += kGroupTicks;
+		if (T::hasP && !T::hasC) xc.sync();  // hand the group over
+	}
+	storeDspState<ROLE>(gs, S);
+#pragma unroll
+	for (int r = T::R0; r < T::R1; ++r) { gs.zre[r] = -half(u, r); gs.zim[r] = -half(v, r); }
+#pragma unroll
+	for (int i = 0; i < kNumDirect; ++i)
+		if (roleUsesDirect<ROLE>(i) && (T::hasC || i != dPreFormantGain)) gs.dir[i] = fmaf(kf, half(dstep, i), half(dir0, i));
+	if (T::hasC) {
+		fm.counter = counter;
+		gs.samplesGenerated = gen;
+		gs.coarseAt = coarseAt;
+		gs.callPos += ticks;
+	}
 }
 
 }  // namespace klatt

@@ -83,6 +83,66 @@ extern "C" int hostsim_render_f32(int sampleRate, const double *frames, const ui
 	return (int)total;
 }
 
+// mode "cells" of the block scheduler (klatt_f32_block.cu): the stream lives in the compact StreamStateLite and is handed, cell
+// by cell, to the hold loop (holdTicks pure hold ticks ahead), the fade loop (64 interior fade ticks ahead, on the 64-sample
+// grid) or the general loop (everything else; it re-aligns a stream to the grid).  Must render the same bits as mode 0 / 1.
+extern "C" int hostsim_render_f32_cells(int sampleRate, const double *frames, const uint32_t *minDur, const uint32_t *fadeDur,
+                                        const int32_t *userIndex, const uint8_t *isNull, uint32_t nFrames, uint64_t seed,
+                                        uint64_t streamId, uint32_t maxSamples, int16_t *out, uint32_t holdTicks, uint32_t fadeTicks,
+                                        uint32_t *ticksByClass /* [3]: hold, fade, general */, int32_t *lastIndexOut) {
+	StreamStateLite *st = (StreamStateLite *)calloc(1, sizeof(StreamStateLite));
+	st->fm.lastUserIndex = -1;
+	st->fm.curIsNull = 1;
+	st->fm.oldIsNull = 1;
+	StreamDesc d;
+	memset(&d, 0, sizeof d);
+	d.state = nullptr; d.frames = frames; d.minDur = minDur; d.fadeDur = fadeDur; d.userIndex = userIndex; d.isNull = isNull;
+	d.qCount = nFrames; d.qBase = 0; d.streamId = streamId;
+	std::vector<FadePlanF32> plans(nFrames);
+	int prevReal = -1;
+	for (uint32_t j = 0; j < nFrames; ++j) {
+		bool prevNull = (j == 0) || (isNull && isNull[j - 1]);
+		bool curNull = isNull && isNull[j];
+		double o[kNumParams], n[kNumParams];
+		plannedFrames(prevReal >= 0 ? frames + (size_t)prevReal * kNumParams : nullptr, prevNull, frames + (size_t)j * kNumParams, curNull, o, n);
+		uint32_t F = fadeDur[j] > 1u ? fadeDur[j] : 1u;
+		planFade(o, n, F, sampleRate, plans[j]);
+		if (!curNull) prevReal = (int)j;
+	}
+	d.plans = plans.data();
+	NoiseConfig nc;
+	nc.mode = kNoisePhilox; nc.seed = seed;
+	uint32_t total = 0;
+	uint32_t used[3] = {0, 0, 0};
+	int32_t lui = -1;
+	uint32_t qh = 0;
+	while (total < maxSamples) {
+		const uint32_t left = maxSamples - total;
+		ArrayOut ao{out + total, 0};
+		XchgSelf xc;
+		if (left >= holdTicks && canHoldF32T(st->fm, st->f32, holdTicks)) {
+			renderHoldF32T<kRoleBoth>(st->fm, st->f32, d, sampleRate, holdTicks, ao, nc, xc);
+			total += holdTicks; used[0] += holdTicks;
+			lui = st->fm.lastUserIndex;
+			continue;
+		}
+		if (left >= fadeTicks && canFadeF32T(st->fm, st->f32, fadeTicks)) {
+			renderFadeF32T<kRoleBoth>(st->fm, st->f32, d, sampleRate, fadeTicks, ao, nc, xc);
+			total += fadeTicks; used[1] += fadeTicks;
+			continue;
+		}
+		uint32_t want = (uint32_t)kCoarseTicks - (uint32_t)(st->f32.samplesGenerated & (uint64_t)(kCoarseTicks - 1));
+		if (want > left) want = left;
+		const uint32_t got = renderGeneralF32T<kRoleBoth>(st->fm, st->f32, d, sampleRate, want, want, ao, nc, xc, &lui, &qh);
+		total += got; used[2] += got;
+		if (got < want) break;
+	}
+	if (ticksByClass) { ticksByClass[0] = used[0]; ticksByClass[1] = used[1]; ticksByClass[2] = used[2]; }
+	if (lastIndexOut) *lastIndexOut = lui;
+	free(st);
+	return (int)total;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Low-latency pull path (nvspeechplayer_b200/csrc/klatt_pull_core.cuh + pull_manager.h): the host frame manager is
 // the product's own; the kernel is emulated "thread by thread" -- the same per-thread passes in the same order, the

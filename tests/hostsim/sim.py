@@ -19,8 +19,33 @@ def lib():
         L.hostsim_render_f32.restype = ctypes.c_int
         L.hostsim_render_f32.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint64,
                                          ctypes.c_uint, vp, ctypes.c_uint, vp, ctypes.c_int, ctypes.c_uint, ctypes.c_uint, vp]
+        L.hostsim_render_f32_cells.restype = ctypes.c_int
+        L.hostsim_render_f32_cells.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint64,
+                                               ctypes.c_uint, vp, ctypes.c_uint, ctypes.c_uint, vp, vp]
         _lib = L
     return _lib
+
+
+def render_f32_cells(sr, frames, min_dur, fade_dur, is_null=None, user_index=None, max_samples=None, seed=0, stream=0,
+                     hold_ticks=128, fade_ticks=64):
+    """The block scheduler's execution model on one stream: compact state, hold / fade / general cells.  Returns
+    (pcm, last_index, [hold ticks, fade ticks, general ticks])."""
+    frames = np.ascontiguousarray(frames, dtype=np.float64).reshape(-1, 47)
+    m = np.ascontiguousarray(min_dur, dtype=np.uint32)
+    f = np.ascontiguousarray(fade_dur, dtype=np.uint32)
+    nul = None if is_null is None else np.ascontiguousarray(is_null, dtype=np.uint8)
+    ux = None if user_index is None else np.ascontiguousarray(user_index, dtype=np.int32)
+    if max_samples is None:
+        mm = m.astype(np.int64)
+        ff = np.maximum(f.astype(np.int64), 1)
+        max_samples = int(np.maximum(mm + 1, ff + 2).sum()) + 16
+    out = np.zeros(max_samples, dtype=np.int16)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    li = ctypes.c_int32(0)
+    used = (ctypes.c_uint32 * 3)()
+    n = lib().hostsim_render_f32_cells(sr, ptr(frames), ptr(m), ptr(f), ptr(ux), ptr(nul), len(m), seed, stream, max_samples,
+                                       ptr(out), hold_ticks, fade_ticks, used, ctypes.byref(li))
+    return out[:n], li.value, list(used)
 
 
 def render_f32(sr, frames, min_dur, fade_dur, is_null=None, user_index=None, max_samples=None, seed=0, stream=0, chunk=0,

@@ -56,3 +56,32 @@ def test_long_fades_do_not_drift(port):
         got, _ = sim.render_f32(16000, fr, m, f, nul, ux, seed=8, stream=s)
         w1, exact, snr, mx = parity.assert_f32_parity(got, want, "vowel pair %d" % s)
         assert mx <= 1 and snr >= 80.0
+
+
+@pytest.mark.parametrize("hold,fade", [(128, 64), (64, 64), (256, 64)])
+def test_cells_equal_one_shot_bitwise(golden_config1, hold, fade):
+    """The block scheduler's execution model (klatt_f32_block.cu): the stream in the compact StreamStateLite, every 64-sample
+    cell handed to the hold loop, the straight-line fade loop (renderFadeF32T) or the general loop.  Same bits as the
+    one-shot general render, on random frames, on config 1 and on the vowel chart's 400 ms fades; and most ticks must
+    actually run in the two fast loops."""
+    sr = 22050
+    for sid, secs in ((7, 2.0), (4242, 3.0)):
+        fr, m, f, nul, ux = workloads.random_stream(sid, secs, sr)
+        n = int(secs * sr)
+        one, li = sim.render_f32(sr, fr, m, f, nul, ux, max_samples=n, seed=1, stream=sid)
+        got, li2, used = sim.render_f32_cells(sr, fr, m, f, nul, ux, max_samples=n, seed=1, stream=sid, hold_ticks=hold, fade_ticks=fade)
+        np.testing.assert_array_equal(got, one)
+        assert li2 == li and sum(used) == n
+        assert used[0] > 0.3 * n and used[1] > 0.1 * n, used
+    g = golden_config1
+    one, _ = sim.render_f32(int(g["sample_rate"]), g["frames"], g["min_dur"], g["fade_dur"], g["is_null"], seed=5, stream=9)
+    got, _, used = sim.render_f32_cells(int(g["sample_rate"]), g["frames"], g["min_dur"], g["fade_dur"], g["is_null"], seed=5, stream=9,
+                                        hold_ticks=hold, fade_ticks=fade)
+    np.testing.assert_array_equal(got, one)
+    fb = workloads.vowel_chart(1, pairs=3)
+    for s in range(fb.num_streams):
+        fr, m, f, nul, ux = fb.stream(s)
+        one, _ = sim.render_f32(16000, fr, m, f, nul, ux, seed=8, stream=s)
+        got, _, used = sim.render_f32_cells(16000, fr, m, f, nul, ux, seed=8, stream=s, hold_ticks=hold, fade_ticks=fade)
+        np.testing.assert_array_equal(got, one)
+        assert used[1] > 0.4 * len(one), used   # 60 % of these ticks are fade ticks

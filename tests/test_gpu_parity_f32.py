@@ -135,18 +135,21 @@ def test_philox_noise_statistics():
 
 def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
     """The batch engine's round-based execution (phase-sorted hold / general chunks, the two sides of a stream in
-    paired warps, several stream groups in flight) and its persistent stream scheduler (the same chunks handed out by
-    device-side rings inside one launch) render the same bits as the one-thread-per-stream kernel,
+    paired warps, several stream groups in flight), its ring scheduler (the same chunks handed out by device-side rings
+    inside one launch) and its block scheduler (the default: streams owned by one thread block each, compact state, hold /
+    fade / general cells of 64..128 ticks) render the same bits as the one-thread-per-stream kernel,
     including streams that drain mid-call, partially filled warps and calls that end inside a chunk."""
     sr, n = 22050, 203
     streams = [workloads.random_stream(500 + s, 0.35 if s % 7 == 3 else 1.0, sr) for s in range(n)]
     fb = workloads._concat(sr, streams, np.arange(500, 500 + n, dtype=np.uint64))
     count = int(1.0 * sr)
     res = {}
-    for mode, min_streams in (("single", "100000000"), ("rounds", "1"), ("sched", "1")):
+    for mode, min_streams in (("single", "100000000"), ("rounds", "1"), ("sched", "1"), ("block", "1")):
         monkeypatch.setenv("NVSP_ROUNDS_MIN_STREAMS", min_streams)
         monkeypatch.setenv("NVSP_GROUPS", "3")
-        monkeypatch.setenv("NVSP_SCHED", "persistent" if mode == "sched" else "rounds")
+        monkeypatch.setenv("NVSP_SCHED", {"sched": "rings", "block": "block"}.get(mode, "rounds"))
+        monkeypatch.setenv("NVSP_BLOCK_MIN_STREAMS", "1")
+        monkeypatch.setenv("NVSP_BLOCK_BLOCKS", "3")   # 68 streams per block on 8 workers: the queues fill and drain
         monkeypatch.setenv("NVSP_SCHED_BLOCKS", "3")  # fewer workers than stream batches: streams queue up in the rings
         monkeypatch.setenv("NVSP_SCHED_HOLD_TICKS", "256")  # several chunks of both classes per stream in a 1-s render
         monkeypatch.setenv("NVSP_SCHED_GEN_TICKS", "128")
@@ -161,8 +164,10 @@ def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
         b.close()
     assert res["rounds"][3] > res["single"][3] + 50, "the rounds path did not run"
     assert res["sched"][3] == res["single"][3] + 2 * 3, "the stream scheduler did not run (seed + workers + finalize per call)"
+    assert res["block"][3] == res["single"][3] + 2 * 3, "the block scheduler did not run (import + workers + export per call)"
     for k in range(3):
         np.testing.assert_array_equal(res["single"][k], res["sched"][k])
+        np.testing.assert_array_equal(res["single"][k], res["block"][k])
     np.testing.assert_array_equal(res["single"][1], res["rounds"][1])
     np.testing.assert_array_equal(res["single"][2], res["rounds"][2])
     np.testing.assert_array_equal(res["single"][0], res["rounds"][0])

@@ -35,5 +35,19 @@ c1)  # baseline data of round 2: GPU suite, A/B of cheap scheduler variants, ncu
 		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline > $O/ncu_long.log 2>&1; echo "ncu long rc=$?"; ls -la $O/prof_long.ncu-rep
 	timeout 120 tools/d2h_probe 1 1024 6 > $O/d2h_1gpu.json 2>&1; cat $O/d2h_1gpu.json
 	;;
+c2)  # parity round: whole GPU suite with the new tests, smoke, the long bench line with its full-hour oracle check
+	timeout 900 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -15 $O/pytest_gpu.log
+	timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -8 $O/smoke.log
+	timeout 400 python bench.py --workload long --steps 3 --warmup 3 > $O/bench_long.json 2> $O/bench_long.err; echo "bench long rc=$?"; cut -c1-1500 $O/bench_long.json; tail -3 $O/bench_long.err
+	;;
+san)  # compute-sanitizer on the long path (short stream)
+	timeout 300 compute-sanitizer --tool memcheck --print-limit 8 python -c "
+import numpy as np
+from nvspeechplayer_b200 import player, workloads
+fr, m, f, nul, ux = workloads.random_stream(9, 0.5, 22050)
+out = player.synthesize_long(22050, fr, m, f, nul, seed=4, stream_id=9, chunk_ticks=256)
+print('ok', len(out[0]))
+" > $O/san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     at\|^=========         in" $O/san.log | head -60
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
