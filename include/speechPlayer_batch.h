@@ -79,6 +79,21 @@ int speechPlayer_batchSynthesizeDevice(speechPlayer_batch_t *batch, unsigned int
 long long speechPlayer_batchSynthesizeHost(speechPlayer_batch_t *batch, unsigned int sampleCount, sample *out,
                                            unsigned int *samplesWritten);
 
+/* Output sinks on the device: what the reference's consumers do with the int16 buffers, without
+ * leaving HBM.  Both read the [numStreams][rowStride] int16 output of speechPlayer_batchSynthesizeDevice (or any int16 rows)
+ * and are asynchronous on cudaStream.
+ *   ...ToFloat32Device : sample / 32767.0 rounded to float32 -- exactly what reference lavPlayer.py:17 feeds its audio graph
+ *                        (numpy int16 / 32767.0, taken as float32).  dOutFloat: device float [numStreams][outStride].
+ *   ...ConcatenateDevice: the ragged rows packed back to back in stream order (reference nvdaAddon/synthDrivers/nvSpeechPlayer/
+ *                        __init__.py:70-73 appends every buffer it pulls to one audio stream): stream s contributes its first
+ *                        dSamplesWritten[s] samples (device u32 [numStreams]; NULL = sampleCount each).  dOffsets: device
+ *                        int64 [numStreams + 1], filled with the exclusive prefix sum (dOffsets[numStreams] = total samples);
+ *                        dOutPacked: device int16, at least the sum of the counts (numStreams * sampleCount always suffices). */
+int speechPlayer_batchToFloat32Device(const void *dPcm, size_t rowStride, unsigned int numStreams, unsigned int sampleCount,
+                                      void *dOutFloat, size_t outStride, void *cudaStream);
+int speechPlayer_batchConcatenateDevice(const void *dPcm, size_t rowStride, unsigned int numStreams, unsigned int sampleCount,
+                                        const void *dSamplesWritten, void *dOffsets, void *dOutPacked, void *cudaStream);
+
 /* getLastIndex of every stream (host int32 [numStreams]); synchronises with the batch's last launch. */
 int speechPlayer_batchGetLastIndices(speechPlayer_batch_t *batch, int *lastIndex);
 

@@ -1258,6 +1258,125 @@ long long speechPlayer_batchSynthesizeHost(speechPlayer_batch_t *b, unsigned int
 	return r;
 }
 
+// ---- output sinks on the device (include/speechPlayer_batch.h) ----
+}  // extern "C"
+
+// int16 -> float32 as reference lavPlayer.py:17 does it: (double)sample / 32767.0, then rounded to float.  HBM-bound: 2 bytes
+// in, 4 bytes out per sample; one thread converts 8 samples (one 16-byte load, two 16-byte stores) when the rows allow it.
+__global__ void __launch_bounds__(256)
+pcm_to_float32_kernel(const int16_t *__restrict__ pcm, size_t rowStride, uint32_t sampleCount, float *__restrict__ out, size_t outStride,
+                      bool vec) {
+	const uint32_t s = blockIdx.y;
+	const int16_t *row = pcm + (size_t)s * rowStride;
+	float *orow = out + (size_t)s * outStride;
+	auto conv = [](int v) { return (float)((double)v / 32767.0); };
+	if (vec) {
+		const uint32_t groups = sampleCount / 8;
+		for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+			const uint4 w = reinterpret_cast<const uint4 *>(row)[g];
+			const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+			float f[8];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) { f[2 * k] = conv((int16_t)(ww[k] & 0xffffu)); f[2 * k + 1] = conv((int16_t)(ww[k] >> 16)); }
+			reinterpret_cast<float4 *>(orow)[2 * g] = make_float4(f[0], f[1], f[2], f[3]);
+			reinterpret_cast<float4 *>(orow)[2 * g + 1] = make_float4(f[4], f[5], f[6], f[7]);
+		}
+		for (uint32_t i = groups * 8 + blockIdx.x * blockDim.x + threadIdx.x; i < sampleCount; i += gridDim.x * blockDim.x) orow[i] = conv(row[i]);
+	} else {
+		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sampleCount; i += gridDim.x * blockDim.x) orow[i] = conv(row[i]);
+	}
+}
+
+// exclusive prefix sum of the per-stream sample counts (one block; numStreams is at most a few million)
+__global__ void __launch_bounds__(1024)
+concat_offsets_kernel(const uint32_t *__restrict__ written, uint32_t sampleCount, uint32_t n, int64_t *__restrict__ offsets) {
+	__shared__ int64_t warpTotal[32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t per = (n + 1023) / 1024;
+	const uint32_t c0 = (uint32_t)tid * per < n ? (uint32_t)tid * per : n, c1 = c0 + per < n ? c0 + per : n;
+	int64_t run = 0;
+	for (uint32_t c = c0; c < c1; ++c) run += written ? (int64_t)(written[c] < sampleCount ? written[c] : sampleCount) : (int64_t)sampleCount;
+	int64_t inc = run;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		int64_t up = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) inc += up;
+	}
+	if (lane == 31) warpTotal[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		int64_t w = warpTotal[lane];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			int64_t up = __shfl_up_sync(0xffffffffu, w, d);
+			if (lane >= d) w += up;
+		}
+		warpTotal[lane] = w;
+	}
+	__syncthreads();
+	int64_t pos = inc - run + (warp > 0 ? warpTotal[warp - 1] : 0);
+	for (uint32_t c = c0; c < c1; ++c) {
+		offsets[c] = pos;
+		pos += written ? (int64_t)(written[c] < sampleCount ? written[c] : sampleCount) : (int64_t)sampleCount;
+	}
+	if (tid == 1023) offsets[n] = warpTotal[31];
+}
+
+// one block row per stream: its first offsets[s+1]-offsets[s] samples go to packed + offsets[s] (destinations are 2-byte
+// aligned only; 32-bit stores from the first even destination index on)
+__global__ void __launch_bounds__(256)
+concat_gather_kernel(const int16_t *__restrict__ pcm, size_t rowStride, const int64_t *__restrict__ offsets, int16_t *__restrict__ packed) {
+	const uint32_t s = blockIdx.y;
+	const int64_t o0 = offsets[s], cnt = offsets[s + 1] - o0;
+	const int16_t *row = pcm + (size_t)s * rowStride;
+	int16_t *dst = packed + o0;
+	const int64_t head = (o0 & 1) ? 1 : 0;  // samples before the first 4-byte aligned destination
+	if (blockIdx.x == 0 && threadIdx.x == 0 && head && cnt > 0) dst[0] = row[0];
+	const int64_t pairs = (cnt - head) / 2;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint32_t lo = (uint16_t)row[head + 2 * i], hi = (uint16_t)row[head + 2 * i + 1];
+		*reinterpret_cast<uint32_t *>(dst + head + 2 * i) = lo | (hi << 16);
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0 && ((cnt - head) & 1) && cnt > head) dst[cnt - 1] = row[cnt - 1];
+}
+
+extern "C" {
+
+int speechPlayer_batchToFloat32Device(const void *dPcm, size_t rowStride, unsigned int numStreams, unsigned int sampleCount,
+                                      void *dOutFloat, size_t outStride, void *cudaStream) {
+	if (!dPcm || !dOutFloat) return fail("null argument");
+	if (rowStride < sampleCount || outStride < sampleCount) return fail("stride < sampleCount");
+	if (numStreams == 0 || sampleCount == 0) return 0;
+	const bool vec = (reinterpret_cast<uintptr_t>(dPcm) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dOutFloat) & 15u) == 0 &&
+	                 rowStride % 8 == 0 && outStride % 4 == 0;
+	const unsigned gx = (unsigned)std::min<size_t>(((size_t)sampleCount / 8 + 255) / 256 + 1, 64);
+	for (unsigned s0 = 0; s0 < numStreams; s0 += 65535u) {
+		const unsigned ny = std::min(numStreams - s0, 65535u);
+		pcm_to_float32_kernel<<<dim3(gx, ny), 256, 0, static_cast<cudaStream_t>(cudaStream)>>>(
+		    static_cast<const int16_t *>(dPcm) + (size_t)s0 * rowStride, rowStride, sampleCount, static_cast<float *>(dOutFloat) + (size_t)s0 * outStride,
+		    outStride, vec);
+	}
+	CU(cudaGetLastError());
+	return 0;
+}
+
+int speechPlayer_batchConcatenateDevice(const void *dPcm, size_t rowStride, unsigned int numStreams, unsigned int sampleCount,
+                                        const void *dSamplesWritten, void *dOffsets, void *dOutPacked, void *cudaStream) {
+	if (!dPcm || !dOffsets || !dOutPacked) return fail("null argument");
+	if (rowStride < sampleCount) return fail("rowStride < sampleCount");
+	if (numStreams == 0) return 0;
+	cudaStream_t stream = static_cast<cudaStream_t>(cudaStream);
+	concat_offsets_kernel<<<1, 1024, 0, stream>>>(static_cast<const uint32_t *>(dSamplesWritten), sampleCount, numStreams, static_cast<int64_t *>(dOffsets));
+	const unsigned gx = (unsigned)std::min<size_t>(((size_t)sampleCount / 2 + 255) / 256 + 1, 32);
+	for (unsigned s0 = 0; s0 < numStreams; s0 += 65535u) {
+		const unsigned ny = std::min(numStreams - s0, 65535u);
+		concat_gather_kernel<<<dim3(gx, ny), 256, 0, stream>>>(static_cast<const int16_t *>(dPcm) + (size_t)s0 * rowStride, rowStride,
+		                                                       static_cast<const int64_t *>(dOffsets) + s0, static_cast<int16_t *>(dOutPacked));
+	}
+	CU(cudaGetLastError());
+	return 0;
+}
+
 int speechPlayer_batchGetLastIndices(speechPlayer_batch_t *b, int *lastIndex) {
 	if (!b || !lastIndex) return fail("null argument");
 	std::lock_guard<std::mutex> lk(b->mu);
@@ -1302,7 +1421,7 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 		const char *e = getenv("NVSP_LONG_CHUNK");
 		chunkTicks = (e && *e) ? (unsigned)strtoul(e, nullptr, 0) : 1024u;
 	}
-	chunkTicks = std::max(chunkTicks, 64u);
+	chunkTicks = std::max(chunkTicks, 64u) & ~31u;  // whole 32-tick tiles (klatt_long.cu stage kernels)
 	const size_t n = numFrames;
 	DevBuf dFrames, dMin, dFade, dNull, dOff, dPlans, dStart, dPrev, dPitch, dVib;
 	DevBuf sig, maps, st, ph, pcm, phChunks, phStart, phFail;  // (function scope: `cleanup` below releases them at exit)

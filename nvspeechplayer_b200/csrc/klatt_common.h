@@ -130,7 +130,7 @@ struct GenStateF32 {
 };
 
 // The same two blocks WITHOUT what a pre-queued (planned) FP32 stream never touches -- the three 47-double frames of the
-// frame manager and the inline fade plan: 472 bytes instead of 2.4 KB.  The block scheduler (klatt_f32_block.cu) keeps the
+// frame manager and the inline fade plan: 544 bytes instead of 2.4 KB.  The block scheduler (klatt_f32_block.cu) keeps the
 // streams of a call in a dense array of these (65 536 streams: 31 MB, resident in the 126 MB L2) and switches a stream
 // between the hold, fade and general loops every 64..128 ticks; members keep the names of the full structures so the
 // render bodies of klatt_f32_core.cuh work on either.
@@ -151,10 +151,12 @@ struct GenStateF32Lite {
 	float dir[kNumDirect];
 	float zc[2 * kNumResonators];
 };
-struct alignas(16) StreamStateLite {
+struct alignas(8) StreamStateLite {  // (8, not 16: the copies staged in shared memory sit on an 8-byte aligned stride)
 	FrameMgrLite fm;
 	GenStateF32Lite f32;
 };
+
+static_assert(sizeof(StreamStateLite) % 16 == 0, "records are copied with 16-byte accesses");
 
 struct StreamState {
 	FrameMgrState fm;

@@ -12,7 +12,11 @@
 // Here a stream belongs to ONE thread block for the whole call (block b owns streams b, b + grid, b + 2 grid, ...), one
 // block of 16 warps = 8 workers per SM:
 //   * its state lives in a dense array of 544-byte StreamStateLite records (35 MB for 65 536 streams: L2-resident; only the
-//     owning SM ever touches a record, so plain cached loads are coherent and a fence.cta orders a hand-over);
+//     owning SM ever touches a record, so plain cached loads are coherent and a fence.cta orders a hand-over).  A worker
+//     copies the 32 records of a cell into shared memory with coalesced 16-byte accesses, the render loops load and store
+//     their state THERE, and the records go back the same way (the first version let every lane read its own record word
+//     by word: 260 requests x 32 sectors per cell saturated the L1 and made a hold tick 2.4 x slower than under the ring
+//     scheduler);
 //   * the block sorts its own streams: three queues in shared memory (hold / fade / general), one spin lock, no global
 //     atomics, no device-wide fences; a worker pops up to 32 streams of the fullest class, renders ONE CELL of them and
 //     pushes them back under the class their state now shows;
@@ -34,6 +38,9 @@ constexpr int kBlkThreads = 512, kBlkWorkers = kBlkThreads / 64;
 constexpr uint32_t kClsHold = 0, kClsFade = 1, kClsGen = 2, kClsDone = 3, kClsExit = 4;
 constexpr uint32_t kCellTicks = kCoarseTicks;  // fade and general cells
 constexpr uint32_t kNoStream = 0xffffu;
+constexpr uint32_t kRecBytes = sizeof(StreamStateLite), kRecPieces = kRecBytes / 16;  // 544 B = 34 pieces of 16 bytes
+constexpr uint32_t kStageStride = kRecBytes + 8;  // bytes between the staged records of neighbouring lanes: 138 words, 2-way conflicts at most
+constexpr uint32_t kStageBytes = 32 * kStageStride;  // per worker
 
 struct BlockCtl {
 	uint32_t lock;
@@ -156,7 +163,8 @@ klatt_block_export_kernel(const StreamDesc *__restrict__ descs, uint32_t numStre
 #define BPROF_LAP(acc)
 #endif
 
-// dynamic shared memory: [hand-over buffers: 8 workers x 8 KB][BlockCtl][ring[3][cap] of uint16 local stream indices]
+// dynamic shared memory: [hand-over buffers: 8 workers x 8 KB][staged records: 8 workers x 32 x 552 B][BlockCtl][ring[3][cap] of
+// uint16 local stream indices]
 __global__ void __launch_bounds__(kBlkThreads, 1)
 klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__restrict__ lite, uint32_t numStreams, int sampleRate,
                        uint32_t sampleCount, uint32_t holdTicks, int16_t *__restrict__ out, size_t rowStride,
@@ -164,7 +172,8 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
                        uint32_t *__restrict__ fault) {
 	extern __shared__ uint4 smem[];
 	uint4 *xbuf = smem;
-	BlockCtl *ctl = reinterpret_cast<BlockCtl *>(smem + kBlkWorkers * 2 * kGroupTicks * 32);
+	unsigned char *stageAll = reinterpret_cast<unsigned char *>(smem + kBlkWorkers * 2 * kGroupTicks * 32);
+	BlockCtl *ctl = reinterpret_cast<BlockCtl *>(stageAll + kBlkWorkers * kStageBytes);
 	uint16_t *ring = reinterpret_cast<uint16_t *>(ctl + 1);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
 	const uint32_t worker = warp >> 1;
@@ -193,6 +202,9 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 	XchgBlk xc{(uint32_t)__cvta_generic_to_shared(&xbuf[worker * 2 * kGroupTicks * 32 + lane]), 1u + worker};
 	uint32_t *work = ctl->work[worker];
 	StreamStateLite *dummy = lite + numStreams + (size_t)blockIdx.x * kBlkWorkers + worker;
+	unsigned char *stage = stageAll + worker * kStageBytes;
+	StreamStateLite *st = reinterpret_cast<StreamStateLite *>(stage + lane * kStageStride);  // this lane's stream while a cell runs
+	const uint32_t tw = tid & 63u;  // thread of the worker
 #ifdef KLATT_BLOCK_PROFILE
 	long long tClaim = 0, tCls[3] = {0, 0, 0}, tPush = 0, nCls[3] = {0, 0, 0}, nLanes = 0;
 	long long t0 = clock64();
@@ -202,11 +214,18 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 			uint32_t cls = kClsExit, n = 0, base = 0;
 			if (lane == 0) {
 				uint32_t idleSpins = 0;
+				unsigned long long idleSince = 0;
 				for (;;) {
 					lockCtl(ctl);
 					const uint32_t c0 = ctl->count[0], c1 = ctl->count[1], c2 = ctl->count[2];
-					// the fullest class; a class is served with a partial warp only when nothing has 32 streams waiting
-					uint32_t pick = (c2 >= c1 && c2 >= c0) ? 2u : (c1 >= c0 ? 1u : 0u);
+					// a full warp of the RAREST class first (general, then fade, then hold: a stream that waits for 31 others of
+					// its kind must not also wait behind the majority); a partial warp of the fullest class only when no class has
+					// 32 streams waiting
+					uint32_t pick;
+					if (c2 >= 32u) pick = 2u;
+					else if (c1 >= 32u) pick = 1u;
+					else if (c0 >= 32u) pick = 0u;
+					else pick = (c2 >= c1 && c2 >= c0) ? 2u : (c1 >= c0 ? 1u : 0u);
 					const uint32_t have = pick == 2u ? c2 : (pick == 1u ? c1 : c0);
 					if (have > 0u) {
 						n = have < 32u ? have : 32u;
@@ -221,9 +240,13 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 					unlockCtl(ctl);
 					if (live == 0u) break;  // cls == kClsExit
 					__nanosleep(256);
-					// watchdog: a cell takes well under a millisecond; a worker that finds nothing to do for ~2 s while streams
+					// watchdog: a cell takes well under a millisecond; a worker that finds nothing to do for 10 s while streams
 					// are still unaccounted for declares the call failed instead of hanging the GPU
-					if (++idleSpins > (1u << 23)) {
+					if ((++idleSpins & 1023u) == 0u) {
+						unsigned long long now;
+						asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+						if (idleSince == 0) idleSince = now;
+						if (now - idleSince <= 10ull * 1000 * 1000 * 1000) continue;
 						if (fault) *fault = 1u;
 						lockCtl(ctl);
 						ctl->live = 0u;
@@ -246,8 +269,20 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 		if (cls == kClsExit) break;
 		const bool valid = l != kNoStream;
 		const uint32_t s = valid ? blockIdx.x + l * gridDim.x : numStreams;
-		StreamStateLite *st = valid ? lite + s : dummy;
 		const StreamDesc &desc = descs[s];
+		// ---- the records of this cell: global -> shared, both warps, 16 bytes per thread and step, consecutive pieces of a record
+		// on consecutive threads (idle lanes get the worker's dummy stream) ----
+#pragma unroll 1
+		for (uint32_t idx = tw; idx < 32u * kRecPieces; idx += 64u) {
+			const uint32_t r = idx / kRecPieces, p = idx - r * kRecPieces;
+			const uint32_t lr = work[r];
+			const StreamStateLite *src = lr != kNoStream ? lite + (blockIdx.x + lr * gridDim.x) : dummy;
+			const uint4 v = reinterpret_cast<const uint4 *>(src)[p];
+			uint2 *dst = reinterpret_cast<uint2 *>(stage + r * kStageStride + p * 16u);
+			dst[0] = make_uint2(v.x, v.y);
+			dst[1] = make_uint2(v.z, v.w);
+		}
+		xc.sync();
 		if (cls == kClsHold) {
 			if (cascade) {
 				int16_t *row = valid ? out + (size_t)s * rowStride + st->f32.callPos : scratchRow;
@@ -291,15 +326,28 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 				renderGeneralF32T<kRoleParallel>(st->fm, st->f32, desc, sampleRate, ticks, kCellTicks, no, noise, xc, &lastUserIndex, &qHead);
 			}
 		}
+		xc.sync();  // both halves of every stream of this cell are in the staged records
+		uint32_t next = kClsExit;
+		if (cascade && valid) next = classifyLite(*st, sampleCount, holdTicks);
+		// ---- shared -> global (the idle lanes' dummy is not written back) ----
+#pragma unroll 1
+		for (uint32_t idx = tw; idx < 32u * kRecPieces; idx += 64u) {
+			const uint32_t r = idx / kRecPieces, p = idx - r * kRecPieces;
+			const uint32_t lr = work[r];
+			if (lr != kNoStream) {
+				const uint2 *src = reinterpret_cast<const uint2 *>(stage + r * kStageStride + p * 16u);
+				const uint2 a = src[0], b = src[1];
+				reinterpret_cast<uint4 *>(lite + (blockIdx.x + lr * gridDim.x))[p] = make_uint4(a.x, a.y, b.x, b.y);
+			}
+		}
 		__threadfence_block();
-		xc.sync();  // both halves of every stream of this cell are stored
+		xc.sync();  // the records are back in the array: the streams may be handed on
 #ifdef KLATT_BLOCK_PROFILE
 		BPROF_LAP(tCls[cls])
 		nCls[cls]++;
 		nLanes += __popc(__ballot_sync(0xffffffffu, valid));
 #endif
 		if (cascade) {
-			const uint32_t next = valid ? classifyLite(*st, sampleCount, holdTicks) : kClsExit;
 			const unsigned below = (1u << lane) - 1u;
 			const unsigned m0 = __ballot_sync(0xffffffffu, next == kClsHold), m1 = __ballot_sync(0xffffffffu, next == kClsFade);
 			const unsigned m2 = __ballot_sync(0xffffffffu, next == kClsGen), mD = __ballot_sync(0xffffffffu, next == kClsDone);
@@ -333,14 +381,15 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 
 // bytes of dynamic shared memory for a block that owns up to `cap` streams
 static size_t blockSmemBytes(uint32_t cap) {
-	return sizeof(uint4) * kBlkWorkers * 2 * kGroupTicks * 32 + sizeof(BlockCtl) + sizeof(uint16_t) * 3 * (size_t)cap;
+	return sizeof(uint4) * kBlkWorkers * 2 * kGroupTicks * 32 + (size_t)kBlkWorkers * kStageBytes + sizeof(BlockCtl) +
+	       sizeof(uint16_t) * 3 * (size_t)cap;
 }
 
 // the block scheduler can take a batch when every block's share fits the 16-bit local indices and the queues fit shared memory
 bool klattF32BlockCanTake(uint32_t numStreams, uint32_t numBlocks) {
 	if (numBlocks == 0) return false;
 	const uint32_t owned = (numStreams + numBlocks - 1) / numBlocks;
-	return owned <= 8192u;
+	return owned <= 2048u;  // 3 queues of 16-bit indices next to 64 KB of hand-over buffers and 138 KB of staged records
 }
 size_t klattF32BlockLiteBytes(uint32_t numStreams, uint32_t numBlocks) {
 	return sizeof(StreamStateLite) * ((size_t)numStreams + (size_t)numBlocks * kBlkWorkers);

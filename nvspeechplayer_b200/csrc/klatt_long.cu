@@ -213,49 +213,81 @@ struct VibWalk {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-// timeline: one thread walks the queue once (a request per iteration; the per-tick work is all in the other kernels)
+// timeline: the queue is walked once, a request per step (the per-tick work is all in the other kernels).  The walk is a
+// serial chain (start ticks, the pitch each request inherits, the vibrato phase), but what it READS is not: one block loads
+// a tile of requests into shared memory with coalesced accesses, thread 0 runs the chain over the tile out of shared memory,
+// and the block writes the tile's results back (round 1 walked global memory directly: 39 ms for the 40 072 requests of
+// config 4, 45 % of the whole call, all of it load latency).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void klatt_long_timeline_kernel(LongStream L) {
-	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+constexpr int kTimelineTile = 256;
+__global__ void __launch_bounds__(kTimelineTile)
+klatt_long_timeline_kernel(LongStream L) {
+	__shared__ uint32_t sM[kTimelineTile], sF[kTimelineTile];
+	__shared__ uint8_t sNull[kTimelineTile];
+	__shared__ double sP0[kTimelineTile], sP1[kTimelineTile];
+	__shared__ int64_t sV0[kTimelineTile], sVs[kTimelineTile], sVF[kTimelineTile];
+	__shared__ uint64_t oStart[kTimelineTile], oVib[kTimelineTile];
+	__shared__ int32_t oPrev[kTimelineTile];
+	__shared__ double oPop[kTimelineTile], oOld[kTimelineTile], oNew[kTimelineTile], oInc[kTimelineTile];
+	// the chain's state (thread 0 only)
 	uint64_t t = 0, vibPos = 0;
 	int32_t prevReal = -1;
 	bool oldIsNull = true;
 	double pitchCur = 0.0;
 	int64_t vPrev = 0;
-	for (uint32_t j = 0; j < L.nReq; ++j) {
-		const uint64_t M = L.minDur[j];
-		const uint32_t fd = L.fadeDur[j];
-		const uint64_t F = fd > 1u ? fd : 1u;
-		const bool null = reqIsNull(L, j);
-		L.start[j] = t;
-		L.prevReal[j] = prevReal;
-		L.pitchPop[j] = pitchCur;
-		double pOld = pitchCur, pNew, inc;
-		if (null) {  // src/frame.cpp:59-63
-			pNew = pitchCur;
-			inc = 0.0;
-		} else {
-			const double *fr = L.frames + (size_t)j * kNumParams;
-			pNew = fr[kVoicePitch];
-			inc = (fr[kEndVoicePitch] - fr[kVoicePitch]) / (double)M;  // src/frame.cpp:98
-			if (oldIsNull) pOld = pNew;                                // :64-67
+	const int tid = threadIdx.x;
+	for (uint32_t base = 0; base < L.nReq; base += kTimelineTile) {
+		const uint32_t j = base + tid;
+		if (j < L.nReq) {
+			sM[tid] = L.minDur[j];
+			sF[tid] = L.fadeDur[j];
+			sNull[tid] = reqIsNull(L, j) ? 1 : 0;
+			sP0[tid] = L.frames[(size_t)j * kNumParams + kVoicePitch];
+			sP1[tid] = L.frames[(size_t)j * kNumParams + kEndVoicePitch];
+			const FadePlanF32 &p = L.plans[j];
+			sV0[tid] = p.vibInc0; sVs[tid] = p.vibIncStep; sVF[tid] = p.vibIncFinal;
 		}
-		pNew += inc * (double)F;  // :71
-		L.pitchOld[j] = pOld; L.pitchNew[j] = pNew; L.pitchInc[j] = inc;
-		const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
-		const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
-		pitchCur = glideExact(landing, inc, occ - F - 2);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
-		L.vibPosStart[j] = vibPos;
-		const FadePlanF32 &p = L.plans[j];
-		uint64_t s = (uint64_t)vPrev + (F - 1) * (uint64_t)p.vibInc0 + (uint64_t)p.vibIncStep * ((F - 1) * F / 2) +
-		             (occ - F) * (uint64_t)p.vibIncFinal;
-		vibPos += s;
-		vPrev = p.vibIncFinal;
-		oldIsNull = null;
-		if (!null) prevReal = (int32_t)j;
-		t += occ;
+		__syncthreads();
+		if (tid == 0) {
+			const uint32_t n = L.nReq - base < (uint32_t)kTimelineTile ? L.nReq - base : (uint32_t)kTimelineTile;
+			for (uint32_t k = 0; k < n; ++k) {
+				const uint64_t M = sM[k];
+				const uint64_t F = sF[k] > 1u ? sF[k] : 1u;
+				const bool null = sNull[k] != 0;
+				oStart[k] = t;
+				oPrev[k] = prevReal;
+				oPop[k] = pitchCur;
+				double pOld = pitchCur, pNew, inc;
+				if (null) {  // src/frame.cpp:59-63
+					pNew = pitchCur;
+					inc = 0.0;
+				} else {
+					pNew = sP0[k];
+					inc = (sP1[k] - sP0[k]) / (double)M;  // src/frame.cpp:98
+					if (oldIsNull) pOld = pNew;            // :64-67
+				}
+				pNew += inc * (double)F;  // :71
+				oOld[k] = pOld; oNew[k] = pNew; oInc[k] = inc;
+				const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
+				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
+				pitchCur = glideExact(landing, inc, occ - F - 2);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
+				oVib[k] = vibPos;
+				vibPos += (uint64_t)vPrev + (F - 1) * (uint64_t)sV0[k] + (uint64_t)sVs[k] * ((F - 1) * F / 2) + (occ - F) * (uint64_t)sVF[k];
+				vPrev = sVF[k];
+				oldIsNull = null;
+				if (!null) prevReal = (int32_t)(base + k);
+				t += occ;
+			}
+		}
+		__syncthreads();
+		if (j < L.nReq) {
+			L.start[j] = oStart[tid]; L.prevReal[j] = oPrev[tid]; L.pitchPop[j] = oPop[tid];
+			L.pitchOld[j] = oOld[tid]; L.pitchNew[j] = oNew[tid]; L.pitchInc[j] = oInc[tid];
+			L.vibPosStart[j] = oVib[tid];
+		}
+		__syncthreads();
 	}
-	L.start[L.nReq] = t;
+	if (tid == 0) L.start[L.nReq] = t;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -535,19 +567,31 @@ struct Affine {
 //   kStageNasal   : in = ci, rN0 (FIR) then rNP (section 1), out = x after the caNP mix (:148-150)
 //   kStageCascade : in = x, section `res`, out = its output (:151-156)
 //   kStageLast    : like kStageCascade for r1, then (x + par) * outputGain * 4000, clamp, truncate (:207-208)
+// Memory: thread i of a warp walks chunk (w + i), i.e. addresses chunkTicks * 4 bytes apart -- a warp-wide access to tick t
+// of 32 chunks touches 32 different sectors (round 1: 8 x the algorithmic traffic on the stores, long_scoreboard 28 cycles
+// per issue).  The signals therefore move through a shared-memory tile per warp: 32 chunks x 32 ticks, loaded and stored as
+// 32 coalesced 128-byte rows (row r = 32 consecutive ticks of chunk w + r), read and written by the owning thread along
+// its row ([32][33]: conflict-free either way).
+constexpr int kStageBlock = 64;   // threads: two warps, three tiles each (in, par, out) = 25 KB of shared memory
+constexpr int kTile = 32;
 template <int STAGE, int PASS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kStageBlock)
 klatt_long_stage_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, int res, const float *__restrict__ in,
                         const float *__restrict__ par, Affine *__restrict__ maps, const float2 *__restrict__ startState,
                         float *__restrict__ out, int16_t *__restrict__ pcm) {
 	constexpr int NR = StageTraits<STAGE>::NR;
+	constexpr bool kHasPar = STAGE == kStageLast && PASS == 2, kHasOut = PASS == 2;
+	__shared__ float tIn[kStageBlock / 32][kTile][kTile + 1];
+	__shared__ float tPar[kHasPar ? kStageBlock / 32 : 1][kHasPar ? kTile : 1][kTile + 1];
+	__shared__ float tOut[kHasOut ? kStageBlock / 32 : 1][kHasOut ? kTile : 1][kTile + 1];
+	const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
 	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
-	if (ch >= numChunks) return;
+	const uint32_t warpChunk0 = ch - lane;  // first chunk of this warp
+	const bool live = ch < numChunks;
 	const uint64_t total = L.start[L.nReq];
-	const uint64_t t0 = (uint64_t)ch * chunkTicks;
+	const uint64_t t0 = live ? (uint64_t)ch * chunkTicks : total;
 	const uint64_t t1 = (t0 + chunkTicks < total) ? t0 + chunkTicks : total;
 	Cursor cur;
-	cur.seek(L, t0);
 	PoleWalk pw[NR], pw0;  // pw0: the FIR anti-resonator of the nasal stage
 	DirWalk mix[NR], extra;  // parallel: pa1..6 + bypass; nasal: caNP; last: outputGain
 	auto loadDirs = [&]() {
@@ -561,76 +605,110 @@ klatt_long_stage_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, i
 			extra.load(L, cur.j, dOutputGain);
 		}
 	};
-#pragma unroll
-	for (int k = 0; k < NR; ++k) pw[k].seek(L, cur.j, cur.c, cur.F, STAGE == kStageParallel ? kResParallel + k : res);
-	if (STAGE == kStageNasal) pw0.seek(L, cur.j, cur.c, cur.F, kResN0);
-	loadDirs();
-	uint32_t loaded = cur.j;
+	uint32_t loaded = 0;
 	float y[NR], d[NR];
 	float p00[NR], p01[NR], p10[NR], p11[NR];
 #pragma unroll
-	for (int k = 0; k < NR; ++k) {
-		if (PASS == 2) { float2 s = startState[(size_t)ch * NR + k]; y[k] = s.x; d[k] = s.y; }
-		else { y[k] = 0.0f; d[k] = 0.0f; p00[k] = 1.0f; p01[k] = 0.0f; p10[k] = 0.0f; p11[k] = 1.0f; }
-	}
-	// the FIR section needs the two inputs before the chunk
-	float in1 = 0.0f, in2 = 0.0f;
-	if (STAGE == kStageNasal) {
-		if (t0 >= 1) in1 = in[t0 - 1];
-		if (t0 >= 2) in2 = in[t0 - 2];
-	}
-	for (uint64_t t = t0; t < t1; ++t) {
-		const uint32_t j = cur.j, c = cur.c, F = cur.F;
-		float x = in[t];
-		const float xin = x;
-		if (STAGE == kStageNasal) {  // rN0 on inputs: src/speechWaveGenerator.cpp:129-135 with anti == true
-			pw0.tick(L, j, c, F, kResN0);
-			float a0, rho0;
-			pw0.coef(a0, rho0);
-			const float dprev = in1 - in2;
-			const float dx = x - in1;
-			const float dx1 = fmaf(-rho0, dprev, dprev);
-			x = n0InvAt(L, j, c, F) ? fmaf(dx - dx1, fastRcp(a0), in1) : fmaf(a0, dx, dx1 + in1);
-			in2 = in1;
-			in1 = xin;
-		}
-		float acc = 0.0f;
+	for (int k = 0; k < NR; ++k) { y[k] = 0.0f; d[k] = 0.0f; p00[k] = 1.0f; p01[k] = 0.0f; p10[k] = 0.0f; p11[k] = 1.0f; }
+	float in1 = 0.0f, in2 = 0.0f;  // the FIR section needs the two inputs before the chunk
+	if (live) {
+		cur.seek(L, t0);
 #pragma unroll
-		for (int k = 0; k < NR; ++k) {
-			pw[k].tick(L, j, c, F, STAGE == kStageParallel ? kResParallel + k : res);
-			float a, rho;
-			pw[k].coef(a, rho);
-			float w = fmaf(-rho, d[k], d[k]);
-			w = fmaf(-a, y[k], w);
-			const float dn = fmaf(a, x, w);
-			d[k] = dn;
-			y[k] += dn;
-			if (PASS == 1) {  // P <- A P with A = [[1-a, 1-rho], [-a, 1-rho]] acting on (y, d)
-				const float g = 1.0f - rho;
-				const float n10 = fmaf(-a, p00[k], g * p10[k]), n11 = fmaf(-a, p01[k], g * p11[k]);
-				p00[k] += n10; p01[k] += n11;
-				p10[k] = n10; p11[k] = n11;
-			}
-			if (STAGE == kStageParallel) acc = fmaf(y[k] - x, mix[k].at(c, F), acc);
-		}
+		for (int k = 0; k < NR; ++k) pw[k].seek(L, cur.j, cur.c, cur.F, STAGE == kStageParallel ? kResParallel + k : res);
+		if (STAGE == kStageNasal) pw0.seek(L, cur.j, cur.c, cur.F, kResN0);
+		loadDirs();
+		loaded = cur.j;
 		if (PASS == 2) {
-			if (STAGE == kStageParallel) {
-				out[t] = fmaf(x - acc, extra.at(c, F), acc);
-			} else if (STAGE == kStageNasal) {
-				out[t] = fmaf(y[0] - xin, extra.at(c, F), xin);
-			} else if (STAGE == kStageCascade) {
-				out[t] = y[0];
-			} else {
-				float s = (y[0] + par[t]) * (extra.at(c, F) * 4000.0f);
-				s = fminf(s, 32000.0f);
-				s = fmaxf(s, -32000.0f);
-				pcm[t] = (int16_t)(int)s;
+#pragma unroll
+			for (int k = 0; k < NR; ++k) { float2 s = startState[(size_t)ch * NR + k]; y[k] = s.x; d[k] = s.y; }
+		}
+		if (STAGE == kStageNasal) {
+			if (t0 >= 1) in1 = in[t0 - 1];
+			if (t0 >= 2) in2 = in[t0 - 2];
+		}
+	}
+	for (uint32_t tile = 0; tile < chunkTicks; tile += kTile) {
+		// ---- tile in: row r = ticks [tile, tile + 32) of chunk warpChunk0 + r ----
+#pragma unroll 4
+		for (int r = 0; r < kTile; ++r) {
+			const uint64_t g = (uint64_t)(warpChunk0 + r) * chunkTicks + tile + lane;
+			const bool ok = warpChunk0 + r < numChunks && g < total;
+			tIn[wib][r][lane] = ok ? in[g] : 0.0f;
+			if (kHasPar) tPar[wib][r][lane] = ok ? par[g] : 0.0f;
+		}
+		__syncwarp();
+		if (live) {
+			const uint64_t tb = t0 + tile;
+			for (int q = 0; q < kTile && tb + q < t1; ++q) {
+				const uint32_t j = cur.j, c = cur.c, F = cur.F;
+				float x = tIn[wib][lane][q];
+				const float xin = x;
+				if (STAGE == kStageNasal) {  // rN0 on inputs: src/speechWaveGenerator.cpp:129-135 with anti == true
+					pw0.tick(L, j, c, F, kResN0);
+					float a0, rho0;
+					pw0.coef(a0, rho0);
+					const float dprev = in1 - in2;
+					const float dx = x - in1;
+					const float dx1 = fmaf(-rho0, dprev, dprev);
+					x = n0InvAt(L, j, c, F) ? fmaf(dx - dx1, fastRcp(a0), in1) : fmaf(a0, dx, dx1 + in1);
+					in2 = in1;
+					in1 = xin;
+				}
+				float acc = 0.0f;
+#pragma unroll
+				for (int k = 0; k < NR; ++k) {
+					pw[k].tick(L, j, c, F, STAGE == kStageParallel ? kResParallel + k : res);
+					float a, rho;
+					pw[k].coef(a, rho);
+					float w = fmaf(-rho, d[k], d[k]);
+					w = fmaf(-a, y[k], w);
+					const float dn = fmaf(a, x, w);
+					d[k] = dn;
+					y[k] += dn;
+					if (PASS == 1) {  // P <- A P with A = [[1-a, 1-rho], [-a, 1-rho]] acting on (y, d)
+						const float g = 1.0f - rho;
+						const float n10 = fmaf(-a, p00[k], g * p10[k]), n11 = fmaf(-a, p01[k], g * p11[k]);
+						p00[k] += n10; p01[k] += n11;
+						p10[k] = n10; p11[k] = n11;
+					}
+					if (STAGE == kStageParallel) acc = fmaf(y[k] - x, mix[k].at(c, F), acc);
+				}
+				if (PASS == 2) {
+					float o;
+					if (STAGE == kStageParallel) {
+						o = fmaf(x - acc, extra.at(c, F), acc);
+					} else if (STAGE == kStageNasal) {
+						o = fmaf(y[0] - xin, extra.at(c, F), xin);
+					} else if (STAGE == kStageCascade) {
+						o = y[0];
+					} else {
+						float sgn = (y[0] + tPar[kHasPar ? wib : 0][kHasPar ? lane : 0][q]) * (extra.at(c, F) * 4000.0f);
+						sgn = fminf(sgn, 32000.0f);
+						sgn = fmaxf(sgn, -32000.0f);
+						o = (float)(int)sgn;  // the int16 value, exactly representable
+					}
+					tOut[kHasOut ? wib : 0][kHasOut ? lane : 0][q] = o;
+				}
+				cur.next(L);
+				if (cur.j != loaded && cur.j < L.nReq) { loadDirs(); loaded = cur.j; }
 			}
 		}
-		cur.next(L);
-		if (cur.j != loaded && cur.j < L.nReq) { loadDirs(); loaded = cur.j; }
+		__syncwarp();
+		// ---- tile out ----
+		if (PASS == 2) {
+#pragma unroll 4
+			for (int r = 0; r < kTile; ++r) {
+				const uint64_t g = (uint64_t)(warpChunk0 + r) * chunkTicks + tile + lane;
+				if (warpChunk0 + r < numChunks && g < total) {
+					const float o = tOut[kHasOut ? wib : 0][kHasOut ? r : 0][lane];
+					if (STAGE == kStageLast) pcm[g] = (int16_t)(int)o;
+					else out[g] = o;
+				}
+			}
+			__syncwarp();
+		}
 	}
-	if (PASS == 1) {
+	if (PASS == 1 && live) {
 #pragma unroll
 		for (int k = 0; k < NR; ++k) {
 			Affine m;
@@ -724,7 +802,7 @@ cudaError_t launchKlattPlan(const int64_t *offsets, uint32_t numStreams, uint64_
                             cudaStream_t stream);
 
 cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream) {
-	klatt_long_timeline_kernel<<<1, 1, 0, stream>>>(L);
+	klatt_long_timeline_kernel<<<1, kTimelineTile, 0, stream>>>(L);
 	return cudaGetLastError();
 }
 
@@ -738,6 +816,7 @@ cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint
 	if (totalTicks == 0) return cudaSuccess;
 	const uint32_t numChunks = (uint32_t)((totalTicks + chunkTicks - 1) / chunkTicks);
 	const dim3 grid((numChunks + 127) / 128), block(128);
+	const dim3 sgrid((numChunks + kStageBlock - 1) / kStageBlock), sblock(kStageBlock);
 	cudaError_t e = cudaMemsetAsync(fail, 0, sizeof(uint32_t), stream);
 	if (e != cudaSuccess) return e;
 	if (serialPhase) {
@@ -752,25 +831,25 @@ cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint
 	}
 	klatt_long_source_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, chunks, startP, fail, ci, pin);
 	// parallel bank
-	klatt_long_stage_kernel<kStageParallel, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, maps, nullptr, nullptr, nullptr);
+	klatt_long_stage_kernel<kStageParallel, 1><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, maps, nullptr, nullptr, nullptr);
 	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 6, startState);
-	klatt_long_stage_kernel<kStageParallel, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, nullptr, startState, par, nullptr);
+	klatt_long_stage_kernel<kStageParallel, 2><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, nullptr, startState, par, nullptr);
 	// rN0 + rNP
-	klatt_long_stage_kernel<kStageNasal, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResNP, ci, nullptr, maps, nullptr, nullptr, nullptr);
+	klatt_long_stage_kernel<kStageNasal, 1><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, kResNP, ci, nullptr, maps, nullptr, nullptr, nullptr);
 	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
-	klatt_long_stage_kernel<kStageNasal, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResNP, ci, nullptr, nullptr, startState, xa, nullptr);
+	klatt_long_stage_kernel<kStageNasal, 2><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, kResNP, ci, nullptr, nullptr, startState, xa, nullptr);
 	// r6 .. r2
 	float *src = xa, *dst = xb;
 	for (int r = kResCascade; r < kResParallel - 1; ++r) {
-		klatt_long_stage_kernel<kStageCascade, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, r, src, nullptr, maps, nullptr, nullptr, nullptr);
+		klatt_long_stage_kernel<kStageCascade, 1><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, r, src, nullptr, maps, nullptr, nullptr, nullptr);
 		klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
-		klatt_long_stage_kernel<kStageCascade, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, r, src, nullptr, nullptr, startState, dst, nullptr);
+		klatt_long_stage_kernel<kStageCascade, 2><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, r, src, nullptr, nullptr, startState, dst, nullptr);
 		float *tmp = src; src = dst; dst = tmp;
 	}
 	// r1 + output
-	klatt_long_stage_kernel<kStageLast, 1><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, maps, nullptr, nullptr, nullptr);
+	klatt_long_stage_kernel<kStageLast, 1><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, maps, nullptr, nullptr, nullptr);
 	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
-	klatt_long_stage_kernel<kStageLast, 2><<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, nullptr, startState, nullptr, pcm);
+	klatt_long_stage_kernel<kStageLast, 2><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, nullptr, startState, nullptr, pcm);
 	if (launchCounter) *launchCounter += 1 + 3 * 8;
 	return cudaGetLastError();
 }

@@ -89,6 +89,10 @@ def load_library():
     L.speechPlayer_batchSynthesizeDevice.argtypes = [vp, u32, vp, ctypes.c_size_t, vp, vp]
     L.speechPlayer_batchSynthesizeHost.restype = ctypes.c_longlong
     L.speechPlayer_batchSynthesizeHost.argtypes = [vp, u32, vp, vp]
+    L.speechPlayer_batchToFloat32Device.restype = i32
+    L.speechPlayer_batchToFloat32Device.argtypes = [vp, ctypes.c_size_t, u32, u32, vp, ctypes.c_size_t, vp]
+    L.speechPlayer_batchConcatenateDevice.restype = i32
+    L.speechPlayer_batchConcatenateDevice.argtypes = [vp, ctypes.c_size_t, u32, u32, vp, vp, vp, vp]
     L.speechPlayer_batchGetLastIndices.restype = i32
     L.speechPlayer_batchGetLastIndices.argtypes = [vp, vp]
     L.speechPlayer_batchGetLaunchStats.restype = i32
@@ -318,6 +322,19 @@ class Batch(object):
 # ----------------------------------------------------------------------------------------------
 # Output sinks: what the reference's demo players do with the int16 buffers
 # ----------------------------------------------------------------------------------------------
+def to_float32_device(d_pcm, row_stride, num_streams, num_samples, d_out, out_stride, cuda_stream=None):
+    """speechPlayer_batchToFloat32Device: int16 rows in HBM -> float32 rows in HBM (value / 32767.0, reference lavPlayer.py:17).
+    Arguments are raw device addresses."""
+    _check(load_library().speechPlayer_batchToFloat32Device(d_pcm, row_stride, num_streams, num_samples, d_out, out_stride, cuda_stream),
+           "speechPlayer_batchToFloat32Device")
+
+
+def concatenate_device(d_pcm, row_stride, num_streams, num_samples, d_written, d_offsets, d_packed, cuda_stream=None):
+    """speechPlayer_batchConcatenateDevice: the ragged rows packed back to back in stream order, offsets = exclusive scan."""
+    _check(load_library().speechPlayer_batchConcatenateDevice(d_pcm, row_stride, num_streams, num_samples, d_written, d_offsets,
+                                                              d_packed, cuda_stream), "speechPlayer_batchConcatenateDevice")
+
+
 def to_float32(pcm):
     """int16 -> float32 in [-1, 1] exactly as reference lavPlayer.py:17 feeds its audio graph (value / 32767.0)."""
     return (np.asarray(pcm, dtype=np.int16).astype(np.float64) / 32767.0).astype(np.float32)

@@ -16,7 +16,7 @@ try:
 except Exception as e:
     print('FAILED', e)
 ")"
-	grep -h "sched profile\|rror" $O/try_err.txt | head -4
+	grep -h "sched profile\|block profile\|rror" $O/try_err.txt | head -4
 }
 case "$stage" in
 c1)  # baseline data of round 2: GPU suite, A/B of cheap scheduler variants, ncu source-level capture, kernel (b) captures, D2H probe
@@ -48,6 +48,29 @@ fr, m, f, nul, ux = workloads.random_stream(9, 0.5, 22050)
 out = player.synthesize_long(22050, fr, m, f, nul, seed=4, stream_id=9, chunk_ticks=256)
 print('ok', len(out[0]))
 " > $O/san.log 2>&1; echo "sanitizer rc=$?"; grep -v "^=========     at\|^=========         in" $O/san.log | head -60
+	;;
+c3)  # block scheduler first light: suite, smoke, A/B against the ring scheduler, cell-length sweep, in-kernel cycle profile
+	timeout 900 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -12 $O/pytest_gpu.log
+	timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -9 $O/smoke.log
+	try "NVSP_SCHED=block"
+	try "NVSP_SCHED=rings"
+	try "NVSP_BLOCK_HOLD_TICKS=64"
+	try "NVSP_BLOCK_HOLD_TICKS=256"
+	try "NVSP_LIB=$PWD/tools/_variants/libbprof.so"
+	timeout 400 python bench.py --workload long --steps 3 --warmup 3 > $O/bench_long.json 2> $O/bench_long.err; echo "bench long rc=$?"; cut -c1-1800 $O/bench_long.json; tail -3 $O/bench_long.err
+	;;
+c4)  # block scheduler with staged records: bitwise test, A/B, cycle profile, ncu capture; kernel (b) after the timeline / tile fixes
+	timeout 600 python -m pytest tests/test_gpu_parity_f32.py tests/test_gpu_long.py -q -m gpu > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -5 $O/pytest_gpu.log
+	try "NVSP_SCHED=block"
+	try "NVSP_SCHED=rings"
+	try "NVSP_BLOCK_HOLD_TICKS=64"
+	try "NVSP_BLOCK_HOLD_TICKS=256"
+	try "NVSP_LIB=$PWD/tools/_variants/libbprof.so"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_f32_block_kernel -s 3 -c 1 -f -o $O/prof_block \
+		python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_block.log 2>&1; echo "ncu block rc=$?"; ls -la $O/prof_block.ncu-rep
+	timeout 400 python bench.py --workload long --steps 3 --warmup 3 > $O/bench_long.json 2> $O/bench_long.err; echo "bench long rc=$?"; cut -c1-400 $O/bench_long.json; tail -3 $O/bench_long.err
+	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/long_launches.csv \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/long_launches.log 2>&1; echo "ncu long list rc=$?"
 	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
