@@ -182,7 +182,7 @@ def long_arm(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("gloo")  # control plane only (barrier, max over ranks): no NCCL anywhere in this path
     sr, secs = args.long_rate, args.long_seconds
     fr, m, f, nul, ux = workloads.random_stream(4_000_000 + rank, secs, sr, seed=args.seed)
     n = int(round(secs * sr))
@@ -213,7 +213,7 @@ def long_arm(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     same = bool(np.array_equal(out[:100000], d_out[:100000].cpu().numpy()))
     if world > 1:
-        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
     if rank == 0:
@@ -281,7 +281,7 @@ def pull_arm(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("gloo")
     sr, pull = args.sample_rate, args.pull_samples
     warm, steps = max(args.warmup, 3), max(args.steps, 50)
     secs = (warm + steps + 2) * pull / sr
@@ -320,7 +320,7 @@ def pull_arm(args, rank, world, local_rank):
     ts = res["stream"]
     total_s = float(ts.sum())
     if world > 1:
-        t = torch.tensor([total_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_s], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_s = float(t[0])
     if rank == 0:
@@ -386,7 +386,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # The data plane has no collective at all (streams are independent: each rank renders its own stream ids into its own
+        # buffers); the control plane -- the barriers around the timed region and the max over ranks -- runs over gloo on the
+        # host, so no NCCL communicator is ever created (BASELINE north star: "no NCCL").
+        dist.init_process_group("gloo")
 
     def barrier():
         if world > 1:
@@ -490,12 +493,12 @@ def main():
     launches1, _ = batch.launch_stats()
     elapsed_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    rendered_all = torch.tensor([float(rendered)], dtype=torch.float64, device=dev)
+    rendered_all = torch.tensor([float(rendered)], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(rendered_all, op=dist.ReduceOp.SUM)
     rendered_all = float(rendered_all.item())                            # samples rendered per step, all ranks
@@ -536,7 +539,7 @@ def main():
         for _ in range(args.e2e_steps):
             e2e_step()
         barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e_launches = eb.launch_stats()[0]
@@ -570,6 +573,27 @@ def main():
                "exact_min": min(exacts), "max_abs_diff": worst, "oracle": "oracle/klatt_oracle.c (port, pinned to the compiled reference)",
                "bar": "fp32: <=1 LSB on >= 99.9 % and >= 60 dB; fp64: exact on >= 99.99 %"}
 
+    # which kernel rendered, and the DRAM traffic of one launch of it from the committed ncu capture of this very command
+    # (tools/ncu_summary.py --json; per launch = per step, like `achieved`)
+    sched = os.environ.get("NVSP_SCHED", "rings")
+    if prec != player.PRECISION_FP32:
+        kernel_name, cap = "klatt_batch_f64_kernel", None
+    elif sched == "rounds":
+        kernel_name, cap = "klatt_f32_hold_kernel + klatt_f32_general_pair_kernel (rounds)", None
+    elif sched != "block" or S < int(os.environ.get("NVSP_BLOCK_MIN_STREAMS", "16384")):
+        kernel_name, cap = "klatt_f32_sched_kernel (ring scheduler: hold and general chunks of all streams in one launch)", "r02_base_sched_traffic.json"
+    else:
+        kernel_name = ("klatt_f32_block_kernel (block scheduler: streams owned by one thread block, hold / fade / general cells, "
+                       "the whole call in one launch)")
+        cap = "r02_block_traffic.json"
+    traffic, traffic_src = None, None
+    if cap and args.workload == "batch" and S == 65536 and abs(secs - 10.0) < 1e-9:
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", cap)))["launches"][0]
+            traffic, traffic_src = rec["dram_bytes"], "profiles/" + cap + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch)"
+        except Exception:
+            pass
+
     if rank == 0:
         peaks = measured_peaks()
         achieved_tf = rendered * flops_per_sample / (kernel_ms * 1e-3) / 1e12  # dominant kernel alone
@@ -596,14 +620,11 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (klatt_f32_sched_kernel:
                          # one launch = one step of config 3), ncu --set full capture summarised in
                          # profiles/r01_v4_ncu_summary.txt; algorithmic bytes of that launch: 36.6 GB (int16 out + queues + plans)
-                         "traffic": 72.2e9 if (prec == player.PRECISION_FP32 and S == 65536 and args.workload == "batch"
-                                               and os.environ.get("NVSP_SCHED") != "rounds") else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "FFMA loop measured on this GPU in this run (MEASURED_PEAKS.json has no FP32 entry)"
                                         if fp32_peak_measured > 0 else "SMs x 128 x 2 x max SM clock",
                          "peak_nominal": nominal_tf, "frac_of_nominal": achieved_tf / nominal_tf,
-                         "kernel": ("klatt_batch_f64_kernel" if prec != player.PRECISION_FP32 else
-                                    "klatt_f32_hold_kernel + klatt_f32_general_pair_kernel (rounds)" if os.environ.get("NVSP_SCHED") == "rounds"
-                                    else "klatt_f32_sched_kernel (persistent stream scheduler: hold and general chunks of all streams in one launch)"),
+                         "kernel": kernel_name,
                          "flops_per_launch": rendered * flops_per_sample, "kernel_ms": kernel_ms,
                          "kernel_share_of_step": kernel_ms / ms_per_step},
             "roofline_hbm": {"bound": "hbm", "achieved": out_bytes_per_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

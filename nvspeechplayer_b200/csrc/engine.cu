@@ -81,7 +81,8 @@ cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream);
 cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
                                   uint64_t *startPhase, PhaseChunk *chunks, double *startP, uint32_t *fail, bool serialPhase,
                                   float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
-                                  float2 *startState, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream);
+                                  float2 *startState, void *scanScratch, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream);
+size_t klattLongScanScratchBytes(uint64_t numChunks);
 }  // namespace klatt
 
 using namespace klatt;
@@ -222,9 +223,10 @@ struct RoundsCtx {
 	DevBuf listHold, listGen, counters, scratchRow;
 	DevBuf ring, ctl;            // stream scheduler (persistent kernel, klatt_f32_sched.cu)
 	bool persistent = true;      // NVSP_SCHED=rounds selects the round-based launch sequence instead
-	// block scheduler (klatt_f32_block.cu): the default for large batches; NVSP_SCHED=rings (or persistent) keeps the ring scheduler
+	// block scheduler (klatt_f32_block.cu), NVSP_SCHED=block: an experiment of round 2 that is correct (bit-identical, tested) but
+	// slower than the ring scheduler -- its code does not fit the SM's 32 KB instruction cache
 	DevBuf lite, blockProf;
-	bool blockSched = true;
+	bool blockSched = false;
 	uint32_t blockHoldTicks = 128, blockMinStreams = 16384, blockBlocks = 0;
 	uint32_t *hostFault = nullptr;  // pinned: the scheduler watchdog's verdict of the last call
 	uint32_t schedHoldTicks = 512, schedGenTicks = 640, schedBlocks = 0;
@@ -247,7 +249,7 @@ struct RoundsCtx {
 		{
 			const char *e = getenv("NVSP_SCHED");
 			persistent = !(e && strcmp(e, "rounds") == 0);
-			blockSched = !(e && (strcmp(e, "rounds") == 0 || strcmp(e, "rings") == 0 || strcmp(e, "persistent") == 0));
+			blockSched = e && strcmp(e, "block") == 0;
 			blockHoldTicks = std::max<uint32_t>(envU("NVSP_BLOCK_HOLD_TICKS", 128) & ~63u, 64);
 			blockMinStreams = envU("NVSP_BLOCK_MIN_STREAMS", 16384);
 			schedGenTicks = std::max<uint32_t>(envU("NVSP_SCHED_GEN_TICKS", 640) & ~63u, 64);
@@ -1424,7 +1426,7 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 	chunkTicks = std::max(chunkTicks, 64u) & ~31u;  // whole 32-tick tiles (klatt_long.cu stage kernels)
 	const size_t n = numFrames;
 	DevBuf dFrames, dMin, dFade, dNull, dOff, dPlans, dStart, dPrev, dPitch, dVib;
-	DevBuf sig, maps, st, ph, pcm, phChunks, phStart, phFail;  // (function scope: `cleanup` below releases them at exit)
+	DevBuf sig, maps, st, ph, pcm, phChunks, phStart, phFail, scanTmp;  // (function scope: `cleanup` below releases them at exit)
 	struct Cleanup {
 		std::vector<DevBuf *> bufs;
 		cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1471,10 +1473,10 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 		const uint64_t numChunks = (ticks + chunkTicks - 1) / chunkTicks;
 		if (numChunks > 0x7fffffffull) return fail("stream too long for one call");
 		const size_t pad = ticks + 64;
-		cleanup.bufs.insert(cleanup.bufs.end(), {&sig, &maps, &st, &ph, &pcm, &phChunks, &phStart, &phFail});
+		cleanup.bufs.insert(cleanup.bufs.end(), {&sig, &maps, &st, &ph, &pcm, &phChunks, &phStart, &phFail, &scanTmp});
 		if (!sig.reserve(5 * pad * sizeof(float)) || !maps.reserve(numChunks * 6 * sizeof(Affine)) ||
 		    !st.reserve(numChunks * 6 * sizeof(float2)) || !ph.reserve(numChunks * 2 * sizeof(double)) ||
-		    !phChunks.reserve(numChunks * sizeof(PhaseChunk)) || !phStart.reserve(numChunks * sizeof(double)) || !phFail.reserve(16))
+		    !phChunks.reserve(numChunks * sizeof(PhaseChunk)) || !scanTmp.reserve(klattLongScanScratchBytes(numChunks)) || !phStart.reserve(numChunks * sizeof(double)) || !phFail.reserve(16))
 			return -1;
 		int16_t *dPcm = reinterpret_cast<int16_t *>(out);
 		if (!outOnDevice) {
@@ -1492,7 +1494,7 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 		for (;;) {
 			CU(launchKlattLongRender(L, ticks, chunkTicks, ph.as<uint64_t>(), ph.as<uint64_t>() + numChunks, phChunks.as<PhaseChunk>(),
 			                         phStart.as<double>(), phFail.as<uint32_t>(), serialPhase, f, f + pad, f + 2 * pad, f + 3 * pad,
-			                         f + 4 * pad, maps.as<Affine>(), st.as<float2>(), dPcm, &launches, stream));
+			                         f + 4 * pad, maps.as<Affine>(), st.as<float2>(), scanTmp.p, dPcm, &launches, stream));
 			CU(cudaEventRecord(cleanup.e1, stream));
 			uint32_t failed = 0;
 			CU(cudaMemcpyAsync(&failed, phFail.p, sizeof failed, cudaMemcpyDeviceToHost, stream));

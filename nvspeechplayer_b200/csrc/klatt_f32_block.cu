@@ -46,6 +46,7 @@ struct BlockCtl {
 	uint32_t lock;
 	uint32_t head[3], count[3];
 	uint32_t live;                      // owned streams that still have ticks to render in this call
+	uint32_t active[3];                 // workers currently rendering a cell of each class
 	uint32_t work[kBlkWorkers][36];     // per worker: 32 local stream indices, class
 };
 
@@ -168,8 +169,8 @@ klatt_block_export_kernel(const StreamDesc *__restrict__ descs, uint32_t numStre
 __global__ void __launch_bounds__(kBlkThreads, 1)
 klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__restrict__ lite, uint32_t numStreams, int sampleRate,
                        uint32_t sampleCount, uint32_t holdTicks, int16_t *__restrict__ out, size_t rowStride,
-                       int16_t *__restrict__ scratchRow, NoiseConfig noise, uint32_t cap, unsigned long long *__restrict__ prof,
-                       uint32_t *__restrict__ fault) {
+                       int16_t *__restrict__ scratchRow, NoiseConfig noise, uint32_t cap, uint32_t maxClasses,
+                       unsigned long long *__restrict__ prof, uint32_t *__restrict__ fault) {
 	extern __shared__ uint4 smem[];
 	uint4 *xbuf = smem;
 	unsigned char *stageAll = reinterpret_cast<unsigned char *>(smem + kBlkWorkers * 2 * kGroupTicks * 32);
@@ -185,7 +186,7 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 
 	if (tid == 0) {
 		ctl->lock = 0;
-		for (int c = 0; c < 3; ++c) { ctl->head[c] = 0; ctl->count[c] = 0; }
+		for (int c = 0; c < 3; ++c) { ctl->head[c] = 0; ctl->count[c] = 0; ctl->active[c] = 0; }
 		ctl->live = 0;
 	}
 	__syncthreads();
@@ -218,41 +219,49 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 				for (;;) {
 					lockCtl(ctl);
 					const uint32_t c0 = ctl->count[0], c1 = ctl->count[1], c2 = ctl->count[2];
-					// a full warp of the RAREST class first (general, then fade, then hold: a stream that waits for 31 others of
-					// its kind must not also wait behind the majority); a partial warp of the fullest class only when no class has
-					// 32 streams waiting
+					// Which class: at most `maxClasses` different classes are in flight on this SM at any time -- every class is two
+					// loops (cascade / parallel side), the SM's instruction cache holds 32 KB, and all six loops together are
+					// 36 KB (measured with no limit: 6.9 stall cycles per issue waiting for instructions).  Among the classes that
+					// are allowed: a full warp of the RAREST class first (general, then fade, then hold: a stream that waits for 31
+					// others of its kind must not also wait behind the majority), else a partial warp of the fullest one.
+					const uint32_t a0 = ctl->active[0], a1 = ctl->active[1], a2 = ctl->active[2];
+					const uint32_t distinct = (a0 != 0u) + (a1 != 0u) + (a2 != 0u);
+					const bool ok0 = a0 != 0u || distinct < maxClasses, ok1 = a1 != 0u || distinct < maxClasses,
+					           ok2 = a2 != 0u || distinct < maxClasses;
+					const uint32_t e0 = ok0 ? c0 : 0u, e1 = ok1 ? c1 : 0u, e2 = ok2 ? c2 : 0u;
 					uint32_t pick;
-					if (c2 >= 32u) pick = 2u;
-					else if (c1 >= 32u) pick = 1u;
-					else if (c0 >= 32u) pick = 0u;
-					else pick = (c2 >= c1 && c2 >= c0) ? 2u : (c1 >= c0 ? 1u : 0u);
+					if (e2 >= 32u) pick = 2u;
+					else if (e1 >= 32u) pick = 1u;
+					else if (e0 >= 32u) pick = 0u;
+					else pick = (e2 >= e1 && e2 >= e0) ? 2u : (e1 >= e0 ? 1u : 0u);
+					if ((pick == 2u ? e2 : (pick == 1u ? e1 : e0)) == 0u) {  // nothing this worker may take right now
+						const uint32_t live = ctl->live;
+						unlockCtl(ctl);
+						if (live == 0u) break;
+						__nanosleep(256);
+						if ((++idleSpins & 4095u) == 0u) {
+							unsigned long long now;
+							asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+							if (idleSince == 0) idleSince = now;
+							if (now - idleSince > 10ull * 1000 * 1000 * 1000) {
+								if (fault) *fault = 1u;
+								lockCtl(ctl);
+								ctl->live = 0u;
+								unlockCtl(ctl);
+								break;
+							}
+						}
+						continue;
+					}
 					const uint32_t have = pick == 2u ? c2 : (pick == 1u ? c1 : c0);
-					if (have > 0u) {
-						n = have < 32u ? have : 32u;
-						base = ctl->head[pick];
-						ctl->head[pick] = base + n;
-						ctl->count[pick] = have - n;
-						cls = pick;
-						unlockCtl(ctl);
-						break;
-					}
-					const uint32_t live = ctl->live;
+					n = have < 32u ? have : 32u;
+					base = ctl->head[pick];
+					ctl->head[pick] = base + n;
+					ctl->count[pick] = have - n;
+					ctl->active[pick] += 1u;
+					cls = pick;
 					unlockCtl(ctl);
-					if (live == 0u) break;  // cls == kClsExit
-					__nanosleep(256);
-					// watchdog: a cell takes well under a millisecond; a worker that finds nothing to do for 10 s while streams
-					// are still unaccounted for declares the call failed instead of hanging the GPU
-					if ((++idleSpins & 1023u) == 0u) {
-						unsigned long long now;
-						asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-						if (idleSince == 0) idleSince = now;
-						if (now - idleSince <= 10ull * 1000 * 1000 * 1000) continue;
-						if (fault) *fault = 1u;
-						lockCtl(ctl);
-						ctl->live = 0u;
-						unlockCtl(ctl);
-						break;
-					}
+					break;
 				}
 			}
 			cls = __shfl_sync(0xffffffffu, cls, 0);
@@ -362,6 +371,7 @@ klatt_f32_block_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 			if (lane == 0) {
 				ctl->count[0] += __popc(m0); ctl->count[1] += __popc(m1); ctl->count[2] += __popc(m2);
 				ctl->live -= __popc(mD);
+				ctl->active[cls] -= 1u;
 				unlockCtl(ctl);
 			}
 		}
@@ -414,9 +424,10 @@ cudaError_t launchKlattF32Block(const StreamDesc *descs, uint32_t numStreams, in
 		smemSet = smem;
 	}
 	const uint32_t numDummies = numBlocks * kBlkWorkers;
+	static const uint32_t maxClasses = getenv("NVSP_BLOCK_MAX_CLASSES") ? (uint32_t)atoi(getenv("NVSP_BLOCK_MAX_CLASSES")) : 2u;
 	klatt_block_import_kernel<<<(numStreams + numDummies + 255) / 256, 256, 0, stream>>>(descs, numStreams, numDummies, lite);
 	klatt_f32_block_kernel<<<numBlocks, kBlkThreads, smem, stream>>>(descs, lite, numStreams, sampleRate, sampleCount, holdTicks, out, rowStride,
-	                                                                 scratchRow, noise, cap, static_cast<unsigned long long *>(profMem),
+	                                                                 scratchRow, noise, cap, maxClasses, static_cast<unsigned long long *>(profMem),
 	                                                                 reinterpret_cast<uint32_t *>(static_cast<unsigned long long *>(profMem) + 31));
 	// the watchdog's verdict travels to a pinned host word; the engine reads it at its next synchronisation point
 	if (hostFault) {

@@ -229,15 +229,22 @@ klatt_long_timeline_kernel(LongStream L) {
 	__shared__ uint64_t oStart[kTimelineTile], oVib[kTimelineTile];
 	__shared__ int32_t oPrev[kTimelineTile];
 	__shared__ double oPop[kTimelineTile], oOld[kTimelineTile], oNew[kTimelineTile], oInc[kTimelineTile];
-	// the chain's state (thread 0 only)
+	__shared__ double gLanding[kTimelineTile], gEnd[kTimelineTile];  // the speculative glides
+	// The pitch a request inherits is a serial chain through the hold glide of its predecessor -- n repeated FP64 additions,
+	// exact in closed form (glideExact) but ~1 us each on one thread.  The chain only enters a request through the LANDING
+	// value old + (new - old) * 1.0, which is insensitive to the last bits of `old` almost always: thread 0 runs the chain with
+	// the glide in plain closed form (a guess good to a few ulps), all threads compute the exact glides from the guessed
+	// landings at once, and thread 0 walks the chain again with the exact values, keeping every glide whose landing it
+	// confirms bit for bit and redoing the few it does not.
 	uint64_t t = 0, vibPos = 0;
 	int32_t prevReal = -1;
-	bool oldIsNull = true;
-	double pitchCur = 0.0;
+	bool oldIsNull = true, gOldIsNull = true;
+	double pitchCur = 0.0, gCur = 0.0;
 	int64_t vPrev = 0;
 	const int tid = threadIdx.x;
 	for (uint32_t base = 0; base < L.nReq; base += kTimelineTile) {
 		const uint32_t j = base + tid;
+		const uint32_t n = L.nReq - base < (uint32_t)kTimelineTile ? L.nReq - base : (uint32_t)kTimelineTile;
 		if (j < L.nReq) {
 			sM[tid] = L.minDur[j];
 			sF[tid] = L.fadeDur[j];
@@ -248,14 +255,42 @@ klatt_long_timeline_kernel(LongStream L) {
 			sV0[tid] = p.vibInc0; sVs[tid] = p.vibIncStep; sVF[tid] = p.vibIncFinal;
 		}
 		__syncthreads();
-		if (tid == 0) {
-			const uint32_t n = L.nReq - base < (uint32_t)kTimelineTile ? L.nReq - base : (uint32_t)kTimelineTile;
+		if (tid == 0) {  // integers of the timeline, and the guessed pitch chain
 			for (uint32_t k = 0; k < n; ++k) {
 				const uint64_t M = sM[k];
 				const uint64_t F = sF[k] > 1u ? sF[k] : 1u;
 				const bool null = sNull[k] != 0;
+				const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
 				oStart[k] = t;
 				oPrev[k] = prevReal;
+				oVib[k] = vibPos;
+				vibPos += (uint64_t)vPrev + (F - 1) * (uint64_t)sV0[k] + (uint64_t)sVs[k] * ((F - 1) * F / 2) + (occ - F) * (uint64_t)sVF[k];
+				vPrev = sVF[k];
+				if (!null) prevReal = (int32_t)(base + k);
+				t += occ;
+				double pOld = gCur, pNew, inc;
+				if (null) { pNew = gCur; inc = 0.0; }
+				else { pNew = sP0[k]; inc = (sP1[k] - sP0[k]) / (double)M; if (gOldIsNull) pOld = pNew; }
+				pNew += inc * (double)F;
+				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
+				gLanding[k] = landing;
+				oInc[k] = inc;
+				gCur = landing + (double)(occ - F - 2) * inc;
+				gOldIsNull = null;
+			}
+		}
+		__syncthreads();
+		if (j < L.nReq) {
+			const uint64_t M = sM[tid], F = sF[tid] > 1u ? sF[tid] : 1u;
+			const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
+			gEnd[tid] = glideExact(gLanding[tid], oInc[tid], occ - F - 2);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
+		}
+		__syncthreads();
+		if (tid == 0) {  // the true chain
+			for (uint32_t k = 0; k < n; ++k) {
+				const uint64_t M = sM[k];
+				const uint64_t F = sF[k] > 1u ? sF[k] : 1u;
+				const bool null = sNull[k] != 0;
 				oPop[k] = pitchCur;
 				double pOld = pitchCur, pNew, inc;
 				if (null) {  // src/frame.cpp:59-63
@@ -267,16 +302,14 @@ klatt_long_timeline_kernel(LongStream L) {
 					if (oldIsNull) pOld = pNew;            // :64-67
 				}
 				pNew += inc * (double)F;  // :71
-				oOld[k] = pOld; oNew[k] = pNew; oInc[k] = inc;
+				oOld[k] = pOld; oNew[k] = pNew;
 				const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
 				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
-				pitchCur = glideExact(landing, inc, occ - F - 2);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
-				oVib[k] = vibPos;
-				vibPos += (uint64_t)vPrev + (F - 1) * (uint64_t)sV0[k] + (uint64_t)sVs[k] * ((F - 1) * F / 2) + (occ - F) * (uint64_t)sVF[k];
-				vPrev = sVF[k];
+				const bool same = __double_as_longlong(landing) == __double_as_longlong(gLanding[k]) &&
+				                  __double_as_longlong(inc) == __double_as_longlong(oInc[k]);
+				pitchCur = same ? gEnd[k] : glideExact(landing, inc, occ - F - 2);
+				oInc[k] = inc;
 				oldIsNull = null;
-				if (!null) prevReal = (int32_t)(base + k);
-				t += occ;
 			}
 		}
 		__syncthreads();
@@ -751,18 +784,61 @@ __device__ __forceinline__ AffineD shflUp(const AffineD &m, int delta) {
 
 constexpr int kScanThreads = 1024;
 
+// (round 1 ran this scan in ONE block: every thread composed a run of ~150 chunks out of global memory, twice -- 1.48 ms per
+// section, 11.8 ms of a config-4 call.)  Three phases now: every block of 256 chunks scans its own maps (one chunk per
+// thread, coalesced loads, Kogge-Stone with warp shuffles) and leaves its total; one block scans the block totals; the blocks
+// scan again and write, for every chunk, the z-part of (its exclusive prefix within the block) after (the prefix of the block).
+constexpr int kScanBlock = 256;
+
+// inclusive scan of one map per thread across a block of kScanBlock threads; returns the exclusive prefix of the thread too
+__device__ __forceinline__ void blockScanAffine(const AffineD &mine, AffineD &inclusive, AffineD &exclusive, AffineD *warpTotal /* smem [8] */) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	AffineD inc = mine;
+#pragma unroll
+	for (int delta = 1; delta < 32; delta <<= 1) {
+		AffineD up = shflUp(inc, delta);
+		if (lane >= delta) inc = compose(inc, up);
+	}
+	if (lane == 31) warpTotal[warp] = inc;
+	__syncthreads();
+	AffineD pre = identityMap();  // everything in the warps before this one
+	for (int w = 0; w < warp; ++w) pre = compose(warpTotal[w], pre);
+	AffineD prevLane = shflUp(inc, 1);
+	exclusive = lane == 0 ? pre : compose(prevLane, pre);
+	inclusive = compose(inc, pre);
+	__syncthreads();
+}
+
+template <int PHASE>  // 1: block totals; 3: start states from the scanned block prefixes
+__global__ void __launch_bounds__(kScanBlock)
+klatt_long_scan_blocks_kernel(const Affine *__restrict__ maps, uint32_t numChunks, int numSections, AffineD *__restrict__ blockTotals,
+                              const AffineD *__restrict__ blockPrefix, float2 *__restrict__ startState) {
+	__shared__ AffineD warpTotal[kScanBlock / 32];
+	const uint32_t c = blockIdx.x * kScanBlock + threadIdx.x;
+	for (int k = 0; k < numSections; ++k) {
+		const AffineD mine = c < numChunks ? toD(maps[(size_t)c * numSections + k]) : identityMap();
+		AffineD inclusive, exclusive;
+		blockScanAffine(mine, inclusive, exclusive, warpTotal);
+		if (PHASE == 1) {
+			if (threadIdx.x == kScanBlock - 1) blockTotals[(size_t)blockIdx.x * numSections + k] = inclusive;
+		} else if (c < numChunks) {
+			const AffineD pre = compose(exclusive, blockPrefix[(size_t)blockIdx.x * numSections + k]);
+			startState[(size_t)c * numSections + k] = make_float2((float)pre.zy, (float)pre.zd);
+		}
+	}
+}
+
+// phase 2: exclusive scan of the block totals in place (one block; every thread takes a run of blocks)
 __global__ void __launch_bounds__(kScanThreads)
-klatt_long_scan_kernel(const Affine *__restrict__ maps, uint32_t numChunks, int numSections, float2 *__restrict__ startState) {
+klatt_long_scan_totals_kernel(AffineD *__restrict__ totals, uint32_t numBlocks, int numSections) {
 	__shared__ AffineD warpTotal[32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t per = (numChunks + kScanThreads - 1) / kScanThreads;
-	const uint32_t c0 = (uint32_t)tid * per < numChunks ? (uint32_t)tid * per : numChunks;
-	const uint32_t c1 = c0 + per < numChunks ? c0 + per : numChunks;
+	const uint32_t per = (numBlocks + kScanThreads - 1) / kScanThreads;
+	const uint32_t c0 = (uint32_t)tid * per < numBlocks ? (uint32_t)tid * per : numBlocks;
+	const uint32_t c1 = c0 + per < numBlocks ? c0 + per : numBlocks;
 	for (int k = 0; k < numSections; ++k) {
-		// 1. this thread's run
 		AffineD run = identityMap();
-		for (uint32_t c = c0; c < c1; ++c) run = compose(toD(maps[(size_t)c * numSections + k]), run);
-		// 2. inclusive scan of the run totals: within the warp by shuffles, then across warps
+		for (uint32_t c = c0; c < c1; ++c) run = compose(totals[(size_t)c * numSections + k], run);
 		AffineD inc = run;
 #pragma unroll
 		for (int delta = 1; delta < 32; delta <<= 1) {
@@ -781,18 +857,27 @@ klatt_long_scan_kernel(const Affine *__restrict__ maps, uint32_t numChunks, int 
 			warpTotal[lane] = w;
 		}
 		__syncthreads();
-		// exclusive prefix of this thread = (inclusive of the previous lane) after (inclusive total of earlier warps)
 		AffineD prev = shflUp(inc, 1);
 		AffineD pre = lane == 0 ? identityMap() : prev;
 		if (warp > 0) pre = compose(pre, warpTotal[warp - 1]);
-		// 3. replay the run
 		for (uint32_t c = c0; c < c1; ++c) {
-			startState[(size_t)c * numSections + k] = make_float2((float)pre.zy, (float)pre.zd);
-			pre = compose(toD(maps[(size_t)c * numSections + k]), pre);
+			const AffineD m = totals[(size_t)c * numSections + k];
+			totals[(size_t)c * numSections + k] = pre;  // exclusive
+			pre = compose(m, pre);
 		}
 		__syncthreads();
 	}
 }
+
+// maps -> start states of all chunks; blockTotals: scratch of ceil(numChunks / 256) * numSections AffineD
+static void launchLongScan(const Affine *maps, uint32_t numChunks, int numSections, void *blockTotals, float2 *startState, cudaStream_t stream) {
+	const uint32_t nb = (numChunks + kScanBlock - 1) / kScanBlock;
+	AffineD *tot = static_cast<AffineD *>(blockTotals);
+	klatt_long_scan_blocks_kernel<1><<<nb, kScanBlock, 0, stream>>>(maps, numChunks, numSections, tot, nullptr, nullptr);
+	klatt_long_scan_totals_kernel<<<1, kScanThreads, 0, stream>>>(tot, nb, numSections);
+	klatt_long_scan_blocks_kernel<3><<<nb, kScanBlock, 0, stream>>>(maps, numChunks, numSections, nullptr, tot, startState);
+}
+size_t klattLongScanScratchBytes(uint64_t numChunks) { return sizeof(AffineD) * 6 * (size_t)((numChunks + kScanBlock - 1) / kScanBlock); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // launcher: everything device-resident; scratch sized by the caller (see engine.cu)
@@ -812,7 +897,7 @@ cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream) {
 cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
                                   uint64_t *startPhase, PhaseChunk *chunks, double *startP, uint32_t *fail, bool serialPhase,
                                   float *ci, float *pin, float *par, float *xa, float *xb, Affine *maps,
-                                  float2 *startState, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream) {
+                                  float2 *startState, void *scanScratch, int16_t *pcm, unsigned long long *launchCounter, cudaStream_t stream) {
 	if (totalTicks == 0) return cudaSuccess;
 	const uint32_t numChunks = (uint32_t)((totalTicks + chunkTicks - 1) / chunkTicks);
 	const dim3 grid((numChunks + 127) / 128), block(128);
@@ -832,25 +917,25 @@ cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint
 	klatt_long_source_kernel<<<grid, block, 0, stream>>>(L, chunkTicks, numChunks, chunks, startP, fail, ci, pin);
 	// parallel bank
 	klatt_long_stage_kernel<kStageParallel, 1><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, maps, nullptr, nullptr, nullptr);
-	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 6, startState);
+	launchLongScan(maps, numChunks, 6, scanScratch, startState, stream);
 	klatt_long_stage_kernel<kStageParallel, 2><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, 0, pin, nullptr, nullptr, startState, par, nullptr);
 	// rN0 + rNP
 	klatt_long_stage_kernel<kStageNasal, 1><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, kResNP, ci, nullptr, maps, nullptr, nullptr, nullptr);
-	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
+	launchLongScan(maps, numChunks, 1, scanScratch, startState, stream);
 	klatt_long_stage_kernel<kStageNasal, 2><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, kResNP, ci, nullptr, nullptr, startState, xa, nullptr);
 	// r6 .. r2
 	float *src = xa, *dst = xb;
 	for (int r = kResCascade; r < kResParallel - 1; ++r) {
 		klatt_long_stage_kernel<kStageCascade, 1><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, r, src, nullptr, maps, nullptr, nullptr, nullptr);
-		klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
+		launchLongScan(maps, numChunks, 1, scanScratch, startState, stream);
 		klatt_long_stage_kernel<kStageCascade, 2><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, r, src, nullptr, nullptr, startState, dst, nullptr);
 		float *tmp = src; src = dst; dst = tmp;
 	}
 	// r1 + output
 	klatt_long_stage_kernel<kStageLast, 1><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, maps, nullptr, nullptr, nullptr);
-	klatt_long_scan_kernel<<<1, kScanThreads, 0, stream>>>(maps, numChunks, 1, startState);
+	launchLongScan(maps, numChunks, 1, scanScratch, startState, stream);
 	klatt_long_stage_kernel<kStageLast, 2><<<sgrid, sblock, 0, stream>>>(L, chunkTicks, numChunks, kResParallel - 1, src, par, nullptr, startState, nullptr, pcm);
-	if (launchCounter) *launchCounter += 1 + 3 * 8;
+	if (launchCounter) *launchCounter += 1 + 5 * 8;
 	return cudaGetLastError();
 }
 

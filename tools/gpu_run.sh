@@ -72,5 +72,15 @@ c4)  # block scheduler with staged records: bitwise test, A/B, cycle profile, nc
 	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/long_launches.csv \
 		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/long_launches.log 2>&1; echo "ncu long list rc=$?"
 	;;
+c5)  # block scheduler: how many classes (loop pairs) may be in flight per SM
+	timeout 300 python -m pytest tests/test_gpu_parity_f32.py -q -m gpu -k "rounds_equal or batch_random" > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -3 $O/pytest_gpu.log
+	try "NVSP_BLOCK_MAX_CLASSES=2"
+	try "NVSP_BLOCK_MAX_CLASSES=1"
+	try "NVSP_BLOCK_MAX_CLASSES=3"
+	try "NVSP_BLOCK_MAX_CLASSES=2 NVSP_LIB=$PWD/tools/_variants/libbprof.so"
+	try "NVSP_BLOCK_MAX_CLASSES=1 NVSP_LIB=$PWD/tools/_variants/libbprof.so"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_f32_block_kernel -s 3 -c 1 -f -o $O/prof_block \
+		python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_block.log 2>&1; echo "ncu block rc=$?"; ls -la $O/prof_block.ncu-rep
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
