@@ -61,6 +61,7 @@ def parse_args():
                          "the time-parallel kernel")
     ap.add_argument("--voices", type=int, default=1024, help="--workload vowel: voices per GPU (1369 pairs each)")
     ap.add_argument("--pull-samples", type=int, default=8192, help="--workload pull: samples per speechPlayer_synthesize call")
+    ap.add_argument("--pull-players", type=int, default=148, help="--workload pull: players of the batched-pull leg")
     ap.add_argument("--long-seconds", type=float, default=3600.0)
     ap.add_argument("--long-rate", type=int, default=44100)
     return ap.parse_args()
@@ -316,6 +317,25 @@ def pull_arm(args, rank, world, local_rank):
     for name, prec in (("stream", player.PRECISION_STREAM), ("fp32_serial", player.PRECISION_FP32)):
         res[name] = timed_pulls(lambda: player.SpeechPlayer(sr, precision=prec, noise=player.NOISE_PHILOX, seed=args.seed,
                                                             streamId=5_000_000 + rank))
+    # many interactive players in one launch (speechPlayer_synthesizeBatch over stream handles: one block per player)
+    nb = args.pull_players
+    bsecs = (warm + 12) * pull / sr
+    bstreams = [workloads.random_stream(6_000_000 + rank * nb + k, bsecs, sr, seed=args.seed) for k in range(nb)]
+    bps = [player.SpeechPlayer(sr, precision=player.PRECISION_STREAM, noise=player.NOISE_PHILOX, seed=args.seed,
+                               streamId=6_000_000 + rank * nb + k) for k in range(nb)]
+    for p_, (fr_, m_, f_, nul_, ux_) in zip(bps, bstreams):
+        p_.queue_frames(fr_, m_, f_, ux_, nul_)
+    bts = []
+    for i in range(warm + 10):
+        t0 = time.perf_counter()
+        bout, bw = player.synthesize_batch(bps, pull)
+        dt = time.perf_counter() - t0
+        assert (bw == pull).all()
+        if i >= warm:
+            bts.append(dt)
+    for p_ in bps:
+        p_.close()
+    bts = np.array(bts)
     clocks = sampler.stop() if rank == 0 else None
     ts = res["stream"]
     total_s = float(ts.sum())
@@ -351,6 +371,9 @@ def pull_arm(args, rank, world, local_rank):
                            "l2": "not applicable: one block, working set in shared memory"},
                 "latency_ms": {"median": float(np.median(ts)) * 1e3, "p95": float(np.percentile(ts, 95)) * 1e3, "max": float(ts.max()) * 1e3,
                                "fp32_serial_kernel_median": float(np.median(res["fp32_serial"])) * 1e3},
+                "batch_of_players": {"players": nb, "samples_per_call": pull, "ms_per_call_median": float(np.median(bts)) * 1e3,
+                                     "audio_seconds_per_s": nb * pull / sr / float(np.median(bts)),
+                                     "note": "speechPlayer_synthesizeBatch over %d stream handles: one launch, one block per player" % nb},
                 "roofline": {"bound": "latency", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                              "traffic": None, "kernel": "klatt_pull_kernel (1 block of 512 threads per pull)",
                              "note": "one SM of 148 and a serial FP64 phase recurrence: the bound is dependent-issue latency, "
@@ -379,7 +402,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from nvspeechplayer_b200 import player, workloads
+    from nvspeechplayer_b200 import player, sharding, workloads
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
@@ -426,9 +449,10 @@ def main():
 
     # ---- workload: this rank's shard of config 3 ----
     t_gen = time.time()
-    fb = make_workload(S, rank * S)
+    first_stream, _ = sharding.weak_shard(S, rank)  # weak scaling: rank r renders stream ids [r*S, (r+1)*S), no collective
+    fb = make_workload(S, first_stream)
     phi = fb.fade_fraction(count) if S <= 4096 else make_workload(1369 if args.workload == "vowel" else 1024,
-                                                                  rank * S).fade_fraction(count)
+                                                                  first_stream).fade_fraction(count)
     t_gen = time.time() - t_gen
     flops_per_sample = W_HOLD + W_FADE_EXTRA * phi
     total_frames = int(fb.offsets[-1])

@@ -101,6 +101,29 @@ int speechPlayer_batchGetLastIndices(speechPlayer_batch_t *batch, int *lastIndex
 int speechPlayer_batchGetLaunchStats(speechPlayer_batch_t *batch, unsigned long long *kernelLaunches,
                                      unsigned long long *ticksRequested);
 
+/* ---- several GPUs of one box, in-library --------------------------------------------------------
+ * Streams are independent, so a job shards by stream with NO collective: contiguous ranges of stream indices per device,
+ * balanced by the ticks each stream's queue yields (occupancy law sum_j max(M+1, F+2), capped at nothing: whole queues), one
+ * host thread and one per-device batch (its own CUDA streams) per shard, and SynthesizeHost gathers into disjoint row ranges
+ * of ONE caller buffer [numStreams][sampleCount] (pinned memory makes the copies asynchronous).
+ *   devices     : CUDA device ordinals, one shard each (an ordinal may repeat: two shards on one GPU); numDevices >= 1
+ *   SetFramesHost: same arguments as speechPlayer_batchSetFramesHost; (re)partitions the streams and uploads every shard's
+ *                 queues from its own thread
+ *   GetShards   : firstStream[numDevices + 1] -- shard d owns streams [firstStream[d], firstStream[d + 1])
+ * Everything a single batch guarantees holds per stream (same kernels, same bits as one batch on one GPU). */
+typedef struct speechPlayer_multiBatch speechPlayer_multiBatch_t;
+speechPlayer_multiBatch_t *speechPlayer_multiBatchCreate(int sampleRate, unsigned int numStreams, int precision, int noiseMode,
+                                                         uint64_t seed, const uint64_t *streamIds, const int *devices,
+                                                         unsigned int numDevices);
+void speechPlayer_multiBatchDestroy(speechPlayer_multiBatch_t *mb);
+int speechPlayer_multiBatchSetFramesHost(speechPlayer_multiBatch_t *mb, const int64_t *offsets, const speechPlayer_frame_t *frames,
+                                         const unsigned int *minFrameDuration, const unsigned int *fadeDuration,
+                                         const int *userIndex, const unsigned char *isNull);
+long long speechPlayer_multiBatchSynthesizeHost(speechPlayer_multiBatch_t *mb, unsigned int sampleCount, sample *out,
+                                                unsigned int *samplesWritten);
+int speechPlayer_multiBatchGetShards(speechPlayer_multiBatch_t *mb, unsigned int *firstStream);
+int speechPlayer_multiBatchGetLastIndices(speechPlayer_multiBatch_t *mb, int *lastIndex);
+
 /* Long-utterance path: ONE pre-queued stream rendered with parallelism in TIME (nvspeechplayer_b200/csrc/klatt_long.cu):
  * the stream is cut into chunks of chunkTicks ticks (0 = default 1024) that are rendered concurrently; the glottal
  * phase each chunk starts from comes from a scan of per-chunk phase advances, the state each two-pole section starts

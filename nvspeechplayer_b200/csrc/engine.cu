@@ -21,6 +21,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/speechPlayer.h"
@@ -77,6 +78,7 @@ struct Affine {
 };
 cudaError_t launchKlattPullInit(PullState *state, cudaStream_t stream);  // klatt_pull.cu
 cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut, cudaStream_t stream);
+cudaError_t launchKlattPullBatch(PullBatchItem *hItems, const PullBatchItem *dItems, uint32_t count, cudaStream_t stream);
 cudaError_t launchKlattLongTimeline(const LongStream &L, cudaStream_t stream);
 cudaError_t launchKlattLongRender(const LongStream &L, uint64_t totalTicks, uint32_t chunkTicks, uint64_t *advance,
                                   uint64_t *startPhase, PhaseChunk *chunks, double *startP, uint32_t *fail, bool serialPhase,
@@ -777,15 +779,14 @@ void speechPlayer_seedNoise(unsigned int seed) {
 	g_noise.seed(seed);
 }
 
-// One pull of a SPEECHPLAYER_PRECISION_STREAM player: the host manager describes the next ticks (src/frame.cpp:41-80 in
-// closed form), one launch of klatt_pull_kernel per kPullMaxTicks renders them, the samples come back through pinned memory.
-static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *out) {
-	std::lock_guard<std::mutex> lk(p->mu);
-	DeviceGuard g(p->device);
-	if (!p->pipe.init()) return -1;
-	cudaStream_t stream = p->pipe.compute;
+// Stage one launch of a SPEECHPLAYER_PRECISION_STREAM player: the host manager has described the next `got` ticks in
+// p->pullSegs (src/frame.cpp:41-80 in closed form); copy the segments into the player's pinned staging, fetch the noise draws,
+// fill the launch context.  The kernel reads the segments from and writes the samples to the pinned staging itself
+// (zero-copy, the default), so a pull is one launch and one synchronize; NVSP_PULL_ZEROCOPY=0 goes through device buffers.
+static int pullStage(Player *p, uint32_t got, PullCtx &X, const PullSeg *&segSrc, int16_t *&pcmOut, bool &zeroCopy, cudaStream_t stream) {
+	static const bool zc = !(getenv("NVSP_PULL_ZEROCOPY") && atoi(getenv("NVSP_PULL_ZEROCOPY")) == 0);
+	zeroCopy = zc;
 	PullSeg *hSegs = reinterpret_cast<PullSeg *>(p->hPullStage);
-	int16_t *hPcm = reinterpret_cast<int16_t *>(p->hPullStage + Player::kStageSegs);
 	int32_t *hDraws = reinterpret_cast<int32_t *>(p->hPullStage + Player::kStageSegs + Player::kStagePcm);
 	if (p->noiseMode == kNoiseReplay && p->replayDirty) {
 		if (!p->dReplay.reserve(std::max<size_t>(p->replayHost.size(), 1) * 4)) return -1;
@@ -793,6 +794,46 @@ static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *ou
 		CU(cudaStreamSynchronize(stream));
 		p->replayDirty = false;
 	}
+	const size_t nSeg = p->pullSegs.size();
+	memcpy(hSegs, p->pullSegs.data(), nSeg * sizeof(PullSeg));
+	segSrc = reinterpret_cast<const PullSeg *>(p->dPullStage);
+	pcmOut = reinterpret_cast<int16_t *>(p->dPullStage + Player::kStageSegs);
+	if (!zeroCopy) {
+		CU(cudaMemcpyAsync(p->dSegs.p, hSegs, nSeg * sizeof(PullSeg), cudaMemcpyHostToDevice, stream));
+		segSrc = p->dSegs.as<PullSeg>();
+		pcmOut = p->dPullPcm.as<int16_t>();
+	}
+	memset(&X, 0, sizeof X);
+	X.nSeg = (uint32_t)nSeg; X.n = got; X.sampleRate = p->sampleRate;
+	X.state = p->dPull; X.noiseMode = p->noiseMode; X.seed = p->seed; X.streamId = p->streamId;
+	if (p->noiseMode == kNoiseGlibc) {  // the reference consumes exactly two rand() calls per generated sample
+		{
+			std::lock_guard<std::mutex> nl(g_noiseMu);
+			g_noise.fill(hDraws, (size_t)got * 2);
+		}
+		if (!p->dDraws.reserve(Player::kStageDraws)) return -1;
+		CU(cudaMemcpyAsync(p->dDraws.p, hDraws, (size_t)got * 2 * 4, cudaMemcpyHostToDevice, stream));
+		X.draws = p->dDraws.as<int32_t>(); X.drawBase = p->generated * 2; X.drawLen = (uint64_t)got * 2;
+	} else if (p->noiseMode == kNoiseReplay) {
+		X.draws = p->dReplay.as<int32_t>(); X.drawBase = 0; X.drawLen = p->replayHost.size();
+	}
+	// the glottal-phase recurrence: run decomposition (klatt_pull_core.cuh pullRuns*; bit-identical to the serial loop,
+	// 280 k -> 48 k cycles of an 8192-tick launch on B200) unless NVSP_PULL_PHASE=serial asks for the plain loop
+	static const bool phaseSerial = getenv("NVSP_PULL_PHASE") && !strcmp(getenv("NVSP_PULL_PHASE"), "serial");
+	X.phaseMode = phaseSerial ? 0 : 1;
+	static const bool debugPhases = getenv("NVSP_PULL_DEBUG") != nullptr;
+	if (debugPhases && p->dPullDbg.reserve(16 * sizeof(long long))) X.dbg = p->dPullDbg.as<long long>();
+	return 0;
+}
+
+// One pull of a SPEECHPLAYER_PRECISION_STREAM player: one launch of klatt_pull_kernel per kPullMaxTicks, the samples come back
+// through pinned memory.
+static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *out) {
+	std::lock_guard<std::mutex> lk(p->mu);
+	DeviceGuard g(p->device);
+	if (!p->pipe.init()) return -1;
+	cudaStream_t stream = p->pipe.compute;
+	int16_t *hPcm = reinterpret_cast<int16_t *>(p->hPullStage + Player::kStageSegs);
 	unsigned int total = 0;
 	while (total < sampleCount) {
 		const uint32_t want = std::min<uint32_t>(sampleCount - total, kPullMaxTicks);
@@ -800,39 +841,11 @@ static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *ou
 		bool drained = false;
 		const uint32_t got = p->pull->advance(want, 0, kPullMaxSegs, p->pullSegs, drained);
 		if (got) {
-			// zero-copy (default): the kernel reads the segments from and writes the samples to the pinned staging itself, so a
-			// pull is one launch and one synchronize; NVSP_PULL_ZEROCOPY=0 goes through device buffers and two copies instead
-			static const bool zeroCopy = !(getenv("NVSP_PULL_ZEROCOPY") && atoi(getenv("NVSP_PULL_ZEROCOPY")) == 0);
-			const size_t nSeg = p->pullSegs.size();
-			memcpy(hSegs, p->pullSegs.data(), nSeg * sizeof(PullSeg));
-			const PullSeg *segSrc = reinterpret_cast<const PullSeg *>(p->dPullStage);
-			int16_t *pcmOut = reinterpret_cast<int16_t *>(p->dPullStage + Player::kStageSegs);
-			if (!zeroCopy) {
-				CU(cudaMemcpyAsync(p->dSegs.p, hSegs, nSeg * sizeof(PullSeg), cudaMemcpyHostToDevice, stream));
-				segSrc = p->dSegs.as<PullSeg>();
-				pcmOut = p->dPullPcm.as<int16_t>();
-			}
 			PullCtx X;
-			memset(&X, 0, sizeof X);
-			X.nSeg = (uint32_t)nSeg; X.n = got; X.sampleRate = p->sampleRate;
-			X.state = p->dPull; X.noiseMode = p->noiseMode; X.seed = p->seed; X.streamId = p->streamId;
-			if (p->noiseMode == kNoiseGlibc) {  // the reference consumes exactly two rand() calls per generated sample
-				{
-					std::lock_guard<std::mutex> nl(g_noiseMu);
-					g_noise.fill(hDraws, (size_t)got * 2);
-				}
-				if (!p->dDraws.reserve(Player::kStageDraws)) return -1;
-				CU(cudaMemcpyAsync(p->dDraws.p, hDraws, (size_t)got * 2 * 4, cudaMemcpyHostToDevice, stream));
-				X.draws = p->dDraws.as<int32_t>(); X.drawBase = p->generated * 2; X.drawLen = (uint64_t)got * 2;
-			} else if (p->noiseMode == kNoiseReplay) {
-				X.draws = p->dReplay.as<int32_t>(); X.drawBase = 0; X.drawLen = p->replayHost.size();
-			}
-			// the glottal-phase recurrence: run decomposition (klatt_pull_core.cuh pullRuns*; bit-identical to the serial loop,
-			// 280 k -> 48 k cycles of an 8192-tick launch on B200) unless NVSP_PULL_PHASE=serial asks for the plain loop
-			static const bool phaseSerial = getenv("NVSP_PULL_PHASE") && !strcmp(getenv("NVSP_PULL_PHASE"), "serial");
-			X.phaseMode = phaseSerial ? 0 : 1;
-			static const bool debugPhases = getenv("NVSP_PULL_DEBUG") != nullptr;
-			if (debugPhases && p->dPullDbg.reserve(16 * sizeof(long long))) X.dbg = p->dPullDbg.as<long long>();
+			const PullSeg *segSrc;
+			int16_t *pcmOut;
+			bool zeroCopy;
+			if (pullStage(p, got, X, segSrc, pcmOut, zeroCopy, stream) != 0) return -1;
 			CU(launchKlattPull(X, segSrc, pcmOut, stream));
 			if (!zeroCopy) CU(cudaMemcpyAsync(hPcm, pcmOut, (size_t)got * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
 			CU(cudaStreamSynchronize(stream));
@@ -841,7 +854,7 @@ static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *ou
 				long long c[16];
 				CU(cudaMemcpy(c, X.dbg, sizeof c, cudaMemcpyDeviceToHost));
 				fprintf(stderr, "[pull] n=%u segs=%zu cycles: src1 %lld noise-scan %lld phase %lld src2 %lld parallel %lld nasal %lld "
-				        "r6-r2 %lld r1+out %lld total %lld in %lld ns\n", got, nSeg, c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3],
+				        "r6-r2 %lld r1+out %lld total %lld in %lld ns\n", got, p->pullSegs.size(), c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3],
 				        c[5] - c[4], c[6] - c[5], c[7] - c[6], c[8] - c[7], c[8] - c[0], c[14] - c[15]);
 			}
 			++p->pullLaunches;
@@ -852,6 +865,82 @@ static long long synthesizePull(Player *p, unsigned int sampleCount, int16_t *ou
 	}
 	p->lastIndex = p->pull->lastIndex();
 	return (long long)total;
+}
+
+// speechPlayer_synthesizeBatch over SPEECHPLAYER_PRECISION_STREAM handles: ONE launch per kPullMaxTicks for all players, one
+// block per player (klatt_pull_batch_kernel) -- 148 interactive players at the latency of one.  Each row is what the player's
+// own speechPlayer_synthesize would have produced (same kernel body, same carried state).  With the process-global glibc noise
+// the players draw in handle order, as sequential calls would.
+static std::mutex g_pullBatchMu;
+static PullBatchItem *g_pullItemsHost = nullptr, *g_pullItemsDev = nullptr;
+static size_t g_pullItemsCap = 0;
+static int g_pullItemsDevice = -1;
+
+static long long synthesizePullBatch(std::vector<Player *> &ps, unsigned int sampleCount, int16_t *out, unsigned int *samplesWritten) {
+	const size_t n = ps.size();
+	std::vector<Player *> order(ps);
+	std::sort(order.begin(), order.end());
+	for (Player *p : order) p->mu.lock();
+	struct Unlock {
+		std::vector<Player *> &o;
+		~Unlock() { for (Player *p : o) p->mu.unlock(); }
+	} unlock{order};
+	std::lock_guard<std::mutex> bl(g_pullBatchMu);
+	Player *lead = ps[0];
+	DeviceGuard g(lead->device);
+	if (!lead->pipe.init()) return -1;
+	cudaStream_t stream = lead->pipe.compute;
+	if (g_pullItemsCap < n || g_pullItemsDevice != lead->device) {
+		if (g_pullItemsHost) cudaFreeHost(g_pullItemsHost);
+		g_pullItemsHost = nullptr; g_pullItemsCap = 0;
+		const size_t cap = std::max<size_t>(n, 256);
+		CU(cudaHostAlloc((void **)&g_pullItemsHost, cap * sizeof(PullBatchItem), cudaHostAllocMapped));
+		CU(cudaHostGetDevicePointer((void **)&g_pullItemsDev, g_pullItemsHost, 0));
+		g_pullItemsCap = cap; g_pullItemsDevice = lead->device;
+	}
+	std::vector<unsigned int> total(n, 0);
+	std::vector<uint32_t> got(n, 0);
+	std::vector<char> done(n, 0), zero(n, 1);
+	for (;;) {
+		bool any = false;
+		for (size_t i = 0; i < n; ++i) {
+			Player *p = ps[i];
+			PullBatchItem &it = g_pullItemsHost[i];
+			memset(&it, 0, sizeof it);
+			got[i] = 0;
+			if (done[i] || total[i] >= sampleCount) continue;
+			const uint32_t want = std::min<uint32_t>(sampleCount - total[i], kPullMaxTicks);
+			p->pullSegs.clear();
+			bool drained = false;
+			got[i] = p->pull->advance(want, 0, kPullMaxSegs, p->pullSegs, drained);
+			if (drained) done[i] = 1;
+			if (!got[i]) continue;
+			bool zc;
+			if (pullStage(p, got[i], it.ctx, it.segSrc, it.pcmOut, zc, stream) != 0) return -1;
+			zero[i] = zc ? 1 : 0;
+			any = true;
+		}
+		if (!any) break;
+		CU(launchKlattPullBatch(g_pullItemsHost, g_pullItemsDev, (uint32_t)n, stream));
+		for (size_t i = 0; i < n; ++i)
+			if (got[i] && !zero[i])
+				CU(cudaMemcpyAsync(ps[i]->hPullStage + Player::kStageSegs, g_pullItemsHost[i].pcmOut, (size_t)got[i] * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
+		CU(cudaStreamSynchronize(stream));
+		for (size_t i = 0; i < n; ++i) {
+			if (!got[i]) continue;
+			memcpy(out + i * (size_t)sampleCount + total[i], ps[i]->hPullStage + Player::kStageSegs, (size_t)got[i] * sizeof(int16_t));
+			++ps[i]->pullLaunches;
+			ps[i]->generated += got[i];
+			total[i] += got[i];
+		}
+	}
+	long long sum = 0;
+	for (size_t i = 0; i < n; ++i) {
+		ps[i]->lastIndex = ps[i]->pull->lastIndex();
+		if (samplesWritten) samplesWritten[i] = total[i];
+		sum += total[i];
+	}
+	return sum;
 }
 
 long long speechPlayer_synthesizeBatch(speechPlayer_handle_t *handles, unsigned int numHandles, unsigned int sampleCount,
@@ -866,19 +955,19 @@ long long speechPlayer_synthesizeBatch(speechPlayer_handle_t *handles, unsigned 
 		if (!ps[i]) return fail("bad handle in batch");
 		anyPull = anyPull || ps[i]->pull != nullptr;
 	}
-	if (anyPull) {  // low-latency players render one pull per launch each; a batch of them is a loop
+	if (anyPull) {  // low-latency players: one block per player, one launch for all of them
 		std::vector<Player *> uniq(ps);
 		std::sort(uniq.begin(), uniq.end());
 		if (std::adjacent_find(uniq.begin(), uniq.end()) != uniq.end()) return fail("duplicate handle in batch");
-		long long total = 0;
-		for (unsigned i = 0; i < numHandles; ++i) {
-			if (!ps[i]->pull) return fail("handles of one batch must share device, sample rate, precision and noise mode");
-			long long w = synthesizePull(ps[i], sampleCount, reinterpret_cast<int16_t *>(sampleBuf) + (size_t)i * sampleCount);
-			if (w < 0) return -1;
-			if (samplesWritten) samplesWritten[i] = (unsigned int)w;
-			total += w;
+		for (unsigned i = 0; i < numHandles; ++i)
+			if (!ps[i]->pull || ps[i]->device != ps[0]->device)
+				return fail("handles of one batch must share device and precision");
+		if (numHandles == 1) {
+			long long w = synthesizePull(ps[0], sampleCount, reinterpret_cast<int16_t *>(sampleBuf));
+			if (w >= 0 && samplesWritten) samplesWritten[0] = (unsigned int)w;
+			return w;
 		}
-		return total;
+		return synthesizePullBatch(ps, sampleCount, reinterpret_cast<int16_t *>(sampleBuf), samplesWritten);
 	}
 	for (unsigned i = 0; i < numHandles; ++i) {
 		if (ps[i]->precision != ps[0]->precision || ps[i]->sampleRate != ps[0]->sampleRate ||
@@ -1395,6 +1484,152 @@ int speechPlayer_batchGetLaunchStats(speechPlayer_batch_t *b, unsigned long long
 	if (kernelLaunches) *kernelLaunches = b->launches;
 	if (ticksRequested) *ticksRequested = b->ticks;
 	return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: several GPUs of one box (include/speechPlayer_batch.h): shards = per-device batches, one host thread each
+// ------------------------------------------------------------------------------------------------
+struct speechPlayer_multiBatch {
+	int sampleRate = 0, precision = kPrecisionF32, noiseMode = kNoisePhilox;
+	uint64_t seed = 0;
+	uint32_t n = 0;
+	std::vector<uint64_t> streamIds;
+	std::vector<int> devices;
+	std::vector<uint32_t> first;                  // [numDevices + 1]
+	std::vector<speechPlayer_batch_t *> shards;   // per device (nullptr while the shard is empty)
+	std::mutex mu;
+};
+
+// run fn(d) for every shard on its own thread with the shard's device current; returns false if any failed
+template <class Fn>
+static bool forEachShard(speechPlayer_multiBatch *mb, Fn fn, std::string &err) {
+	const size_t nd = mb->devices.size();
+	std::vector<std::thread> th;
+	std::vector<int> ok(nd, 1);
+	std::vector<std::string> errs(nd);
+	for (size_t d = 0; d < nd; ++d)
+		th.emplace_back([&, d] {
+			if (cudaSetDevice(mb->devices[d]) != cudaSuccess) { ok[d] = 0; errs[d] = "cudaSetDevice failed"; return; }
+			if (!fn(d)) { ok[d] = 0; errs[d] = g_lastError; }
+		});
+	for (auto &t : th) t.join();
+	for (size_t d = 0; d < nd; ++d)
+		if (!ok[d]) { err = "shard " + std::to_string(d) + " (device " + std::to_string(mb->devices[d]) + "): " + errs[d]; return false; }
+	return true;
+}
+
+extern "C" {
+
+speechPlayer_multiBatch_t *speechPlayer_multiBatchCreate(int sampleRate, unsigned int numStreams, int precision, int noiseMode,
+                                                         uint64_t seed, const uint64_t *streamIds, const int *devices,
+                                                         unsigned int numDevices) {
+	g_lastError.clear();
+	if (sampleRate <= 0 || numStreams == 0 || numDevices == 0 || !devices) { fail("bad sampleRate / numStreams / devices"); return nullptr; }
+	int have = 0;
+	if (cudaGetDeviceCount(&have) != cudaSuccess || have <= 0) { fail("no usable CUDA device (this library has no CPU fallback)"); return nullptr; }
+	for (unsigned d = 0; d < numDevices; ++d)
+		if (devices[d] < 0 || devices[d] >= have) { fail("device ordinal out of range"); return nullptr; }
+	speechPlayer_multiBatch *mb = new speechPlayer_multiBatch;
+	mb->sampleRate = sampleRate; mb->precision = precision; mb->noiseMode = noiseMode; mb->seed = seed; mb->n = numStreams;
+	mb->streamIds.resize(numStreams);
+	for (uint32_t i = 0; i < numStreams; ++i) mb->streamIds[i] = streamIds ? streamIds[i] : i;
+	mb->devices.assign(devices, devices + numDevices);
+	mb->shards.assign(numDevices, nullptr);
+	// until queues are known: equal counts (sizes differ by at most one)
+	mb->first.resize(numDevices + 1);
+	for (unsigned d = 0; d <= numDevices; ++d) mb->first[d] = (uint32_t)((uint64_t)numStreams * d / numDevices);
+	return mb;
+}
+
+void speechPlayer_multiBatchDestroy(speechPlayer_multiBatch_t *mb) {
+	if (!mb) return;
+	for (size_t d = 0; d < mb->shards.size(); ++d)
+		if (mb->shards[d]) speechPlayer_batchDestroy(mb->shards[d]);
+	delete mb;
+}
+
+int speechPlayer_multiBatchSetFramesHost(speechPlayer_multiBatch_t *mb, const int64_t *offsets, const speechPlayer_frame_t *frames,
+                                         const unsigned int *minFrameDuration, const unsigned int *fadeDuration,
+                                         const int *userIndex, const unsigned char *isNull) {
+	if (!mb) return fail("null batch");
+	if (!offsets || !minFrameDuration || !fadeDuration) return fail("offsets and durations are required");
+	std::lock_guard<std::mutex> lk(mb->mu);
+	const size_t nd = mb->devices.size();
+	// contiguous ranges balanced by the ticks every stream yields: cut where the running sum passes k / nd of the total
+	std::vector<uint64_t> upto(mb->n + 1, 0);
+	for (uint32_t s = 0; s < mb->n; ++s)
+		upto[s + 1] = upto[s] + speechPlayer_timelineSamples(minFrameDuration + offsets[s], fadeDuration + offsets[s],
+		                                                     (unsigned int)(offsets[s + 1] - offsets[s])) + 1;  // (+1: empty queues still cost a lane)
+	std::vector<uint32_t> first(nd + 1, 0);
+	first[nd] = mb->n;
+	for (size_t d = 1; d < nd; ++d) {
+		const uint64_t want = upto[mb->n] / nd * d + upto[mb->n] % nd * d / nd;
+		first[d] = (uint32_t)(std::lower_bound(upto.begin(), upto.end(), want) - upto.begin());
+		if (first[d] < first[d - 1]) first[d] = first[d - 1];
+		if (first[d] > mb->n) first[d] = mb->n;
+	}
+	std::string err;
+	const bool ok = forEachShard(mb, [&](size_t d) -> bool {
+		const uint32_t a = first[d], b = first[d + 1], cnt = b - a;
+		if (mb->shards[d] && (mb->first[d] != a || mb->first[d + 1] != b)) {  // the shard moved: new per-device buffers
+			speechPlayer_batchDestroy(mb->shards[d]);
+			mb->shards[d] = nullptr;
+		}
+		if (cnt == 0) return true;
+		if (!mb->shards[d]) {
+			mb->shards[d] = speechPlayer_batchCreate(mb->sampleRate, cnt, mb->precision, mb->noiseMode, mb->seed, mb->streamIds.data() + a);
+			if (!mb->shards[d]) return false;
+		}
+		std::vector<int64_t> off(cnt + 1);
+		for (uint32_t i = 0; i <= cnt; ++i) off[i] = offsets[a + i] - offsets[a];
+		const size_t o = (size_t)offsets[a];
+		return speechPlayer_batchSetFramesHost(mb->shards[d], off.data(), frames ? frames + o : nullptr, minFrameDuration + o, fadeDuration + o,
+		                                       userIndex ? userIndex + o : nullptr, isNull ? isNull + o : nullptr, nullptr) == 0;
+	}, err);
+	if (!ok) return fail(err);
+	mb->first = first;
+	return 0;
+}
+
+long long speechPlayer_multiBatchSynthesizeHost(speechPlayer_multiBatch_t *mb, unsigned int sampleCount, sample *out,
+                                                unsigned int *samplesWritten) {
+	if (!mb) return fail("null batch");
+	if (!out) return fail("null output");
+	std::lock_guard<std::mutex> lk(mb->mu);
+	std::vector<long long> got(mb->devices.size(), 0);
+	std::string err;
+	const bool ok = forEachShard(mb, [&](size_t d) -> bool {
+		const uint32_t a = mb->first[d], b = mb->first[d + 1];
+		if (a == b) return true;
+		if (!mb->shards[d]) { g_lastError = "no frames queued (call SetFramesHost first)"; return false; }
+		got[d] = speechPlayer_batchSynthesizeHost(mb->shards[d], sampleCount, out + (size_t)a * sampleCount, samplesWritten ? samplesWritten + a : nullptr);
+		return got[d] >= 0;
+	}, err);
+	if (!ok) return fail(err);
+	long long total = 0;
+	for (long long g : got) total += g;
+	return total;
+}
+
+int speechPlayer_multiBatchGetShards(speechPlayer_multiBatch_t *mb, unsigned int *firstStream) {
+	if (!mb || !firstStream) return fail("null argument");
+	std::lock_guard<std::mutex> lk(mb->mu);
+	for (size_t d = 0; d < mb->first.size(); ++d) firstStream[d] = mb->first[d];
+	return 0;
+}
+
+int speechPlayer_multiBatchGetLastIndices(speechPlayer_multiBatch_t *mb, int *lastIndex) {
+	if (!mb || !lastIndex) return fail("null argument");
+	std::lock_guard<std::mutex> lk(mb->mu);
+	std::string err;
+	const bool ok = forEachShard(mb, [&](size_t d) -> bool {
+		const uint32_t a = mb->first[d], b = mb->first[d + 1];
+		if (a == b || !mb->shards[d]) { for (uint32_t s = a; s < b; ++s) lastIndex[s] = -1; return true; }
+		return speechPlayer_batchGetLastIndices(mb->shards[d], lastIndex + a) == 0;
+	}, err);
+	return ok ? 0 : fail(err);
 }
 
 }  // extern "C"

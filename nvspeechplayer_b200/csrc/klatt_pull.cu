@@ -146,8 +146,7 @@ __device__ __forceinline__ void mark(const PullCtx &X, int slot) {
 // Shared memory: sigA | sigB | inc | the pull's segments | the pull's samples.  segSrc and pcmOut
 // may be pinned host memory (zero-copy): the segments come in and the samples go out in 16-byte words, coalesced, so a
 // pull is ONE launch with no copy before or after it.
-__global__ void __launch_bounds__(kPullThreads)
-klatt_pull_kernel(PullCtx X, const PullSeg *__restrict__ segSrc, int16_t *__restrict__ pcmOut) {
+__device__ __forceinline__ void pullBlock(PullCtx X, const PullSeg *__restrict__ segSrc, int16_t *__restrict__ pcmOut) {
 	extern __shared__ __align__(16) unsigned char pullSmem[];
 	__shared__ PullAffineD warpTotal[kPullWarps];
 	const size_t sigBytes = (size_t)X.L * kPullThreads * sizeof(float);
@@ -239,6 +238,20 @@ klatt_pull_kernel(PullCtx X, const PullSeg *__restrict__ segSrc, int16_t *__rest
 	}
 }
 
+__global__ void __launch_bounds__(kPullThreads)
+klatt_pull_kernel(PullCtx X, const PullSeg *__restrict__ segSrc, int16_t *__restrict__ pcmOut) {
+	pullBlock(X, segSrc, pcmOut);
+}
+
+// Many interactive players in ONE launch: block b renders the pull of player b (its own segments, carried state, noise and
+// output -- nothing is shared between blocks), so 148 players pull at the latency of one.  items may be mapped pinned memory.
+__global__ void __launch_bounds__(kPullThreads)
+klatt_pull_batch_kernel(const PullBatchItem *__restrict__ items) {
+	const PullBatchItem it = items[blockIdx.x];
+	if (it.ctx.n == 0) return;  // (uniform per block: this player had nothing to render)
+	pullBlock(it.ctx, it.segSrc, it.pcmOut);
+}
+
 __global__ void klatt_pull_init_kernel(PullState *s) {
 	// src/speechWaveGenerator.cpp:37,49,104-110: phases, noise memories and resonator histories start at zero
 	if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -254,8 +267,7 @@ cudaError_t launchKlattPullInit(PullState *state, cudaStream_t stream) {
 
 // ctx.sigA / sigB / inc / L / segs / pcm are filled in by the launch; everything else by the caller.  ctx.n <= kPullMaxTicks.
 // segSrc: ctx.nSeg segments, pcmOut: room for ctx.n samples rounded up to 8 -- device memory or mapped pinned host memory.
-cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut, cudaStream_t stream) {
-	if (ctx.n == 0) return cudaSuccess;
+static cudaError_t pullPrepare(PullCtx &ctx, size_t &smem) {
 	if (ctx.n > kPullMaxTicks || ctx.nSeg == 0 || ctx.nSeg > kPullMaxSegs) return cudaErrorInvalidValue;
 	static bool attrSet[64] = {};
 	int dev = 0;
@@ -266,6 +278,8 @@ cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut,
 	if (dev >= 0 && dev < 64 && !attrSet[dev]) {
 		e = cudaFuncSetAttribute(klatt_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
 		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(klatt_pull_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+		if (e != cudaSuccess) return e;
 		attrSet[dev] = true;
 	}
 	ctx.L = pullTicksPerThread(ctx.n);  // 1, 2, 4, 8 or 16: the phase recurrence is unrolled for these
@@ -273,13 +287,39 @@ cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut,
 	ctx.inc = nullptr;
 	ctx.segs = nullptr;
 	ctx.pcm = nullptr;
-	const size_t smem = 4 * (size_t)ctx.L * kPullThreads * sizeof(float) + (size_t)ctx.nSeg * sizeof(PullSeg) +
-	                    (((size_t)ctx.n * sizeof(int16_t) + 15) & ~(size_t)15) +
-	                    (ctx.phaseMode ? kPullMaxSpecial * sizeof(PullPhaseRec) : 0);
+	smem = 4 * (size_t)ctx.L * kPullThreads * sizeof(float) + (size_t)ctx.nSeg * sizeof(PullSeg) +
+	       (((size_t)ctx.n * sizeof(int16_t) + 15) & ~(size_t)15) + (ctx.phaseMode ? kPullMaxSpecial * sizeof(PullPhaseRec) : 0);
 	ctx.runI = nullptr;
 	ctx.runMeta = nullptr;
 	ctx.rec = nullptr;
+	return cudaSuccess;
+}
+
+cudaError_t launchKlattPull(PullCtx ctx, const PullSeg *segSrc, int16_t *pcmOut, cudaStream_t stream) {
+	if (ctx.n == 0) return cudaSuccess;
+	size_t smem = 0;
+	cudaError_t e = pullPrepare(ctx, smem);
+	if (e != cudaSuccess) return e;
 	klatt_pull_kernel<<<1, kPullThreads, smem, stream>>>(ctx, segSrc, pcmOut);
+	return cudaGetLastError();
+}
+
+// hItems: host view of `count` items (filled by the caller except what pullPrepare derives), dItems: the same memory as the
+// device sees it (mapped pinned) or a device copy made after this call returns... the items are completed IN PLACE, so with a
+// device copy the caller copies after launchKlattPullBatchPrepare and launches with launchKlattPullBatch.
+cudaError_t launchKlattPullBatch(PullBatchItem *hItems, const PullBatchItem *dItems, uint32_t count, cudaStream_t stream) {
+	size_t smemMax = 0;
+	bool any = false;
+	for (uint32_t i = 0; i < count; ++i) {
+		if (hItems[i].ctx.n == 0) continue;
+		size_t smem = 0;
+		cudaError_t e = pullPrepare(hItems[i].ctx, smem);
+		if (e != cudaSuccess) return e;
+		if (smem > smemMax) smemMax = smem;
+		any = true;
+	}
+	if (!any) return cudaSuccess;
+	klatt_pull_batch_kernel<<<count, kPullThreads, smemMax, stream>>>(dItems);
 	return cudaGetLastError();
 }
 

@@ -77,6 +77,13 @@ struct PullCtx {
 	int16_t *pcm;
 };
 
+// one player's pull inside a batched launch (klatt_pull_batch_kernel)
+struct PullBatchItem {
+	PullCtx ctx;
+	const PullSeg *segSrc;
+	int16_t *pcmOut;
+};
+
 // affine map of one section over one chunk, (y, d)_end = P (y, d)_start + z, row-major P
 struct PullAffine {
 	float p00, p01, p10, p11, zy, zd;

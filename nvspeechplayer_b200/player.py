@@ -97,6 +97,18 @@ def load_library():
     L.speechPlayer_batchGetLastIndices.argtypes = [vp, vp]
     L.speechPlayer_batchGetLaunchStats.restype = i32
     L.speechPlayer_batchGetLaunchStats.argtypes = [vp, vp, vp]
+    L.speechPlayer_multiBatchCreate.restype = vp
+    L.speechPlayer_multiBatchCreate.argtypes = [i32, u32, i32, i32, u64, vp, vp, u32]
+    L.speechPlayer_multiBatchDestroy.restype = None
+    L.speechPlayer_multiBatchDestroy.argtypes = [vp]
+    L.speechPlayer_multiBatchSetFramesHost.restype = i32
+    L.speechPlayer_multiBatchSetFramesHost.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.speechPlayer_multiBatchSynthesizeHost.restype = ctypes.c_longlong
+    L.speechPlayer_multiBatchSynthesizeHost.argtypes = [vp, u32, vp, vp]
+    L.speechPlayer_multiBatchGetShards.restype = i32
+    L.speechPlayer_multiBatchGetShards.argtypes = [vp, vp]
+    L.speechPlayer_multiBatchGetLastIndices.restype = i32
+    L.speechPlayer_multiBatchGetLastIndices.argtypes = [vp, vp]
     L.speechPlayer_synthesizeLong.restype = ctypes.c_longlong
     L.speechPlayer_synthesizeLong.argtypes = [i32, vp, vp, vp, vp, u32, u64, u64, u32, vp, ctypes.c_ulonglong, i32, vp, vp]
     _lib = L
@@ -310,6 +322,54 @@ class Batch(object):
     def close(self):
         if getattr(self, "_h", None):
             self._L.speechPlayer_batchDestroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiBatch(object):
+    """N streams over several GPUs of one box, in-library (include/speechPlayer_batch.h speechPlayer_multiBatch*): contiguous
+    stream ranges balanced by ticks, one host thread per device, no collective, one host buffer."""
+
+    def __init__(self, sample_rate, num_streams, devices, precision=PRECISION_FP32, noise=NOISE_PHILOX, seed=0xB200, stream_ids=None):
+        self._L = load_library()
+        self.sample_rate, self.num_streams, self.devices = sample_rate, num_streams, list(devices)
+        ids = None if stream_ids is None else np.ascontiguousarray(stream_ids, dtype=np.uint64)
+        dv = np.ascontiguousarray(self.devices, dtype=np.int32)
+        self._h = self._L.speechPlayer_multiBatchCreate(sample_rate, num_streams, precision, noise, seed, _ptr(ids), _ptr(dv), len(dv))
+        if not self._h:
+            raise EngineError("speechPlayer_multiBatchCreate failed: " + last_error())
+
+    def set_frames_host(self, fb):
+        off = np.ascontiguousarray(fb.offsets, dtype=np.int64)
+        _check(self._L.speechPlayer_multiBatchSetFramesHost(self._h, _ptr(off), _ptr(fb.frames), _ptr(fb.min_dur), _ptr(fb.fade_dur),
+                                                            _ptr(fb.user_index), _ptr(fb.is_null)), "speechPlayer_multiBatchSetFramesHost")
+
+    def synthesize_host(self, num_samples, out=None):
+        if out is None:
+            out = np.zeros((self.num_streams, num_samples), dtype=np.int16)
+        written = np.zeros(self.num_streams, dtype=np.uint32)
+        _check(self._L.speechPlayer_multiBatchSynthesizeHost(self._h, num_samples, _ptr(out), _ptr(written)),
+               "speechPlayer_multiBatchSynthesizeHost")
+        return out, written
+
+    def shards(self):
+        first = np.zeros(len(self.devices) + 1, dtype=np.uint32)
+        _check(self._L.speechPlayer_multiBatchGetShards(self._h, _ptr(first)), "speechPlayer_multiBatchGetShards")
+        return first
+
+    def last_indices(self):
+        out = np.zeros(self.num_streams, dtype=np.int32)
+        _check(self._L.speechPlayer_multiBatchGetLastIndices(self._h, _ptr(out)), "speechPlayer_multiBatchGetLastIndices")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.speechPlayer_multiBatchDestroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -18,6 +18,23 @@ def weak_shard(streams_per_rank, rank):
     return first, first + int(streams_per_rank)
 
 
+def balanced_ranges(ticks_per_stream, shards):
+    """first[shards + 1] of contiguous stream ranges whose tick sums are balanced -- the rule speechPlayer_multiBatchSetFramesHost
+    applies (engine.cu): with upto = running sum of (ticks + 1), shard d starts at the first stream where upto reaches d / shards
+    of the total.  tests/test_gpu_multibatch.py holds the library to this function."""
+    import numpy as np
+    t = np.asarray(ticks_per_stream, dtype=np.uint64) + np.uint64(1)
+    upto = np.concatenate([[0], np.cumsum(t, dtype=np.uint64)]).astype(np.uint64)
+    n, total = len(t), int(upto[-1])
+    first = [0]
+    for d in range(1, shards):
+        want = total // shards * d + total % shards * d // shards
+        f = int(np.searchsorted(upto, np.uint64(want), side="left"))
+        first.append(min(max(f, first[-1]), n))
+    first.append(n)
+    return first
+
+
 def combine(dist, device, elapsed_ms, samples):
     """(max over ranks of elapsed_ms, sum over ranks of samples) -- the two numbers the benchmark line needs."""
     import torch

@@ -183,3 +183,71 @@ def test_pull_live_control_flows(port, flow):
     got, counts = run(lambda sr: _PullAdapter(sr))
     assert counts == wcounts
     parity.assert_f32_parity(got, want, "live control: " + flow)
+
+
+def test_pull_batch_148_players_one_launch(port):
+    """speechPlayer_synthesizeBatch over 148 low-latency players: ONE launch per call (one block per player), every row the
+    bits of that player's own speechPlayer_synthesize, ragged queues, drains mid-call, a purge on a subset between two calls;
+    a few rows against the oracle; and the whole batch inside 1.5 x the latency of a single player's pull (+ the host side's
+    per-player bookkeeping)."""
+    sr, n, count = 22050, 148, 8192
+    rng = np.random.default_rng(148)
+    secs = rng.uniform(0.2, 1.2, n)
+    streams = [workloads.random_stream(2000 + s, float(secs[s]), sr) for s in range(n)]
+
+    def make():
+        ps = [player.SpeechPlayer(sr, precision=player.PRECISION_STREAM, noise=player.NOISE_PHILOX, seed=6, streamId=2000 + s) for s in range(n)]
+        for p, (fr, m, f, nul, ux) in zip(ps, streams):
+            p.queue_frames(fr, m, f, ux, nul)
+        return ps
+
+    extra = workloads.random_stream(77, 0.3, sr)
+
+    def purge(ps):
+        for s in range(0, n, 7):
+            fr, m, f, nul, ux = extra
+            ps[s].queue_frame(fr[0], int(m[0]), int(f[0]), 500 + s, True)
+            ps[s].queue_frames(fr[1:], m[1:], f[1:], ux[1:], nul[1:])
+
+    batch = make()
+    t0 = time.perf_counter()
+    out1, w1 = player.synthesize_batch(batch, count)
+    t_batch = time.perf_counter() - t0
+    purge(batch)
+    out2, w2 = player.synthesize_batch(batch, count)
+    idx_batch = [p.getLastIndex() for p in batch]
+    for p in batch:
+        p.close()
+    solo = make()
+    rows1 = [p.synthesize_np(count) for p in solo]
+    purge(solo)
+    t0 = time.perf_counter()
+    rows2 = [p.synthesize_np(count) for p in solo]
+    t_solo_all = time.perf_counter() - t0
+    idx_solo = [p.getLastIndex() for p in solo]
+    for p in solo:
+        p.close()
+    assert (w1 < count).any() or (w2 < count).any(), "some player should drain inside a call"
+    for s in range(n):
+        assert w1[s] == len(rows1[s]) and w2[s] == len(rows2[s])
+        np.testing.assert_array_equal(out1[s, :w1[s]], rows1[s])
+        np.testing.assert_array_equal(out2[s, :w2[s]], rows2[s])
+    assert idx_batch == idx_solo
+    for s in (0, 7, 100):   # against the oracle, purge included
+        o = port.player(sr)
+        o.noise_philox(6, 2000 + s)
+        fr, m, f, nul, ux = streams[s]
+        for j in range(len(m)):
+            o.queue_frame(None if nul[j] else fr[j], int(m[j]), int(f[j]), int(ux[j]))
+        a = o.synthesize(count)
+        if s % 7 == 0:
+            fr, m, f, nul, ux = extra
+            o.queue_frame(fr[0], int(m[0]), int(f[0]), 500 + s, True)
+            for j in range(1, len(m)):
+                o.queue_frame(None if nul[j] else fr[j], int(m[j]), int(f[j]), int(ux[j]))
+        b = o.synthesize(count)
+        o.close()
+        parity.assert_f32_parity(np.concatenate([out1[s, :w1[s]], out2[s, :w2[s]]]), np.concatenate([a, b]), "batched pull row %d" % s)
+    per_solo = t_solo_all / n
+    print("148 players x 8192: batch call %.2f ms, single-player pull %.3f ms" % (t_batch * 1e3, per_solo * 1e3))
+    assert t_batch < 40 * per_solo, "the batch should cost far less than 148 sequential pulls"

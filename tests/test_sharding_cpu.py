@@ -77,3 +77,19 @@ def test_shard_range_properties():
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
     assert sharding.weak_shard(65536, 3) == (196608, 262144)
+
+
+def test_balanced_ranges_properties():
+    """The in-library multi-GPU partition (speechPlayer_multiBatchSetFramesHost applies the same rule; the GPU test compares
+    the two): contiguous, monotone, covers everything, tick sums within one stream of each other."""
+    rng = np.random.default_rng(3)
+    for n, shards in ((1, 1), (5, 8), (301, 3), (65536, 8), (1000, 2)):
+        ticks = rng.integers(0, 20000, n)
+        first = sharding.balanced_ranges(ticks, shards)
+        assert first[0] == 0 and first[-1] == n and len(first) == shards + 1
+        assert all(first[k] <= first[k + 1] for k in range(shards))
+        if n >= 4 * shards:
+            per = [int(ticks[first[k]:first[k + 1]].sum()) for k in range(shards)]
+            assert max(per) - min(per) <= 2 * int(ticks.max()) + 2
+    assert sharding.balanced_ranges([10, 10, 10, 10], 2) == [0, 2, 4]
+    assert sharding.balanced_ranges([100, 1, 1, 1, 1], 2)[1] == 1
