@@ -220,107 +220,132 @@ struct VibWalk {
 // config 4, 45 % of the whole call, all of it load latency).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTimelineTile = 256;
+
+// inclusive scan of one uint64 per thread over the block (Hillis-Steele in shared memory: 256 values, 8 steps)
+__device__ __forceinline__ uint64_t tileScanAdd(uint64_t v, uint64_t *buf) {
+	const int tid = threadIdx.x;
+	buf[tid] = v;
+	__syncthreads();
+	for (int d = 1; d < kTimelineTile; d <<= 1) {
+		const uint64_t up = tid >= d ? buf[tid - d] : 0;
+		__syncthreads();
+		buf[tid] += up;
+		__syncthreads();
+	}
+	return buf[tid];
+}
+
 __global__ void __launch_bounds__(kTimelineTile)
 klatt_long_timeline_kernel(LongStream L) {
-	__shared__ uint32_t sM[kTimelineTile], sF[kTimelineTile];
+	__shared__ uint64_t scanBuf[kTimelineTile];
 	__shared__ uint8_t sNull[kTimelineTile];
-	__shared__ double sP0[kTimelineTile], sP1[kTimelineTile];
-	__shared__ int64_t sV0[kTimelineTile], sVs[kTimelineTile], sVF[kTimelineTile];
-	__shared__ uint64_t oStart[kTimelineTile], oVib[kTimelineTile];
-	__shared__ int32_t oPrev[kTimelineTile];
+	__shared__ double sPNew[kTimelineTile], sInc[kTimelineTile];       // new.voicePitch after :71 (real requests), voicePitchInc
+	__shared__ uint64_t sHold[kTimelineTile];                          // hold ticks F+2 .. occ-1 of the request
+	__shared__ double gLanding[kTimelineTile], gEnd[kTimelineTile];    // the speculative glides
 	__shared__ double oPop[kTimelineTile], oOld[kTimelineTile], oNew[kTimelineTile], oInc[kTimelineTile];
-	__shared__ double gLanding[kTimelineTile], gEnd[kTimelineTile];  // the speculative glides
-	// The pitch a request inherits is a serial chain through the hold glide of its predecessor -- n repeated FP64 additions,
-	// exact in closed form (glideExact) but ~1 us each on one thread.  The chain only enters a request through the LANDING
-	// value old + (new - old) * 1.0, which is insensitive to the last bits of `old` almost always: thread 0 runs the chain with
-	// the glide in plain closed form (a guess good to a few ulps), all threads compute the exact glides from the guessed
-	// landings at once, and thread 0 walks the chain again with the exact values, keeping every glide whose landing it
-	// confirms bit for bit and redoing the few it does not.
-	uint64_t t = 0, vibPos = 0;
-	int32_t prevReal = -1;
-	bool oldIsNull = true, gOldIsNull = true;
-	double pitchCur = 0.0, gCur = 0.0;
-	int64_t vPrev = 0;
+	// Everything that is a prefix sum (start ticks, vibrato phase, last real request) is scanned by the whole block.  What is
+	// left is the pitch a request inherits: a serial chain through the hold glide of its predecessor -- n repeated FP64
+	// additions, exact in closed form (glideExact) but ~1 us each on one thread.  The chain only enters a request through the
+	// LANDING value old + (new - old) * 1.0, which is insensitive to the last bits of `old` almost always: thread 0 runs the
+	// chain with the glide in plain closed form (a guess good to a few ulps), all threads compute the exact glides from the
+	// guessed landings at once, and thread 0 walks the chain again with the exact values, keeping every glide whose landing
+	// it confirms bit for bit and redoing the few it does not.  (Round 1 walked global memory on one thread: 39 ms for the
+	// 40 072 requests of config 4, 45 % of the whole call.)
+	uint64_t tBase = 0, vibBase = 0;      // carried across tiles (every thread keeps the same copy)
+	int64_t vPrevCarry = 0;
+	int32_t prevRealCarry = -1;
+	bool oldIsNull = true, gOldIsNull = true;   // thread 0
+	double pitchCur = 0.0, gCur = 0.0;          // thread 0
 	const int tid = threadIdx.x;
 	for (uint32_t base = 0; base < L.nReq; base += kTimelineTile) {
 		const uint32_t j = base + tid;
 		const uint32_t n = L.nReq - base < (uint32_t)kTimelineTile ? L.nReq - base : (uint32_t)kTimelineTile;
-		if (j < L.nReq) {
-			sM[tid] = L.minDur[j];
-			sF[tid] = L.fadeDur[j];
-			sNull[tid] = reqIsNull(L, j) ? 1 : 0;
-			sP0[tid] = L.frames[(size_t)j * kNumParams + kVoicePitch];
-			sP1[tid] = L.frames[(size_t)j * kNumParams + kEndVoicePitch];
+		const bool in = j < L.nReq;
+		uint64_t occ = 0, vibOwn = 0;
+		int64_t vF = 0, v0 = 0, vs = 0;
+		uint64_t F = 1;
+		bool null = true;
+		if (in) {
+			const uint64_t M = L.minDur[j];
+			const uint32_t fd = L.fadeDur[j];
+			F = fd > 1u ? fd : 1u;
+			null = reqIsNull(L, j);
+			occ = (M + 1 > F + 2) ? M + 1 : F + 2;
 			const FadePlanF32 &p = L.plans[j];
-			sV0[tid] = p.vibInc0; sVs[tid] = p.vibIncStep; sVF[tid] = p.vibIncFinal;
+			v0 = p.vibInc0; vs = p.vibIncStep; vF = p.vibIncFinal;
+			vibOwn = (F - 1) * (uint64_t)v0 + (uint64_t)vs * ((F - 1) * F / 2) + (occ - F) * (uint64_t)vF;  // (+ the predecessor's final increment once)
+			double inc = 0.0, pNew = 0.0;
+			if (!null) {
+				const double p0 = L.frames[(size_t)j * kNumParams + kVoicePitch], p1 = L.frames[(size_t)j * kNumParams + kEndVoicePitch];
+				inc = (p1 - p0) / (double)M;       // src/frame.cpp:98
+				pNew = p0 + inc * (double)F;      // :71
+			}
+			sNull[tid] = null ? 1 : 0; sInc[tid] = inc; sPNew[tid] = pNew; sHold[tid] = occ - F - 2;
 		}
+		// start tick = exclusive sum of the occupancies
+		const uint64_t tIncl = tileScanAdd(occ, scanBuf);
+		const uint64_t start = tBase + tIncl - occ;
+		const uint64_t tTile = scanBuf[kTimelineTile - 1];
 		__syncthreads();
-		if (tid == 0) {  // integers of the timeline, and the guessed pitch chain
+		// vibrato phase before the pop tick = exclusive sum of (own sum + the predecessor's final increment)
+		scanBuf[tid] = in ? (uint64_t)vF : 0;
+		__syncthreads();
+		const int64_t vPrev = tid == 0 ? vPrevCarry : (int64_t)scanBuf[tid - 1];
+		const int64_t vLast = (int64_t)scanBuf[n - 1];
+		__syncthreads();
+		const uint64_t vibMine = in ? vibOwn + (uint64_t)vPrev : 0;
+		const uint64_t vIncl = tileScanAdd(vibMine, scanBuf);
+		const uint64_t vibStart = vibBase + vIncl - vibMine;
+		const uint64_t vibTile = scanBuf[kTimelineTile - 1];
+		__syncthreads();
+		// last real request before j: running maximum of (real ? index + 1 : 0)
+		scanBuf[tid] = (in && !null) ? (uint64_t)j + 1 : 0;
+		__syncthreads();
+		for (int d = 1; d < kTimelineTile; d <<= 1) {
+			const uint64_t up = tid >= d ? scanBuf[tid - d] : 0;
+			__syncthreads();
+			if (up > scanBuf[tid]) scanBuf[tid] = up;
+			__syncthreads();
+		}
+		const uint64_t before = tid == 0 ? 0 : scanBuf[tid - 1];
+		const int32_t prevReal = before ? (int32_t)before - 1 : prevRealCarry;
+		const uint64_t lastReal = scanBuf[kTimelineTile - 1];
+		__syncthreads();
+		if (in) { L.start[j] = start; L.vibPosStart[j] = vibStart; L.prevReal[j] = prevReal; }
+		tBase += tTile; vibBase += vibTile; vPrevCarry = vLast;
+		if (lastReal) prevRealCarry = (int32_t)lastReal - 1;
+
+		if (tid == 0) {  // the guessed pitch chain
 			for (uint32_t k = 0; k < n; ++k) {
-				const uint64_t M = sM[k];
-				const uint64_t F = sF[k] > 1u ? sF[k] : 1u;
-				const bool null = sNull[k] != 0;
-				const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
-				oStart[k] = t;
-				oPrev[k] = prevReal;
-				oVib[k] = vibPos;
-				vibPos += (uint64_t)vPrev + (F - 1) * (uint64_t)sV0[k] + (uint64_t)sVs[k] * ((F - 1) * F / 2) + (occ - F) * (uint64_t)sVF[k];
-				vPrev = sVF[k];
-				if (!null) prevReal = (int32_t)(base + k);
-				t += occ;
-				double pOld = gCur, pNew, inc;
-				if (null) { pNew = gCur; inc = 0.0; }
-				else { pNew = sP0[k]; inc = (sP1[k] - sP0[k]) / (double)M; if (gOldIsNull) pOld = pNew; }
-				pNew += inc * (double)F;
+				const bool nul = sNull[k] != 0;
+				double pOld = gCur, pNew = nul ? gCur : sPNew[k];
+				if (!nul && gOldIsNull) pOld = pNew;
 				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
 				gLanding[k] = landing;
-				oInc[k] = inc;
-				gCur = landing + (double)(occ - F - 2) * inc;
-				gOldIsNull = null;
+				gCur = landing + (double)sHold[k] * sInc[k];
+				gOldIsNull = nul;
 			}
 		}
 		__syncthreads();
-		if (j < L.nReq) {
-			const uint64_t M = sM[tid], F = sF[tid] > 1u ? sF[tid] : 1u;
-			const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
-			gEnd[tid] = glideExact(gLanding[tid], oInc[tid], occ - F - 2);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
-		}
+		if (in) gEnd[tid] = glideExact(gLanding[tid], sInc[tid], sHold[tid]);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
 		__syncthreads();
 		if (tid == 0) {  // the true chain
 			for (uint32_t k = 0; k < n; ++k) {
-				const uint64_t M = sM[k];
-				const uint64_t F = sF[k] > 1u ? sF[k] : 1u;
-				const bool null = sNull[k] != 0;
+				const bool nul = sNull[k] != 0;
 				oPop[k] = pitchCur;
-				double pOld = pitchCur, pNew, inc;
-				if (null) {  // src/frame.cpp:59-63
-					pNew = pitchCur;
-					inc = 0.0;
-				} else {
-					pNew = sP0[k];
-					inc = (sP1[k] - sP0[k]) / (double)M;  // src/frame.cpp:98
-					if (oldIsNull) pOld = pNew;            // :64-67
-				}
-				pNew += inc * (double)F;  // :71
-				oOld[k] = pOld; oNew[k] = pNew;
-				const uint64_t occ = (M + 1 > F + 2) ? M + 1 : F + 2;
+				double pOld = pitchCur, pNew = nul ? pitchCur : sPNew[k];   // src/frame.cpp:59-63 / :71
+				if (!nul && oldIsNull) pOld = pNew;                           // :64-67
+				oOld[k] = pOld; oNew[k] = pNew; oInc[k] = sInc[k];
 				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
-				const bool same = __double_as_longlong(landing) == __double_as_longlong(gLanding[k]) &&
-				                  __double_as_longlong(inc) == __double_as_longlong(oInc[k]);
-				pitchCur = same ? gEnd[k] : glideExact(landing, inc, occ - F - 2);
-				oInc[k] = inc;
-				oldIsNull = null;
+				pitchCur = __double_as_longlong(landing) == __double_as_longlong(gLanding[k]) ? gEnd[k] : glideExact(landing, sInc[k], sHold[k]);
+				oldIsNull = nul;
 			}
 		}
 		__syncthreads();
-		if (j < L.nReq) {
-			L.start[j] = oStart[tid]; L.prevReal[j] = oPrev[tid]; L.pitchPop[j] = oPop[tid];
-			L.pitchOld[j] = oOld[tid]; L.pitchNew[j] = oNew[tid]; L.pitchInc[j] = oInc[tid];
-			L.vibPosStart[j] = oVib[tid];
-		}
+		if (in) { L.pitchPop[j] = oPop[tid]; L.pitchOld[j] = oOld[tid]; L.pitchNew[j] = oNew[tid]; L.pitchInc[j] = oInc[tid]; }
 		__syncthreads();
 	}
-	if (tid == 0) L.start[L.nReq] = t;
+	if (tid == 0) L.start[L.nReq] = tBase;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

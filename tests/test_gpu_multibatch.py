@@ -36,7 +36,7 @@ def test_multibatch_equals_one_batch_and_balances_by_ticks(prec):
     assert list(first) == sharding.balanced_ranges(fb.timeline_samples(), shards)
     ticks = fb.timeline_samples().astype(np.int64)
     per = [int(ticks[first[d]:first[d + 1]].sum()) for d in range(shards)]
-    assert max(per) - min(per) <= int(ticks.max()) + 1, per
+    assert max(per) - min(per) <= 2 * int(ticks.max()) + 2, per   # a cut lands within one stream of the ideal point
     assert first[1] - first[0] < first[2] - first[1]   # fewer of the long streams in the first shard
     parts = [mb.synthesize_host(c) for c in (3000, count - 3000)]
     out = np.concatenate([p[0] for p in parts], axis=1)

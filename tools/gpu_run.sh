@@ -82,5 +82,28 @@ c5)  # block scheduler: how many classes (loop pairs) may be in flight per SM
 	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_f32_block_kernel -s 3 -c 1 -f -o $O/prof_block \
 		python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_block.log 2>&1; echo "ncu block rc=$?"; ls -la $O/prof_block.ncu-rep
 	;;
+c6)  # completeness round: whole suite (multi-batch, sinks, batched pull, kernel b), kernel (b) timings + captures, pull bench
+	timeout 1200 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -8 $O/pytest_gpu.log
+	timeout 400 python bench.py --workload long --steps 3 --warmup 3 > $O/bench_long.json 2> $O/bench_long.err; echo "bench long rc=$?"; cut -c1-300 $O/bench_long.json; tail -3 $O/bench_long.err
+	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/long_launches.csv \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/long_launches.log 2>&1; echo "ncu long list rc=$?"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_long_stage -s 60 -c 3 -f -o $O/prof_long \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/ncu_long.log 2>&1; echo "ncu long rc=$?"
+	timeout 300 python bench.py --workload pull > $O/bench_pull.json 2> $O/bench_pull.err; echo "bench pull rc=$?"; cut -c1-2000 $O/bench_pull.json; tail -3 $O/bench_pull.err
+	;;
+c7)  # validation after the timeline rewrite and the multi-batch test fix
+	timeout 1200 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -5 $O/pytest_gpu.log
+	timeout 400 python bench.py --workload long --steps 3 --warmup 3 > $O/bench_long.json 2> $O/bench_long.err; echo "bench long rc=$?"; cut -c1-300 $O/bench_long.json; tail -3 $O/bench_long.err
+	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/long_launches.csv \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/long_launches.log 2>&1; echo "ncu long list rc=$?"
+	timeout 200 python tools/multibatch_bench.py --gpus 1 --streams-per-gpu 16384 > $O/multibatch_1gpu.json 2> $O/multibatch.err; echo "multibatch rc=$?"; cat $O/multibatch_1gpu.json; tail -2 $O/multibatch.err
+	;;
+mg)  # N GPUs of one box (gpurun --gpus N): concurrent D2H ceiling, the in-library multi-GPU line, the torchrun bench
+	N=${1:-8}
+	for g in 1 2 4 8; do [ $g -le $N ] && { timeout 300 tools/d2h_probe $g 1024 6 > $O/d2h_${g}gpu.json 2>&1; cat $O/d2h_${g}gpu.json; }; done
+	timeout 600 python tools/multibatch_bench.py --gpus $N --streams-per-gpu 16384 > $O/multibatch_${N}gpu.json 2> $O/multibatch.err; echo "multibatch rc=$?"; cat $O/multibatch_${N}gpu.json; tail -2 $O/multibatch.err
+	timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline \
+		> $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err; echo "bench x$N rc=$?"; cut -c1-2500 $O/bench_${N}gpu.json; tail -3 $O/bench_${N}gpu.err
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
