@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kTimelineTile)
 klatt_long_timeline_kernel(LongStream L) {
 	__shared__ uint64_t scanBuf[kTimelineTile];
 	__shared__ uint8_t sNull[kTimelineTile];
-	__shared__ double sPNew[kTimelineTile], sInc[kTimelineTile];       // new.voicePitch after :71 (real requests), voicePitchInc
+	__shared__ double sP0[kTimelineTile], sPNew[kTimelineTile], sInc[kTimelineTile];  // the frame's voicePitch, new.voicePitch after :71 (real requests), voicePitchInc
 	__shared__ uint64_t sHold[kTimelineTile];                          // hold ticks F+2 .. occ-1 of the request
 	__shared__ double gLanding[kTimelineTile], gEnd[kTimelineTile];    // the speculative glides
 	__shared__ double oPop[kTimelineTile], oOld[kTimelineTile], oNew[kTimelineTile], oInc[kTimelineTile];
@@ -274,13 +274,14 @@ klatt_long_timeline_kernel(LongStream L) {
 			const FadePlanF32 &p = L.plans[j];
 			v0 = p.vibInc0; vs = p.vibIncStep; vF = p.vibIncFinal;
 			vibOwn = (F - 1) * (uint64_t)v0 + (uint64_t)vs * ((F - 1) * F / 2) + (occ - F) * (uint64_t)vF;  // (+ the predecessor's final increment once)
-			double inc = 0.0, pNew = 0.0;
+			double inc = 0.0, pNew = 0.0, pStart = 0.0;
 			if (!null) {
 				const double p0 = L.frames[(size_t)j * kNumParams + kVoicePitch], p1 = L.frames[(size_t)j * kNumParams + kEndVoicePitch];
 				inc = (p1 - p0) / (double)M;       // src/frame.cpp:98
 				pNew = p0 + inc * (double)F;      // :71
+				pStart = p0;
 			}
-			sNull[tid] = null ? 1 : 0; sInc[tid] = inc; sPNew[tid] = pNew; sHold[tid] = occ - F - 2;
+			sNull[tid] = null ? 1 : 0; sInc[tid] = inc; sPNew[tid] = pNew; sP0[tid] = pStart; sHold[tid] = occ - F - 2;
 		}
 		// start tick = exclusive sum of the occupancies
 		const uint64_t tIncl = tileScanAdd(occ, scanBuf);
@@ -319,7 +320,7 @@ klatt_long_timeline_kernel(LongStream L) {
 			for (uint32_t k = 0; k < n; ++k) {
 				const bool nul = sNull[k] != 0;
 				double pOld = gCur, pNew = nul ? gCur : sPNew[k];
-				if (!nul && gOldIsNull) pOld = pNew;
+				if (!nul && gOldIsNull) pOld = sP0[k];   // :64-67 copies the frame BEFORE :71 moves new.voicePitch
 				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
 				gLanding[k] = landing;
 				gCur = landing + (double)sHold[k] * sInc[k];
@@ -334,7 +335,7 @@ klatt_long_timeline_kernel(LongStream L) {
 				const bool nul = sNull[k] != 0;
 				oPop[k] = pitchCur;
 				double pOld = pitchCur, pNew = nul ? pitchCur : sPNew[k];   // src/frame.cpp:59-63 / :71
-				if (!nul && oldIsNull) pOld = pNew;                           // :64-67
+				if (!nul && oldIsNull) pOld = sP0[k];                         // :64-67 (the copy is taken before :71)
 				oOld[k] = pOld; oNew[k] = pNew; oInc[k] = sInc[k];
 				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
 				pitchCur = __double_as_longlong(landing) == __double_as_longlong(gLanding[k]) ? gEnd[k] : glideExact(landing, sInc[k], sHold[k]);

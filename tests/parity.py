@@ -23,11 +23,18 @@ def metrics(got, want):
 
 
 def assert_f32_parity(got, want, what="", within=F32_WITHIN_1LSB, snr_db=F32_SNR_DB, short_ok=2):
+    """The FP32 bar.  Two allowances, both for SHORT or SILENT renders only, and the margins are printed so the log shows
+    how far inside the bar every case sits (pytest -s / -rA):
+      * fewer than `short_ok` samples off by more than 1 LSB pass whatever the percentage (a 12-sample scenario cannot meet
+        a 99.9 % bar with one 2-LSB sample);
+      * the SNR bar is waived when the reference is silent (peak < 50) or -- for renders of at most 10 000 samples -- when
+        no sample is off by more than 1 LSB."""
     assert len(got) == len(want), "%s: %d vs %d samples" % (what, len(got), len(want))
     w1, exact, snr, mx = metrics(got, want)
     bad = int(round((1 - w1) * len(want)))
-    # short renders: a couple of 2-LSB samples would break a percentage bar that is meant for long audio
+    print("parity %-44s n=%8d  <=1LSB %.6f  exact %.6f  SNR %6.1f dB  max|d| %g" % (what, len(want), w1, exact, snr, mx))
     assert w1 >= within or bad <= short_ok, "%s: only %.5f within 1 LSB (max %g, snr %.1f dB)" % (what, w1, mx, snr)
     quiet = float(np.abs(np.asarray(want, dtype=np.float64)).max()) < 50 if len(want) else True
-    assert snr >= snr_db or quiet or mx <= 1, "%s: SNR %.1f dB (max %g)" % (what, snr, mx)
+    short_and_tight = len(want) <= 10000 and mx <= 1
+    assert snr >= snr_db or quiet or short_and_tight, "%s: SNR %.1f dB (max %g)" % (what, snr, mx)
     return w1, exact, snr, mx
