@@ -1660,8 +1660,22 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 	}
 	chunkTicks = std::max(chunkTicks, 64u) & ~31u;  // whole 32-tick tiles (klatt_long.cu stage kernels)
 	const size_t n = numFrames;
-	DevBuf dFrames, dMin, dFade, dNull, dOff, dPlans, dStart, dPrev, dPitch, dVib;
-	DevBuf sig, maps, st, ph, pcm, phChunks, phStart, phFail, scanTmp;  // (function scope: `cleanup` below releases them at exit)
+	// Scratch of the long path: grow-only buffers kept per device between calls (a config-4 call needs ~5 GB of stage signals;
+	// allocating and freeing them inside every call cost 10-20 ms of a 40 ms render).  One long render at a time per process.
+	struct LongScratch {
+		DevBuf dFrames, dMin, dFade, dNull, dOff, dPlans, dStart, dPrev, dPitch, dVib;
+		DevBuf sig, maps, st, ph, pcm, phChunks, phStart, phFail, scanTmp;
+	};
+	static std::mutex longMu;
+	static LongScratch pool[16];
+	std::lock_guard<std::mutex> longLock(longMu);
+	LongScratch local;
+	static const bool usePool = !(getenv("NVSP_LONG_POOL") && atoi(getenv("NVSP_LONG_POOL")) == 0);
+	LongScratch &S = (usePool && dev >= 0 && dev < 16) ? pool[dev] : local;
+	DevBuf &dFrames = S.dFrames, &dMin = S.dMin, &dFade = S.dFade, &dNull = S.dNull, &dOff = S.dOff, &dPlans = S.dPlans, &dStart = S.dStart,
+	       &dPrev = S.dPrev, &dPitch = S.dPitch, &dVib = S.dVib;
+	DevBuf &sig = S.sig, &maps = S.maps, &st = S.st, &ph = S.ph, &pcm = S.pcm, &phChunks = S.phChunks, &phStart = S.phStart, &phFail = S.phFail,
+	       &scanTmp = S.scanTmp;
 	struct Cleanup {
 		std::vector<DevBuf *> bufs;
 		cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1671,7 +1685,8 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 			if (e1) cudaEventDestroy(e1);
 		}
 	} cleanup;
-	cleanup.bufs = {&dFrames, &dMin, &dFade, &dNull, &dOff, &dPlans, &dStart, &dPrev, &dPitch, &dVib};
+	if (&S == &local) cleanup.bufs = {&dFrames, &dMin, &dFade, &dNull, &dOff, &dPlans, &dStart, &dPrev, &dPitch, &dVib, &sig, &maps, &st, &ph, &pcm,
+	                                  &phChunks, &phStart, &phFail, &scanTmp};
 	if (!dFrames.reserve(n * sizeof(speechPlayer_frame_t)) || !dMin.reserve(n * 4) || !dFade.reserve(n * 4) || !dNull.reserve(n) ||
 	    !dOff.reserve(16) || !dPlans.reserve(n * sizeof(FadePlanF32)) || !dStart.reserve((n + 1) * 8) || !dPrev.reserve(n * 4) ||
 	    !dPitch.reserve(n * 8 * 4) || !dVib.reserve(n * 8))
@@ -1708,7 +1723,6 @@ extern "C" long long speechPlayer_synthesizeLong(int sampleRate, const speechPla
 		const uint64_t numChunks = (ticks + chunkTicks - 1) / chunkTicks;
 		if (numChunks > 0x7fffffffull) return fail("stream too long for one call");
 		const size_t pad = ticks + 64;
-		cleanup.bufs.insert(cleanup.bufs.end(), {&sig, &maps, &st, &ph, &pcm, &phChunks, &phStart, &phFail, &scanTmp});
 		if (!sig.reserve(5 * pad * sizeof(float)) || !maps.reserve(numChunks * 6 * sizeof(Affine)) ||
 		    !st.reserve(numChunks * 6 * sizeof(float2)) || !ph.reserve(numChunks * 2 * sizeof(double)) ||
 		    !phChunks.reserve(numChunks * sizeof(PhaseChunk)) || !scanTmp.reserve(klattLongScanScratchBytes(numChunks)) || !phStart.reserve(numChunks * sizeof(double)) || !phFail.reserve(16))

@@ -245,17 +245,14 @@ klatt_long_timeline_kernel(LongStream L) {
 	__shared__ double oPop[kTimelineTile], oOld[kTimelineTile], oNew[kTimelineTile], oInc[kTimelineTile];
 	// Everything that is a prefix sum (start ticks, vibrato phase, last real request) is scanned by the whole block.  What is
 	// left is the pitch a request inherits: a serial chain through the hold glide of its predecessor -- n repeated FP64
-	// additions, exact in closed form (glideExact) but ~1 us each on one thread.  The chain only enters a request through the
-	// LANDING value old + (new - old) * 1.0, which is insensitive to the last bits of `old` almost always: thread 0 runs the
-	// chain with the glide in plain closed form (a guess good to a few ulps), all threads compute the exact glides from the
-	// guessed landings at once, and thread 0 walks the chain again with the exact values, keeping every glide whose landing
-	// it confirms bit for bit and redoing the few it does not.  (Round 1 walked global memory on one thread: 39 ms for the
-	// 40 072 requests of config 4, 45 % of the whole call.)
+	// additions, exact in closed form (glideExact) but ~1 us each on one thread -- which is speculated and verified in parallel
+	// (below).  (Round 1 walked global memory on one thread: 39 ms for the 40 072 requests of config 4, 45 % of the whole
+	// call.)
 	uint64_t tBase = 0, vibBase = 0;      // carried across tiles (every thread keeps the same copy)
 	int64_t vPrevCarry = 0;
 	int32_t prevRealCarry = -1;
-	bool oldIsNull = true, gOldIsNull = true;   // thread 0
-	double pitchCur = 0.0, gCur = 0.0;          // thread 0
+	double carryEnd = 0.0;       // exact end pitch of the last real request of the earlier tiles (0: none yet, frame.cpp:86)
+	bool carryPrevNull = true;   // the request before this tile was a NULL request (or there is none: frame.cpp:87)
 	const int tid = threadIdx.x;
 	for (uint32_t base = 0; base < L.nReq; base += kTimelineTile) {
 		const uint32_t j = base + tid;
@@ -316,32 +313,63 @@ klatt_long_timeline_kernel(LongStream L) {
 		tBase += tTile; vibBase += vibTile; vPrevCarry = vLast;
 		if (lastReal) prevRealCarry = (int32_t)lastReal - 1;
 
-		if (tid == 0) {  // the guessed pitch chain
-			for (uint32_t k = 0; k < n; ++k) {
-				const bool nul = sNull[k] != 0;
-				double pOld = gCur, pNew = nul ? gCur : sPNew[k];
-				if (!nul && gOldIsNull) pOld = sP0[k];   // :64-67 copies the frame BEFORE :71 moves new.voicePitch
-				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
-				gLanding[k] = landing;
-				gCur = landing + (double)sHold[k] * sInc[k];
-				gOldIsNull = nul;
-			}
+		// ---- the pitch every request inherits.  A NULL request hands its pitch on unchanged (src/frame.cpp:59-63: new = old,
+		// inc = 0), so a request inherits the END pitch of the last REAL request before it (prevReal, scanned above):
+		//   1. every real request guesses that value in closed form (landing ~ new pitch, glide = n * inc: good to a few ulps),
+		//      forms its landing from the guess and runs its exact glide -- all requests at once;
+		//   2. every request recomputes its landing from the EXACT end its predecessor just produced; if all landings of the
+		//      tile are confirmed bit for bit, every end is exact by induction from the tile's carried-in value;
+		//   3. otherwise (rare) thread 0 walks the tile serially.
+		const bool prevNull = in && (j == 0 || (tid == 0 ? carryPrevNull : sNull[tid - 1] != 0));
+		const bool realPrevInTile = in && before != 0 && (int64_t)before - 1 >= (int64_t)base;
+		const uint32_t rLocal = realPrevInTile ? (uint32_t)(before - 1 - base) : 0u;
+		double myInc = 0.0, myPNew = 0.0, myP0 = 0.0;
+		uint64_t myHold = 0;
+		if (in) { myInc = sInc[tid]; myPNew = sPNew[tid]; myP0 = sP0[tid]; myHold = sHold[tid]; }
+		if (in && !null) {
+			const double curGuess = realPrevInTile ? sPNew[rLocal] + (double)sHold[rLocal] * sInc[rLocal] : carryEnd;
+			const double pOld = prevNull ? myP0 : curGuess;   // :64-67 copies the frame BEFORE :71 moves new.voicePitch
+			const double landing = (myPNew != myPNew) ? pOld : pOld + ((myPNew - pOld) * 1.0);
+			gLanding[tid] = landing;
+			gEnd[tid] = glideExact(landing, myInc, myHold);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
 		}
 		__syncthreads();
-		if (in) gEnd[tid] = glideExact(gLanding[tid], sInc[tid], sHold[tid]);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
-		__syncthreads();
-		if (tid == 0) {  // the true chain
-			for (uint32_t k = 0; k < n; ++k) {
-				const bool nul = sNull[k] != 0;
-				oPop[k] = pitchCur;
-				double pOld = pitchCur, pNew = nul ? pitchCur : sPNew[k];   // src/frame.cpp:59-63 / :71
-				if (!nul && oldIsNull) pOld = sP0[k];                         // :64-67 (the copy is taken before :71)
-				oOld[k] = pOld; oNew[k] = pNew; oInc[k] = sInc[k];
-				const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
-				pitchCur = __double_as_longlong(landing) == __double_as_longlong(gLanding[k]) ? gEnd[k] : glideExact(landing, sInc[k], sHold[k]);
-				oldIsNull = nul;
+		bool okMine = true;
+		double curTrue = 0.0, pOldTrue = 0.0, pNewTrue = 0.0;
+		if (in) {
+			curTrue = realPrevInTile ? gEnd[rLocal] : carryEnd;
+			if (null) { pOldTrue = curTrue; pNewTrue = curTrue; }
+			else {
+				pOldTrue = prevNull ? myP0 : curTrue;
+				pNewTrue = myPNew;
+				const double landing = (pNewTrue != pNewTrue) ? pOldTrue : pOldTrue + ((pNewTrue - pOldTrue) * 1.0);
+				okMine = __double_as_longlong(landing) == __double_as_longlong(gLanding[tid]);
 			}
 		}
+		const int allOk = __syncthreads_and(okMine ? 1 : 0);
+		if (allOk) {
+			if (in) { oPop[tid] = curTrue; oOld[tid] = pOldTrue; oNew[tid] = pNewTrue; oInc[tid] = myInc; }
+			if (lastReal && (int64_t)lastReal - 1 >= (int64_t)base) carryEnd = gEnd[(uint32_t)(lastReal - 1 - base)];
+		} else {
+			if (tid == 0) {  // the true chain, serially
+				double pitchCur = carryEnd;
+				bool oldIsNull = carryPrevNull;
+				for (uint32_t k = 0; k < n; ++k) {
+					const bool nul = sNull[k] != 0;
+					oPop[k] = pitchCur;
+					double pOld = pitchCur, pNew = nul ? pitchCur : sPNew[k];
+					if (!nul && (oldIsNull || base + k == 0)) pOld = sP0[k];
+					oOld[k] = pOld; oNew[k] = pNew; oInc[k] = sInc[k];
+					const double landing = (pNew != pNew) ? pOld : pOld + ((pNew - pOld) * 1.0);
+					pitchCur = glideExact(landing, sInc[k], sHold[k]);
+					oldIsNull = nul;
+				}
+				gEnd[0] = pitchCur;  // hand the tile's last value to everybody
+			}
+			__syncthreads();
+			carryEnd = gEnd[0];
+		}
+		carryPrevNull = sNull[n - 1] != 0;
 		__syncthreads();
 		if (in) { L.pitchPop[j] = oPop[tid]; L.pitchOld[j] = oOld[tid]; L.pitchNew[j] = oNew[tid]; L.pitchInc[j] = oInc[tid]; }
 		__syncthreads();

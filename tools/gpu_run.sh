@@ -105,5 +105,23 @@ mg)  # N GPUs of one box (gpurun --gpus N): concurrent D2H ceiling, the in-libra
 	timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline \
 		> $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err; echo "bench x$N rc=$?"; cut -c1-2500 $O/bench_${N}gpu.json; tail -3 $O/bench_${N}gpu.err
 	;;
+final)  # the round's evidence on one GPU: suite, smoke, the three bench lines, launch lists, full captures
+	timeout 1200 python -m pytest tests -q -m gpu -rA > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -3 $O/pytest_gpu.log
+	timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -9 $O/smoke.log
+	timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; cut -c1-3000 $O/bench.json; tail -3 $O/bench.err
+	timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > $O/bench_reference.json 2> $O/bench_reference.err; echo "bench ref rc=$?"; cut -c1-600 $O/bench_reference.json
+	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
+		python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/launches.log 2>&1; echo "ncu list rc=$?"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_f32_sched_kernel -s 3 -c 1 -f -o $O/prof_sched \
+		python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_sched.log 2>&1; echo "ncu sched rc=$?"
+	timeout 400 python bench.py --workload long --steps 5 --warmup 3 > $O/bench_long.json 2> $O/bench_long.err; echo "bench long rc=$?"; cut -c1-300 $O/bench_long.json; tail -3 $O/bench_long.err
+	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/long_launches.csv \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/long_launches.log 2>&1; echo "ncu long list rc=$?"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_long_stage -s 60 -c 3 -f -o $O/prof_long \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/ncu_long.log 2>&1; echo "ncu long rc=$?"
+	timeout 300 python bench.py --workload pull > $O/bench_pull.json 2> $O/bench_pull.err; echo "bench pull rc=$?"; cut -c1-300 $O/bench_pull.json; tail -3 $O/bench_pull.err
+	timeout 200 python bench.py --workload midi --no-cpu-baseline --no-e2e > $O/bench_midi.json 2> $O/bench_midi.err; echo "bench midi rc=$?"; cut -c1-300 $O/bench_midi.json
+	timeout 200 python bench.py --workload vowel --no-cpu-baseline --no-e2e > $O/bench_vowel.json 2> $O/bench_vowel.err; echo "bench vowel rc=$?"; cut -c1-300 $O/bench_vowel.json
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
