@@ -605,7 +605,7 @@ def main():
     elif sched == "rounds":
         kernel_name, cap = "klatt_f32_hold_kernel + klatt_f32_general_pair_kernel (rounds)", None
     elif sched != "block" or S < int(os.environ.get("NVSP_BLOCK_MIN_STREAMS", "16384")):
-        kernel_name, cap = "klatt_f32_sched_kernel (ring scheduler: hold and general chunks of all streams in one launch)", "r02_base_sched_traffic.json"
+        kernel_name, cap = "klatt_f32_sched_kernel (ring scheduler: hold and general chunks of all streams in one launch)", "r02_sched_traffic.json"
     else:
         kernel_name = ("klatt_f32_block_kernel (block scheduler: streams owned by one thread block, hold / fade / general cells, "
                        "the whole call in one launch)")

@@ -333,20 +333,31 @@ klatt_long_timeline_kernel(LongStream L) {
 			gLanding[tid] = landing;
 			gEnd[tid] = glideExact(landing, myInc, myHold);  // hold ticks F+2 .. occ-1: one addition each (src/frame.cpp:77)
 		}
-		__syncthreads();
-		bool okMine = true;
+		// 2. fixed-point iteration: every request recomputes its landing from the end its predecessor currently shows; the
+		// ones whose landing moved redo their glide.  A pass without a change means every landing is consistent with an exact
+		// predecessor, by induction from the tile's carried-in value.  (The landing is insensitive to the last bits of the
+		// inherited pitch almost always, so corrections do not travel: two or three passes.)
 		double curTrue = 0.0, pOldTrue = 0.0, pNewTrue = 0.0;
-		if (in) {
-			curTrue = realPrevInTile ? gEnd[rLocal] : carryEnd;
-			if (null) { pOldTrue = curTrue; pNewTrue = curTrue; }
-			else {
-				pOldTrue = prevNull ? myP0 : curTrue;
-				pNewTrue = myPNew;
-				const double landing = (pNewTrue != pNewTrue) ? pOldTrue : pOldTrue + ((pNewTrue - pOldTrue) * 1.0);
-				okMine = __double_as_longlong(landing) == __double_as_longlong(gLanding[tid]);
+		int allOk = 0;
+		for (int pass = 0; pass < 12 && !allOk; ++pass) {
+			__syncthreads();
+			bool changed = false;
+			double newEnd = 0.0;
+			if (in) {
+				curTrue = realPrevInTile ? gEnd[rLocal] : carryEnd;
+				if (null) { pOldTrue = curTrue; pNewTrue = curTrue; }
+				else {
+					pOldTrue = prevNull ? myP0 : curTrue;
+					pNewTrue = myPNew;
+					const double landing = (pNewTrue != pNewTrue) ? pOldTrue : pOldTrue + ((pNewTrue - pOldTrue) * 1.0);
+					changed = __double_as_longlong(landing) != __double_as_longlong(gLanding[tid]);
+					if (changed) { gLanding[tid] = landing; newEnd = glideExact(landing, myInc, myHold); }
+				}
 			}
+			allOk = !__syncthreads_or(changed ? 1 : 0);
+			if (changed) gEnd[tid] = newEnd;
 		}
-		const int allOk = __syncthreads_and(okMine ? 1 : 0);
+		__syncthreads();
 		if (allOk) {
 			if (in) { oPop[tid] = curTrue; oOld[tid] = pOldTrue; oNew[tid] = pNewTrue; oInc[tid] = myInc; }
 			if (lastReal && (int64_t)lastReal - 1 >= (int64_t)base) carryEnd = gEnd[(uint32_t)(lastReal - 1 - base)];
