@@ -566,6 +566,21 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        # The ceiling the end-to-end number lives under, measured in the same run: every rank copies its device rows into its
+        # pinned host buffer at the same time, in the engine's gather shape (2-D, one 2-s slice of every row), with no kernel
+        # running.  At N > 1 this is the HOST's concurrent device->pinned bandwidth (tools/d2h_probe.cu, profiles/r02_d2h_probe_*:
+        # 55 / 68 / 73 / 92 GB/s for 1 / 2 / 4 / 8 GPUs on this pool's boxes), not a property of the engine.
+        reps = 3
+        h_out.copy_(d_out[:, :slice_ticks], non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            h_out.copy_(d_out[:, :slice_ticks], non_blocking=True)
+        torch.cuda.synchronize()
+        dtp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+        host_ceiling = world * reps * S * slice_ticks * 2 / float(dtp.item()) / 1e9
         e2e_launches = eb.launch_stats()[0]
         # the device-resident and the host path must agree bit for bit
         same = bool(torch.equal(d_out[:64, :slice_ticks].cpu(), h_out[:64]))
@@ -573,7 +588,11 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                "ms_per_step": 1e3 * float(dt.item()) / args.e2e_steps, "matches_device_path": same,
                "slice_seconds": slice_ticks / sr, "rank_cpus_bound_to_gpu_numa_node": cpus_bound,
-               "kernel_launches_total": int(e2e_launches)}
+               "kernel_launches_total": int(e2e_launches),
+               "d2h_GBps_achieved": world * d2h * args.e2e_steps / float(dt.item()) / 1e9,
+               "host_d2h_GBps_all_ranks_concurrent": host_ceiling,
+               "note": "PCIe / host bound: d2h_GBps_achieved is the int16 of all ranks over the e2e wall time (H2D of the queues, planning "
+                       "and the first render included); host_d2h_GBps_all_ranks_concurrent is the same copies alone, all ranks at once"}
         eb.close()
 
     # ---- parity of what was just timed (outside the timed region): random rows of d_out against the oracle, whole length ----
