@@ -670,7 +670,7 @@ struct Affine {
 // per issue).  The signals therefore move through a shared-memory tile per warp: 32 chunks x 32 ticks, loaded and stored as
 // 32 coalesced 128-byte rows (row r = 32 consecutive ticks of chunk w + r), read and written by the owning thread along
 // its row ([32][33]: conflict-free either way).
-constexpr int kStageBlock = 64;   // threads: two warps, three tiles each (in, par, out) = 25 KB of shared memory
+constexpr int kStageBlock = 64;   // threads: two warps, one tile each (+ one for the parallel-bank signal in the last stage)
 constexpr int kTile = 32;
 template <int STAGE, int PASS>
 __global__ void __launch_bounds__(kStageBlock)
@@ -681,7 +681,9 @@ klatt_long_stage_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, i
 	constexpr bool kHasPar = STAGE == kStageLast && PASS == 2, kHasOut = PASS == 2;
 	__shared__ float tIn[kStageBlock / 32][kTile][kTile + 1];
 	__shared__ float tPar[kHasPar ? kStageBlock / 32 : 1][kHasPar ? kTile : 1][kTile + 1];
-	__shared__ float tOut[kHasOut ? kStageBlock / 32 : 1][kHasOut ? kTile : 1][kTile + 1];
+	// (the output tile IS the input tile: a thread overwrites tick q of its own row after it has consumed it -- one tile per
+	// warp instead of two lets twice as many warps share an SM, and these kernels are bound by the latency of their recurrences)
+	float (*tOut)[kTile][kTile + 1] = tIn;
 	const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
 	const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t warpChunk0 = ch - lane;  // first chunk of this warp
@@ -785,7 +787,7 @@ klatt_long_stage_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, i
 						sgn = fmaxf(sgn, -32000.0f);
 						o = (float)(int)sgn;  // the int16 value, exactly representable
 					}
-					tOut[kHasOut ? wib : 0][kHasOut ? lane : 0][q] = o;
+					tOut[wib][lane][q] = o;
 				}
 				cur.next(L);
 				if (cur.j != loaded && cur.j < L.nReq) { loadDirs(); loaded = cur.j; }
@@ -798,7 +800,7 @@ klatt_long_stage_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, i
 			for (int r = 0; r < kTile; ++r) {
 				const uint64_t g = (uint64_t)(warpChunk0 + r) * chunkTicks + tile + lane;
 				if (warpChunk0 + r < numChunks && g < total) {
-					const float o = tOut[kHasOut ? wib : 0][kHasOut ? r : 0][lane];
+					const float o = tOut[wib][r][lane];
 					if (STAGE == kStageLast) pcm[g] = (int16_t)(int)o;
 					else out[g] = o;
 				}

@@ -123,5 +123,18 @@ final)  # the round's evidence on one GPU: suite, smoke, the three bench lines, 
 	timeout 200 python bench.py --workload midi --no-cpu-baseline --no-e2e > $O/bench_midi.json 2> $O/bench_midi.err; echo "bench midi rc=$?"; cut -c1-300 $O/bench_midi.json
 	timeout 200 python bench.py --workload vowel --no-cpu-baseline --no-e2e > $O/bench_vowel.json 2> $O/bench_vowel.err; echo "bench vowel rc=$?"; cut -c1-300 $O/bench_vowel.json
 	;;
+c9)  # kernel (b) after the timeline fix; staging size of the host pipeline
+	timeout 600 python -m pytest tests/test_gpu_long.py tests/test_gpu_parity_f32.py tests/test_gpu_configs.py -q -m gpu > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -3 $O/pytest_gpu.log
+	timeout 400 python bench.py --workload long --steps 5 --warmup 3 > $O/bench_long.json 2> $O/bench_long.err; echo "bench long rc=$?"; cut -c1-300 $O/bench_long.json; tail -3 $O/bench_long.err
+	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/long_launches.csv \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/long_launches.log 2>&1; echo "ncu long list rc=$?"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_long_stage -s 60 -c 3 -f -o $O/prof_long \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/ncu_long.log 2>&1; echo "ncu long rc=$?"
+	for mb in 1024 2048 4096; do
+		NVSP_STAGE_MB=$mb timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity > $O/bench_stage$mb.json 2> $O/bench_stage$mb.err
+		python -c "
+import json; d=json.load(open('$O/bench_stage$mb.json')); e=d['e2e']; print('NVSP_STAGE_MB=$mb: device %.1f ms, e2e %.1f ms/step, %.1f GB/s achieved, host ceiling %.1f GB/s' % (d['ms_per_step'], e['ms_per_step'], e['d2h_GBps_achieved'], e['host_d2h_GBps_all_ranks_concurrent']))"
+	done
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
