@@ -98,6 +98,13 @@ struct Cursor {
 		left = L.start[j + 1] - t;
 		load(L);
 	}
+	// n <= left ticks at once (the caller stays inside the request; reaching its end moves on like next())
+	__device__ void advance(const LongStream &L, uint32_t n) {
+		if (n == 0) return;
+		c += n - 1;
+		left -= n - 1;
+		next(L);
+	}
 	__device__ void next(const LongStream &L) {
 		++c;
 		if (--left == 0) {
@@ -161,6 +168,15 @@ struct PoleWalk {
 			exact(L, j, c, F, r);  // drift control: back onto the closed form
 			return;
 		}
+		float tr = fmaf(-zr, wr, wr);
+		tr = fmaf(zi, wi, tr);
+		float ti = fmaf(-zr, wi, wi);
+		ti = fmaf(-zi, wr, ti);
+		zr += tr;
+		zi += ti;
+	}
+	// a plain interior fade tick (1 < c < F, not a multiple of kCoarseTicks): the last six operations of tick()
+	__device__ __forceinline__ void step() {
 		float tr = fmaf(-zr, wr, wr);
 		tr = fmaf(zi, wi, tr);
 		float ti = fmaf(-zr, wi, wi);
@@ -739,58 +755,109 @@ klatt_long_stage_kernel(LongStream L, uint32_t chunkTicks, uint32_t numChunks, i
 		__syncwarp();
 		if (live) {
 			const uint64_t tb = t0 + tile;
-			for (int q = 0; q < kTile && tb + q < t1; ++q) {
-				const uint32_t j = cur.j, c = cur.c, F = cur.F;
+			const int qEnd = (tb + kTile <= t1) ? kTile : (tb < t1 ? (int)(t1 - tb) : 0);
+			// One tick of the stage with the coefficients of that tick given: the FIR anti-resonator (nasal stage), the scanned
+			// sections, the affine map (pass 1), the stage's output (pass 2).
+			auto tickWith = [&](int q, const float *a, const float *rho, const float *mixv, float extraV, bool n0Inv, float a0, float rho0) {
 				float x = tIn[wib][lane][q];
 				const float xin = x;
 				if (STAGE == kStageNasal) {  // rN0 on inputs: src/speechWaveGenerator.cpp:129-135 with anti == true
-					pw0.tick(L, j, c, F, kResN0);
-					float a0, rho0;
-					pw0.coef(a0, rho0);
 					const float dprev = in1 - in2;
 					const float dx = x - in1;
 					const float dx1 = fmaf(-rho0, dprev, dprev);
-					x = n0InvAt(L, j, c, F) ? fmaf(dx - dx1, fastRcp(a0), in1) : fmaf(a0, dx, dx1 + in1);
+					x = n0Inv ? fmaf(dx - dx1, fastRcp(a0), in1) : fmaf(a0, dx, dx1 + in1);
 					in2 = in1;
 					in1 = xin;
 				}
 				float acc = 0.0f;
 #pragma unroll
 				for (int k = 0; k < NR; ++k) {
-					pw[k].tick(L, j, c, F, STAGE == kStageParallel ? kResParallel + k : res);
-					float a, rho;
-					pw[k].coef(a, rho);
-					float w = fmaf(-rho, d[k], d[k]);
-					w = fmaf(-a, y[k], w);
-					const float dn = fmaf(a, x, w);
+					float w = fmaf(-rho[k], d[k], d[k]);
+					w = fmaf(-a[k], y[k], w);
+					const float dn = fmaf(a[k], x, w);
 					d[k] = dn;
 					y[k] += dn;
 					if (PASS == 1) {  // P <- A P with A = [[1-a, 1-rho], [-a, 1-rho]] acting on (y, d)
-						const float g = 1.0f - rho;
-						const float n10 = fmaf(-a, p00[k], g * p10[k]), n11 = fmaf(-a, p01[k], g * p11[k]);
+						const float g = 1.0f - rho[k];
+						const float n10 = fmaf(-a[k], p00[k], g * p10[k]), n11 = fmaf(-a[k], p01[k], g * p11[k]);
 						p00[k] += n10; p01[k] += n11;
 						p10[k] = n10; p11[k] = n11;
 					}
-					if (STAGE == kStageParallel) acc = fmaf(y[k] - x, mix[k].at(c, F), acc);
+					if (STAGE == kStageParallel) acc = fmaf(y[k] - x, mixv[k], acc);
 				}
 				if (PASS == 2) {
 					float o;
 					if (STAGE == kStageParallel) {
-						o = fmaf(x - acc, extra.at(c, F), acc);
+						o = fmaf(x - acc, extraV, acc);
 					} else if (STAGE == kStageNasal) {
-						o = fmaf(y[0] - xin, extra.at(c, F), xin);
+						o = fmaf(y[0] - xin, extraV, xin);
 					} else if (STAGE == kStageCascade) {
 						o = y[0];
 					} else {
-						float sgn = (y[0] + tPar[kHasPar ? wib : 0][kHasPar ? lane : 0][q]) * (extra.at(c, F) * 4000.0f);
+						float sgn = (y[0] + tPar[kHasPar ? wib : 0][kHasPar ? lane : 0][q]) * (extraV * 4000.0f);
 						sgn = fminf(sgn, 32000.0f);
 						sgn = fmaxf(sgn, -32000.0f);
 						o = (float)(int)sgn;  // the int16 value, exactly representable
 					}
 					tOut[wib][lane][q] = o;
 				}
-				cur.next(L);
-				if (cur.j != loaded && cur.j < L.nReq) { loadDirs(); loaded = cur.j; }
+			};
+			// Events, not branches (as in the batch kernels): a tick that may change something -- the pop tick, the first fade
+			// tick, a drift-control point, the landing, the first tick of a tile -- runs the general code; the ticks that follow
+			// it inside the same RUN (the rest of a hold: constant coefficients; the fade ticks up to the next multiple of 64:
+			// plain pole steps) run a tight loop with no frame-manager logic.  Same operations on the same values per tick.
+			int q = 0;
+			while (q < qEnd) {
+				float a[NR], rho[NR], mixv[NR], a0 = 0.0f, rho0 = 0.0f, extraV = 0.0f;
+				bool n0Inv = false;
+				{
+					const uint32_t j = cur.j, c = cur.c, F = cur.F;
+					if (STAGE == kStageNasal) {
+						pw0.tick(L, j, c, F, kResN0);
+						pw0.coef(a0, rho0);
+						n0Inv = n0InvAt(L, j, c, F);
+					}
+#pragma unroll
+					for (int k = 0; k < NR; ++k) {
+						pw[k].tick(L, j, c, F, STAGE == kStageParallel ? kResParallel + k : res);
+						pw[k].coef(a[k], rho[k]);
+						mixv[k] = STAGE == kStageParallel ? mix[k].at(c, F) : 0.0f;
+					}
+					if (STAGE != kStageCascade) extraV = extra.at(c, F);
+					tickWith(q, a, rho, mixv, extraV, n0Inv, a0, rho0);
+					++q;
+					cur.next(L);
+					if (cur.j != loaded && cur.j < L.nReq) { loadDirs(); loaded = cur.j; }
+				}
+				if (q >= qEnd || cur.j >= L.nReq) continue;
+				const uint32_t c = cur.c, F = cur.F;
+				if (c > F) {  // inside a hold: nothing moves until the request ends
+					uint32_t n = (uint32_t)(qEnd - q);
+					if ((uint64_t)n > cur.left) n = (uint32_t)cur.left;
+					for (uint32_t i = 0; i < n; ++i) tickWith(q + (int)i, a, rho, mixv, extraV, n0Inv, a0, rho0);
+					q += (int)n;
+					cur.advance(L, n);
+					if (cur.j != loaded && cur.j < L.nReq) { loadDirs(); loaded = cur.j; }
+				} else if (c > 1 && c < F && (c & (uint32_t)(kCoarseTicks - 1)) != 0) {  // plain interior fade ticks
+					uint32_t n = (uint32_t)(qEnd - q);
+					const uint32_t toLanding = F - c, toGrid = (uint32_t)kCoarseTicks - (c & (uint32_t)(kCoarseTicks - 1));
+					if (n > toLanding) n = toLanding;
+					if (n > toGrid) n = toGrid;
+					for (uint32_t i = 0; i < n; ++i) {
+						const uint32_t ci = c + i;
+						if (STAGE == kStageNasal) { pw0.step(); pw0.coef(a0, rho0); }
+#pragma unroll
+						for (int k = 0; k < NR; ++k) {
+							pw[k].step();
+							pw[k].coef(a[k], rho[k]);
+							if (STAGE == kStageParallel) mixv[k] = mix[k].at(ci, F);
+						}
+						if (STAGE != kStageCascade) extraV = extra.at(ci, F);
+						tickWith(q + (int)i, a, rho, mixv, extraV, n0Inv, a0, rho0);
+					}
+					q += (int)n;
+					cur.advance(L, n);  // (stays inside the request: n <= F - c < left)
+				}
 			}
 		}
 		__syncwarp();

@@ -136,5 +136,14 @@ c9)  # kernel (b) after the timeline fix; staging size of the host pipeline
 import json; d=json.load(open('$O/bench_stage$mb.json')); e=d['e2e']; print('NVSP_STAGE_MB=$mb: device %.1f ms, e2e %.1f ms/step, %.1f GB/s achieved, host ceiling %.1f GB/s' % (d['ms_per_step'], e['ms_per_step'], e['d2h_GBps_achieved'], e['host_d2h_GBps_all_ranks_concurrent']))"
 	done
 	;;
+lg)  # kernel (b) only: tests, bench line, launch list, stage-kernel capture
+	timeout 600 python -m pytest tests/test_gpu_long.py -q -m gpu > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -3 $O/pytest_gpu.log
+	timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $O/smoke.log
+	timeout 400 python bench.py --workload long --steps 5 --warmup 3 > $O/bench_long.json 2> $O/bench_long.err; echo "bench long rc=$?"; cut -c1-300 $O/bench_long.json; tail -3 $O/bench_long.err
+	timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/long_launches.csv \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/long_launches.log 2>&1; echo "ncu long list rc=$?"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_long_stage -s 60 -c 3 -f -o $O/prof_long \
+		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/ncu_long.log 2>&1; echo "ncu long rc=$?"
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
