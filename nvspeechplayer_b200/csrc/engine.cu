@@ -47,9 +47,11 @@ cudaError_t launchKlattF32Rounds(const StreamDesc *descs, uint32_t numStreams, i
 cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                                 uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride, uint32_t *samplesWritten,
                                 StreamResult *results, NoiseConfig noise, uint32_t *ring, uint32_t ringCap, void *ctlMem,
-                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, cudaStream_t stream,
+                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, void *liteMem, cudaStream_t stream,
                                 unsigned long long *launchCounter);
 int klattF32SchedBlocksPerSm();
+bool klattF32SchedUsesLite();
+size_t klattF32SchedLiteBytes(uint32_t numStreams, uint32_t numBlocks);
 cudaError_t launchKlattF32Block(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount, uint32_t holdTicks,
                                 int16_t *out, size_t rowStride, uint32_t *samplesWritten, StreamResult *results, NoiseConfig noise,
                                 void *liteMem, int16_t *scratchRow, uint32_t numBlocks, void *profMem, uint32_t *hostFault,
@@ -332,9 +334,10 @@ static cudaError_t launchRender(int precision, const StreamDesc *descs, uint32_t
 		if (!rc->ring.reserve(sizeof(uint32_t) * 2 * (size_t)cap) || !rc->ctl.reserve(2048) ||
 		    !rc->scratchRow.reserve(sizeof(int16_t) * (size_t)std::max(rc->schedHoldTicks, rc->holdTicks)))
 			return cudaErrorMemoryAllocation;
+		if (klattF32SchedUsesLite() && !rc->lite.reserve(klattF32SchedLiteBytes(n, rc->schedBlocks))) return cudaErrorMemoryAllocation;
 		return launchKlattF32Sched(descs, n, sampleRate, sampleCount, rc->schedHoldTicks, rc->schedGenTicks, out, rowStride, written,
 		                           results, noise, rc->ring.as<uint32_t>(), cap, rc->ctl.p, rc->scratchRow.as<int16_t>(),
-		                           rc->schedBlocks, rc->hostFault, stream, launchCounter);
+		                           rc->schedBlocks, rc->hostFault, rc->lite.p, stream, launchCounter);
 	}
 	if (rc && planned && rc->init() && n >= rc->minStreams && sampleCount > rc->genTicks) {
 		const uint32_t rounds = (sampleCount + rc->genTicks - 1) / rc->genTicks;

@@ -158,6 +158,17 @@ klatt_block_export_kernel(const StreamDesc *__restrict__ descs, uint32_t numStre
 	}
 }
 
+// the two conversions as launchers (the ring scheduler's compact-state mode uses them too, klatt_f32_sched.cu)
+cudaError_t launchKlattLiteImport(const StreamDesc *descs, uint32_t numStreams, uint32_t numDummies, void *lite, cudaStream_t stream) {
+	klatt_block_import_kernel<<<(numStreams + numDummies + 255) / 256, 256, 0, stream>>>(descs, numStreams, numDummies, static_cast<StreamStateLite *>(lite));
+	return cudaGetLastError();
+}
+cudaError_t launchKlattLiteExport(const StreamDesc *descs, uint32_t numStreams, const void *lite, uint32_t *samplesWritten, StreamResult *results,
+                                  cudaStream_t stream) {
+	klatt_block_export_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, numStreams, static_cast<const StreamStateLite *>(lite), samplesWritten, results);
+	return cudaGetLastError();
+}
+
 #ifdef KLATT_BLOCK_PROFILE
 #define BPROF_LAP(acc) { long long t1 = clock64(); acc += t1 - t0; t0 = t1; }
 #else

@@ -8,13 +8,28 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stddef.h>
 #include "klatt_common.h"
 #include "klatt_f32_core.cuh"
 #include "out_writer.cuh"
 #include "klatt_f32_pair.cuh"
 
+// KLATT_SCHED_LITE (default 1, round 2): the streams of a call live in a dense array of 544-byte StreamStateLite records
+// (klatt_common.h; 35 MB for 65 536 streams: L2-resident) instead of the 2.4 KB AoS blocks; a worker copies the 32 records of
+// its chunk into shared memory with coalesced 16-byte ld.global.cg, the render loops load and store their state (and the
+// drift-control record zc, every 64 fade ticks) THERE, and the records go back with st.global.cg before the fence and the
+// push.  Everything mutable that crosses SMs moves through those explicit L1-bypassing copies, so the translation unit no
+// longer needs -dlcm=cg: plans, queues and descriptors are read through the L1 like any read-only data.  Measured (config 3):
+// DRAM traffic of a step 72.1 -> see profiles/r02_sched_ncu_summary.txt.
+#ifndef KLATT_SCHED_LITE
+#define KLATT_SCHED_LITE 1
+#endif
+
 namespace klatt {
 
+cudaError_t launchKlattLiteImport(const StreamDesc *descs, uint32_t numStreams, uint32_t numDummies, void *lite, cudaStream_t stream);
+cudaError_t launchKlattLiteExport(const StreamDesc *descs, uint32_t numStreams, const void *lite, uint32_t *samplesWritten, StreamResult *results,
+                                  cudaStream_t stream);
 cudaError_t launchKlattFinalize(const StreamDesc *descs, uint32_t numStreams, uint32_t *samplesWritten, StreamResult *results,
                                 cudaStream_t stream);
 
@@ -83,12 +98,18 @@ __device__ __forceinline__ uint32_t ldVolatile(const uint32_t *p) { return *rein
 __device__ __forceinline__ void stVolatile(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
 // class of a stream's next chunk, or kClassExit when the call is complete for it
-__device__ __forceinline__ uint32_t classifyNext(const StreamState *st, uint32_t sampleCount, uint32_t holdTicks) {
-	const GenStateF32 &gs = st->gen.f32;
+template <class FM, class GS>
+__device__ __forceinline__ uint32_t classifyNextT(const FM &fm, const GS &gs, uint32_t sampleCount, uint32_t holdTicks) {
 	const uint32_t pos = gs.callPos;
 	if (pos >= sampleCount || gs.callDrained != 0) return kClassExit;
-	return (sampleCount - pos >= holdTicks && canHoldF32(*st, holdTicks)) ? kClassHold : kClassGen;
+	return (sampleCount - pos >= holdTicks && canHoldF32T(fm, gs, holdTicks)) ? kClassHold : kClassGen;
 }
+__device__ __forceinline__ uint32_t classifyNext(const StreamState *st, uint32_t sampleCount, uint32_t holdTicks) {
+	return classifyNextT(st->fm, st->gen.f32, sampleCount, holdTicks);
+}
+constexpr uint32_t kRecPieces = sizeof(StreamStateLite) / 16, kStageStride = sizeof(StreamStateLite) + 8, kStageBytes = 32 * kStageStride;
+constexpr uint32_t kHoldPiecesOut = (uint32_t)(offsetof(StreamStateLite, f32) + offsetof(GenStateF32Lite, zre)) / 16;  // everything before the pole state
+static_assert((offsetof(StreamStateLite, f32) + offsetof(GenStateF32Lite, zre)) % 16 == 0, "the hold chunk's write-back ends on a 16-byte piece");
 
 // every lane of the calling warp: push stream s into ring cls (cls == kClassExit: nothing to push, the stream is done)
 template <bool SEED>
@@ -208,16 +229,20 @@ __device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, ui
 
 // start of a call: reset the per-call cursors of every stream and seed the rings
 __global__ void __launch_bounds__(256)
-klatt_sched_seed_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, uint32_t sampleCount, uint32_t holdTicks,
-                        SchedCtl *ctl, uint32_t *ring, uint32_t ringCap) {
+klatt_sched_seed_kernel(const StreamDesc *__restrict__ descs, const StreamStateLite *__restrict__ lite, uint32_t numStreams,
+                        uint32_t sampleCount, uint32_t holdTicks, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool valid = s < numStreams;
 	uint32_t cls = kClassExit;
 	if (valid) {
-		StreamState *st = descs[s].state;
-		st->gen.f32.callPos = 0;
-		st->gen.f32.callDrained = 0;
-		cls = classifyNext(st, sampleCount, holdTicks);
+		if (lite) {  // (the import kernel has reset the per-call cursors)
+			cls = classifyNextT(lite[s].fm, lite[s].f32, sampleCount, holdTicks);
+		} else {
+			StreamState *st = descs[s].state;
+			st->gen.f32.callPos = 0;
+			st->gen.f32.callDrained = 0;
+			cls = classifyNext(st, sampleCount, holdTicks);
+		}
 	}
 	schedPush<true>(ctl, ring, ringCap, cls, s, valid);
 }
@@ -226,15 +251,23 @@ klatt_sched_seed_kernel(const StreamDesc *__restrict__ descs, uint32_t numStream
 #define KLATT_SCHED_MINB 4
 #endif
 __global__ void __launch_bounds__(kPairBlock, KLATT_SCHED_MINB)
-klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
-                       uint32_t holdTicks, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,
+klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__restrict__ lite, uint32_t numStreams, int sampleRate,
+                       uint32_t sampleCount, uint32_t holdTicks, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,
                        int16_t *__restrict__ scratchRow, NoiseConfig noise, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap,
                        uint32_t holdSms) {
-	__shared__ uint4 xbuf[2][2 * kGroupTicks * 32];
+	// dynamic shared memory: [hand-over buffers: 2 workers x 8 KB][staged records: 2 workers x 32 x 552 B (KLATT_SCHED_LITE)]
+	extern __shared__ uint4 schedSmem[];
+	uint4 (*xbuf)[2 * kGroupTicks * 32] = reinterpret_cast<uint4 (*)[2 * kGroupTicks * 32]>(schedSmem);
 	__shared__ uint32_t work[2][34];  // per worker: 32 stream indices, class
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, pair = warp & 1u;
 	const bool cascade = cascadeRole(warp);
 	XchgSmem xc{(uint32_t)__cvta_generic_to_shared(&xbuf[pair][lane]), 1u + pair};
+#if KLATT_SCHED_LITE
+	unsigned char *stage = reinterpret_cast<unsigned char *>(schedSmem + 2 * 2 * kGroupTicks * 32) + pair * kStageBytes;
+	StreamStateLite *st = reinterpret_cast<StreamStateLite *>(stage + lane * kStageStride);  // this lane's stream while a chunk runs
+	StreamStateLite *dummy = lite + numStreams + (size_t)blockIdx.x * 2 + pair;
+	const uint32_t tw = (warp >> 1) * 32u + lane;  // thread of the worker
+#endif
 #ifdef KLATT_SCHED_PROFILE
 	long long tClaim = 0, tHold = 0, tGen = 0, tPush = 0, nHold = 0, nGen = 0, nLanes = 0;
 	long long t0 = clock64();
@@ -261,18 +294,38 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams
 		if (cls == kClassExit) break;
 		const bool valid = s < numStreams;
 		const StreamDesc &desc = descs[s];
+#if KLATT_SCHED_LITE
+		// the records of this chunk: global -> shared, both warps, 16 bytes per thread and step, L1 bypassed (the stream may have
+		// been on another SM a moment ago)
+#pragma unroll 1
+		for (uint32_t idx = tw; idx < 32u * kRecPieces; idx += 64u) {
+			const uint32_t r = idx / kRecPieces, p = idx - r * kRecPieces;
+			const uint32_t sr = work[pair][r];
+			const StreamStateLite *src = sr < numStreams ? lite + sr : dummy;
+			const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(src) + p);
+			uint2 *dst = reinterpret_cast<uint2 *>(stage + r * kStageStride + p * 16u);
+			dst[0] = make_uint2(v.x, v.y);
+			dst[1] = make_uint2(v.z, v.w);
+		}
+		xc.sync();
+		FrameMgrLite &fm = st->fm;
+		GenStateF32Lite &gs = st->f32;
+#else
+		FrameMgrState &fm = desc.state->fm;
+		GenStateF32 &gs = desc.state->gen.f32;
+#endif
 		if (cls == kClassHold) {
 			if (cascade) {
-				int16_t *row = valid ? out + (size_t)s * rowStride + desc.state->gen.f32.callPos : scratchRow;
+				int16_t *row = valid ? out + (size_t)s * rowStride + gs.callPos : scratchRow;
 				OutWriter ow;
 				ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0));
-				renderHoldF32<kRoleCascadeOsc>(desc, sampleRate, holdTicks, ow, noise, xc);
+				renderHoldF32T<kRoleCascadeOsc>(fm, gs, desc, sampleRate, holdTicks, ow, noise, xc);
 			} else {
 				NullOut no;
-				renderHoldF32<kRoleParallelOnly>(desc, sampleRate, holdTicks, no, noise, xc);
+				renderHoldF32T<kRoleParallelOnly>(fm, gs, desc, sampleRate, holdTicks, no, noise, xc);
 			}
 		} else {
-			const uint32_t pos = desc.state->gen.f32.callPos;
+			const uint32_t pos = gs.callPos;
 			uint32_t ticks = 0;
 			if (valid) {
 				ticks = sampleCount - pos;
@@ -284,14 +337,31 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams
 				int16_t *row = out + (size_t)(valid ? s : 0) * rowStride;
 				OutWriter ow;
 				ow.init(row + pos, ((reinterpret_cast<uintptr_t>(row + pos) & 15u) == 0));
-				const uint32_t produced = renderGeneralF32<kRoleCascade>(desc, sampleRate, ticks, genTicks, ow, noise, xc, &lastUserIndex, &qHead);
+				const uint32_t produced = renderGeneralF32T<kRoleCascade>(fm, gs, desc, sampleRate, ticks, genTicks, ow, noise, xc, &lastUserIndex, &qHead);
 				ow.flush();
 				if (produced < ticks) zeroRow(row, pos + produced, sampleCount);
 			} else {
 				NullOut no;
-				renderGeneralF32<kRoleParallel>(desc, sampleRate, ticks, genTicks, no, noise, xc, &lastUserIndex, &qHead);
+				renderGeneralF32T<kRoleParallel>(fm, gs, desc, sampleRate, ticks, genTicks, no, noise, xc, &lastUserIndex, &qHead);
 			}
 		}
+#if KLATT_SCHED_LITE
+		xc.sync();  // both halves of every stream of this chunk are in the staged records
+		const uint32_t next = (cascade && valid) ? classifyNextT(fm, gs, sampleCount, holdTicks) : kClassExit;
+		// (a hold chunk only moves the frame-manager counters, the oscillators, the noise memories and the section memories:
+		// the first 256 bytes of a record; the pole state, the direct parameters and the drift-control record are unchanged)
+		const uint32_t piecesOut = cls == kClassHold ? kHoldPiecesOut : kRecPieces;
+#pragma unroll 1
+		for (uint32_t idx = tw; idx < 32u * piecesOut; idx += 64u) {
+			const uint32_t r = idx / piecesOut, p = idx - r * piecesOut;
+			const uint32_t sr = work[pair][r];
+			if (sr < numStreams) {
+				const uint2 *src = reinterpret_cast<const uint2 *>(stage + r * kStageStride + p * 16u);
+				const uint2 a = src[0], b = src[1];
+				__stcg(reinterpret_cast<uint4 *>(lite + sr) + p, make_uint4(a.x, a.y, b.x, b.y));
+			}
+		}
+#endif
 		__threadfence();
 		xc.sync();  // both halves of every stream of this batch are stored
 #ifdef KLATT_SCHED_PROFILE
@@ -299,7 +369,9 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams
 		nLanes += __popc(__ballot_sync(0xffffffffu, valid));
 #endif
 		if (cascade) {
+#if !KLATT_SCHED_LITE
 			const uint32_t next = valid ? classifyNext(desc.state, sampleCount, holdTicks) : kClassExit;
+#endif
 			schedPush<false>(ctl, ring, ringCap, next, s, valid);
 		}
 		PROF_LAP(tPush)
@@ -315,29 +387,50 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, uint32_t numStreams
 #endif
 }
 
+static size_t schedSmemBytes() {
+	return sizeof(uint4) * 2 * 2 * kGroupTicks * 32 + (KLATT_SCHED_LITE ? 2 * (size_t)kStageBytes : 0);
+}
+bool klattF32SchedUsesLite() { return KLATT_SCHED_LITE != 0; }
+size_t klattF32SchedLiteBytes(uint32_t numStreams, uint32_t numBlocks) {
+	return sizeof(StreamStateLite) * ((size_t)numStreams + 2 * (size_t)numBlocks);
+}
+
 // One call through the stream scheduler: seed the rings, then one persistent launch.  scratch: ring[2 * ringCap]
 // (ringCap a power of two >= 2 * numStreams), ctl, scratchRow[holdTicks].  descs holds numStreams + 1 entries.
 cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                                 uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride, uint32_t *samplesWritten,
                                 StreamResult *results, NoiseConfig noise, uint32_t *ring, uint32_t ringCap, void *ctlMem,
-                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, cudaStream_t stream,
+                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, void *liteMem, cudaStream_t stream,
                                 unsigned long long *launchCounter) {
 	if (numStreams == 0 || sampleCount == 0) return cudaSuccess;
 	SchedCtl *ctl = static_cast<SchedCtl *>(ctlMem);
+	StreamStateLite *lite = KLATT_SCHED_LITE ? static_cast<StreamStateLite *>(liteMem) : nullptr;
+	static bool attrSet = false;
+	if (!attrSet) {
+		cudaError_t ea = cudaFuncSetAttribute(klatt_f32_sched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schedSmemBytes());
+		if (ea != cudaSuccess) return ea;
+		attrSet = true;
+	}
 	cudaError_t e = cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * 2 * (size_t)ringCap, stream);
 	if (e != cudaSuccess) return e;
 	if ((e = cudaMemsetAsync(ctl, 0, 2048, stream)) != cudaSuccess) return e;
-	klatt_sched_seed_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, numStreams, sampleCount, holdTicks, ctl, ring, ringCap);
 	const uint32_t batches = (numStreams + 31) / 32;
 	// paired workers: two warps per batch, two batches per block
 	const uint32_t blocksWanted = (batches + 1) / 2, grid = blocksWanted < numBlocks ? blocksWanted : numBlocks;
+	if (lite && (e = launchKlattLiteImport(descs, numStreams, 2 * grid, lite, stream)) != cudaSuccess) return e;
+	klatt_sched_seed_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, lite, numStreams, sampleCount, holdTicks, ctl, ring, ringCap);
 	static const uint32_t holdSms = getenv("NVSP_SCHED_HOLD_SMS") ? (uint32_t)atoi(getenv("NVSP_SCHED_HOLD_SMS")) : 0u;
-	klatt_f32_sched_kernel<<<grid, kPairBlock, 0, stream>>>(descs, numStreams, sampleRate, sampleCount, holdTicks, genTicks, out,
-	                                                         rowStride, scratchRow, noise, ctl, ring, ringCap, holdSms);
+	klatt_f32_sched_kernel<<<grid, kPairBlock, schedSmemBytes(), stream>>>(descs, lite, numStreams, sampleRate, sampleCount, holdTicks, genTicks,
+	                                                                        out, rowStride, scratchRow, noise, ctl, ring, ringCap, holdSms);
 	// the watchdog's verdict travels to a pinned host word; the engine reads it at its next synchronisation point
 	if (hostFault && (e = cudaMemcpyAsync(hostFault, &ctl->fault, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-	if ((e = launchKlattFinalize(descs, numStreams, samplesWritten, results, stream)) != cudaSuccess) return e;
-	if (launchCounter) *launchCounter += 3;
+	if (lite) {
+		if ((e = launchKlattLiteExport(descs, numStreams, lite, samplesWritten, results, stream)) != cudaSuccess) return e;
+		if (launchCounter) *launchCounter += 4;  // import, seed, workers, export
+	} else {
+		if ((e = launchKlattFinalize(descs, numStreams, samplesWritten, results, stream)) != cudaSuccess) return e;
+		if (launchCounter) *launchCounter += 3;
+	}
 #ifdef KLATT_SCHED_PROFILE
 	{
 		unsigned long long h[16];
@@ -355,7 +448,8 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
 // resident blocks of the scheduler kernel per SM (occupancy query; the grid is SMs x this)
 int klattF32SchedBlocksPerSm() {
 	int n = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, klatt_f32_sched_kernel, kPairBlock, 0) != cudaSuccess) n = 0;
+	cudaFuncSetAttribute(klatt_f32_sched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schedSmemBytes());
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, klatt_f32_sched_kernel, kPairBlock, schedSmemBytes()) != cudaSuccess) n = 0;
 	return n;
 }
 

@@ -27,7 +27,11 @@ struct OutWriter {
 		if ((count & 7u) == 0) {
 			int16_t *p = row + (count - 8);
 			if (vec) {
+#ifdef KLATT_OUT_STREAMING  // A/B: st.global.cs (evict-first in L2: the output is written once and never read by the kernel)
+				__stcs(reinterpret_cast<uint4 *>(p), make_uint4(w0, w1, w2, w3));
+#else
 				*reinterpret_cast<uint4 *>(p) = make_uint4(w0, w1, w2, w3);
+#endif
 			} else {
 				storeScalar(p, 8);
 			}

@@ -163,7 +163,7 @@ def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
         res[mode] = (np.concatenate(parts, axis=1), written, b.last_indices(), b.launch_stats()[0])
         b.close()
     assert res["rounds"][3] > res["single"][3] + 50, "the rounds path did not run"
-    assert res["sched"][3] == res["single"][3] + 2 * 3, "the stream scheduler did not run (seed + workers + finalize per call)"
+    assert res["sched"][3] == res["single"][3] + 3 * 3, "the stream scheduler did not run (import + seed + workers + export per call)"
     assert res["block"][3] == res["single"][3] + 2 * 3, "the block scheduler did not run (import + workers + export per call)"
     for k in range(3):
         np.testing.assert_array_equal(res["single"][k], res["sched"][k])

@@ -145,5 +145,29 @@ lg)  # kernel (b) only: tests, bench line, launch list, stage-kernel capture
 	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_long_stage -s 60 -c 3 -f -o $O/prof_long \
 		python bench.py --workload long --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/ncu_long.log 2>&1; echo "ncu long rc=$?"
 	;;
+rl)  # ring scheduler with compact staged records (KLATT_SCHED_LITE) vs round 1's AoS state with -dlcm=cg
+	timeout 600 python -m pytest tests/test_gpu_parity_f32.py tests/test_gpu_configs.py tests/test_gpu_multibatch.py tests/test_gpu_sinks.py -q -m gpu > $O/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -3 $O/pytest_gpu.log
+	timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -4 $O/smoke.log
+	try "NVSP_X=lite"
+	try "NVSP_LIB=$PWD/tools/_variants/libnolite.so"
+	try "NVSP_X=lite"
+	try "NVSP_LIB=$PWD/tools/_variants/libnolite.so"
+	try "NVSP_LIB=$PWD/tools/_variants/libprof.so"
+	try "NVSP_SCHED_GEN_TICKS=512"
+	try "NVSP_SCHED_GEN_TICKS=384 NVSP_SCHED_HOLD_TICKS=384"
+	try "NVSP_SCHED_HOLD_TICKS=256 NVSP_SCHED_GEN_TICKS=512"
+	timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_f32_sched_kernel -s 3 -c 1 -f -o $O/prof_sched \
+		python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_sched.log 2>&1; echo "ncu sched rc=$?"
+	;;
+rl2)  # ring scheduler (compact staged records): chunk-length sweep, streaming output stores
+	timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $O/smoke.log
+	for hg in "256 512" "256 384" "256 256" "192 384" "384 512" "128 256" "256 640" "320 448" "192 512" "128 384"; do
+		set -- $hg
+		try "NVSP_SCHED_HOLD_TICKS=$1 NVSP_SCHED_GEN_TICKS=$2"
+	done
+	try "NVSP_LIB=$PWD/tools/_variants/libstream.so NVSP_SCHED_HOLD_TICKS=256 NVSP_SCHED_GEN_TICKS=512"
+	NVSP_LIB=$PWD/tools/_variants/libstream.so NVSP_SCHED_HOLD_TICKS=256 NVSP_SCHED_GEN_TICKS=512 timeout 300 ncu --set full --clock-control none -k regex:klatt_f32_sched_kernel -s 3 -c 1 -f -o $O/prof_sched_stream \
+		python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_sched.log 2>&1; echo "ncu sched rc=$?"
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
