@@ -47,8 +47,8 @@ cudaError_t launchKlattF32Rounds(const StreamDesc *descs, uint32_t numStreams, i
 cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                                 uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride, uint32_t *samplesWritten,
                                 StreamResult *results, NoiseConfig noise, uint32_t *ring, uint32_t ringCap, void *ctlMem,
-                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, void *liteMem, cudaStream_t stream,
-                                unsigned long long *launchCounter);
+                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, void *liteMem, uint32_t holdMax,
+                                cudaStream_t stream, unsigned long long *launchCounter);
 int klattF32SchedBlocksPerSm();
 bool klattF32SchedUsesLite();
 size_t klattF32SchedLiteBytes(uint32_t numStreams, uint32_t numBlocks);
@@ -233,7 +233,7 @@ struct RoundsCtx {
 	bool blockSched = false;
 	uint32_t blockHoldTicks = 128, blockMinStreams = 16384, blockBlocks = 0;
 	uint32_t *hostFault = nullptr;  // pinned: the scheduler watchdog's verdict of the last call
-	uint32_t schedHoldTicks = 512, schedGenTicks = 640, schedBlocks = 0;
+	uint32_t schedHoldTicks = 256, schedGenTicks = 384, schedHoldMax = 4096, schedBlocks = 0;
 	cudaStream_t lanes[2 * kMaxGroups] = {};
 	cudaEvent_t evStart = nullptr, evFork[kMaxGroups] = {}, evJoin[kMaxGroups] = {};
 	uint32_t holdTicks = 512, genTicks = 256, minStreams = 2048, groups = 4;
@@ -256,8 +256,13 @@ struct RoundsCtx {
 			blockSched = e && strcmp(e, "block") == 0;
 			blockHoldTicks = std::max<uint32_t>(envU("NVSP_BLOCK_HOLD_TICKS", 128) & ~63u, 64);
 			blockMinStreams = envU("NVSP_BLOCK_MIN_STREAMS", 16384);
-			schedGenTicks = std::max<uint32_t>(envU("NVSP_SCHED_GEN_TICKS", 640) & ~63u, 64);
-			schedHoldTicks = std::max<uint32_t>(envU("NVSP_SCHED_HOLD_TICKS", 512) & ~63u, 64);
+			// (round 1, AoS state with L1-bypassing loads: 512 / 640 was the optimum; with the compact staged records a change of
+			// loop is cheaper and the optimum is a flat basin around 256 / 384: 200.2 ms vs 207.9 ms at 512 / 640)
+			schedGenTicks = std::max<uint32_t>(envU("NVSP_SCHED_GEN_TICKS", 384) & ~63u, 64);
+			schedHoldTicks = std::max<uint32_t>(envU("NVSP_SCHED_HOLD_TICKS", 256) & ~63u, 64);
+			// a hold chunk whose 32 streams can all hold longer runs up to this many ticks (steady vowels, sung notes; measured
+			// 256 -> 4096: config 2 292 -> 278 ms, config 5 163 -> 155 ms, config 3 unchanged)
+			schedHoldMax = std::max<uint32_t>(envU("NVSP_SCHED_HOLD_MAX", 4096) & ~63u, schedHoldTicks);
 			int dev = 0, sms = 0;
 			cudaGetDevice(&dev);
 			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -332,12 +337,12 @@ static cudaError_t launchRender(int precision, const StreamDesc *descs, uint32_t
 		}
 		if (*rc->hostFault) return cudaErrorLaunchTimeout;  // an earlier call of this batch tripped the watchdog
 		if (!rc->ring.reserve(sizeof(uint32_t) * 2 * (size_t)cap) || !rc->ctl.reserve(2048) ||
-		    !rc->scratchRow.reserve(sizeof(int16_t) * (size_t)std::max(rc->schedHoldTicks, rc->holdTicks)))
+		    !rc->scratchRow.reserve(sizeof(int16_t) * (size_t)std::max(std::max(rc->schedHoldTicks, rc->schedHoldMax), rc->holdTicks)))
 			return cudaErrorMemoryAllocation;
 		if (klattF32SchedUsesLite() && !rc->lite.reserve(klattF32SchedLiteBytes(n, rc->schedBlocks))) return cudaErrorMemoryAllocation;
 		return launchKlattF32Sched(descs, n, sampleRate, sampleCount, rc->schedHoldTicks, rc->schedGenTicks, out, rowStride, written,
 		                           results, noise, rc->ring.as<uint32_t>(), cap, rc->ctl.p, rc->scratchRow.as<int16_t>(),
-		                           rc->schedBlocks, rc->hostFault, rc->lite.p, stream, launchCounter);
+		                           rc->schedBlocks, rc->hostFault, rc->lite.p, rc->schedHoldMax, stream, launchCounter);
 	}
 	if (rc && planned && rc->init() && n >= rc->minStreams && sampleCount > rc->genTicks) {
 		const uint32_t rounds = (sampleCount + rc->genTicks - 1) / rc->genTicks;

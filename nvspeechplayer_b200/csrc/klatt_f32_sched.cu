@@ -2,13 +2,14 @@
 // the round-based launch sequence of klatt_f32.cu instead; DESIGN.md section 5b has the measurements of both).
 // Same render bodies as the round kernels (klatt_f32_core.cuh), so the same bits.
 //
-// This translation unit is compiled with -fmad=false like klatt_f32.cu AND with -Xptxas -dlcm=cg: the kernel moves a
-// stream's state between SMs without a kernel boundary in between, so no global load may be served from a stale L1
-// line.
+// This translation unit is compiled with -fmad=false like klatt_f32.cu.  The kernel moves a stream's state between SMs
+// without a kernel boundary in between: everything mutable travels in explicit L1-bypassing copies (KLATT_SCHED_LITE
+// below; the round-1 layout, KLATT_SCHED_LITE=0, needs -Xptxas -dlcm=cg for the whole unit instead).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <stddef.h>
+#include <string.h>
 #include "klatt_common.h"
 #include "klatt_f32_core.cuh"
 #include "out_writer.cuh"
@@ -19,8 +20,12 @@
 // its chunk into shared memory with coalesced 16-byte ld.global.cg, the render loops load and store their state (and the
 // drift-control record zc, every 64 fade ticks) THERE, and the records go back with st.global.cg before the fence and the
 // push.  Everything mutable that crosses SMs moves through those explicit L1-bypassing copies, so the translation unit no
-// longer needs -dlcm=cg: plans, queues and descriptors are read through the L1 like any read-only data.  Measured (config 3):
-// DRAM traffic of a step 72.1 -> see profiles/r02_sched_ncu_summary.txt.
+// longer needs -dlcm=cg: plans, queues and descriptors are read through the L1 like any read-only data.  After a hold chunk
+// only the first 256 bytes of a record go back (the pole state, the direct parameters and zc do not move in a hold).  The
+// record array sits in a persisting L2 access-policy window and the output leaves with st.global.cs (out_writer.cuh).
+// Measured (config 3): 222 -> 200 ms per step, DRAM traffic of a step 72.1 -> 51.6 GB (algorithmic: 31.8 GB;
+// profiles/r02_sched_ncu_summary.txt).  An evict-last L2 prefetch of the fade plans at the start of
+// a general chunk was tried and made it worse (83 GB: the marked lines crowd the output's write-combining out of the L2).
 #ifndef KLATT_SCHED_LITE
 #define KLATT_SCHED_LITE 1
 #endif
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(kPairBlock, KLATT_SCHED_MINB)
 klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__restrict__ lite, uint32_t numStreams, int sampleRate,
                        uint32_t sampleCount, uint32_t holdTicks, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,
                        int16_t *__restrict__ scratchRow, NoiseConfig noise, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap,
-                       uint32_t holdSms) {
+                       uint32_t holdSms, uint32_t holdMax) {
 	// dynamic shared memory: [hand-over buffers: 2 workers x 8 KB][staged records: 2 workers x 32 x 552 B (KLATT_SCHED_LITE)]
 	extern __shared__ uint4 schedSmem[];
 	uint4 (*xbuf)[2 * kGroupTicks * 32] = reinterpret_cast<uint4 (*)[2 * kGroupTicks * 32]>(schedSmem);
@@ -315,14 +320,31 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 		GenStateF32 &gs = desc.state->gen.f32;
 #endif
 		if (cls == kClassHold) {
+			// every stream here can hold for holdTicks (that is what put it into this ring); when ALL 32 can hold longer (steady
+			// vowels, sung notes), run as far as the shortest of them allows, up to holdMax: fewer record round trips per tick.
+			// Both warps of the pair compute this from the same staged records.
+			uint32_t ticks = holdTicks;
+#if KLATT_SCHED_LITE
+			if (holdMax > holdTicks) {
+				uint32_t can = 0xffffffffu;
+				if (valid) {
+					const uint32_t left = sampleCount - gs.callPos, quiet = fm.oldM - fm.counter;  // (canHoldF32T: counter + ticks <= oldM)
+					can = left < quiet ? left : quiet;
+				}
+				can = __reduce_min_sync(0xffffffffu, can);
+				if (can > holdMax) can = holdMax;
+				can &= ~63u;
+				if (can > ticks) ticks = can;
+			}
+#endif
 			if (cascade) {
 				int16_t *row = valid ? out + (size_t)s * rowStride + gs.callPos : scratchRow;
 				OutWriter ow;
 				ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0));
-				renderHoldF32T<kRoleCascadeOsc>(fm, gs, desc, sampleRate, holdTicks, ow, noise, xc);
+				renderHoldF32T<kRoleCascadeOsc>(fm, gs, desc, sampleRate, ticks, ow, noise, xc);
 			} else {
 				NullOut no;
-				renderHoldF32T<kRoleParallelOnly>(fm, gs, desc, sampleRate, holdTicks, no, noise, xc);
+				renderHoldF32T<kRoleParallelOnly>(fm, gs, desc, sampleRate, ticks, no, noise, xc);
 			}
 		} else {
 			const uint32_t pos = gs.callPos;
@@ -396,12 +418,12 @@ size_t klattF32SchedLiteBytes(uint32_t numStreams, uint32_t numBlocks) {
 }
 
 // One call through the stream scheduler: seed the rings, then one persistent launch.  scratch: ring[2 * ringCap]
-// (ringCap a power of two >= 2 * numStreams), ctl, scratchRow[holdTicks].  descs holds numStreams + 1 entries.
+// (ringCap a power of two >= 2 * numStreams), ctl, scratchRow[max(holdTicks, holdMax)].  descs holds numStreams + 1 entries.
 cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                                 uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride, uint32_t *samplesWritten,
                                 StreamResult *results, NoiseConfig noise, uint32_t *ring, uint32_t ringCap, void *ctlMem,
-                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, void *liteMem, cudaStream_t stream,
-                                unsigned long long *launchCounter) {
+                                int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, void *liteMem, uint32_t holdMax,
+                                cudaStream_t stream, unsigned long long *launchCounter) {
 	if (numStreams == 0 || sampleCount == 0) return cudaSuccess;
 	SchedCtl *ctl = static_cast<SchedCtl *>(ctlMem);
 	StreamStateLite *lite = KLATT_SCHED_LITE ? static_cast<StreamStateLite *>(liteMem) : nullptr;
@@ -420,8 +442,40 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
 	if (lite && (e = launchKlattLiteImport(descs, numStreams, 2 * grid, lite, stream)) != cudaSuccess) return e;
 	klatt_sched_seed_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, lite, numStreams, sampleCount, holdTicks, ctl, ring, ringCap);
 	static const uint32_t holdSms = getenv("NVSP_SCHED_HOLD_SMS") ? (uint32_t)atoi(getenv("NVSP_SCHED_HOLD_SMS")) : 0u;
+	// The records are read and written once per chunk (~800 times per stream and call) while 29 GB of output stream through the
+	// same L2: pin the record array there (persisting access-policy window on the launching stream; the output leaves with
+	// st.global.cs).  NVSP_L2_PERSIST=0 turns it off.
+	static const bool l2Persist = !(getenv("NVSP_L2_PERSIST") && atoi(getenv("NVSP_L2_PERSIST")) == 0);
+	bool windowSet = false;
+	if (lite && l2Persist) {
+		int dev = 0, maxPersist = 0, maxWindow = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+		cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+		const size_t bytes = klattF32SchedLiteBytes(numStreams, grid);
+		if (maxPersist > 0 && maxWindow > 0) {
+			static size_t limitSet = 0;
+			const size_t wantLimit = bytes < (size_t)maxPersist ? bytes : (size_t)maxPersist;
+			if (wantLimit > limitSet && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, wantLimit) == cudaSuccess) limitSet = wantLimit;
+			cudaStreamAttrValue attr;
+			memset(&attr, 0, sizeof attr);
+			attr.accessPolicyWindow.base_ptr = lite;
+			attr.accessPolicyWindow.num_bytes = bytes < (size_t)maxWindow ? bytes : (size_t)maxWindow;
+			attr.accessPolicyWindow.hitRatio = limitSet >= bytes ? 1.0f : (float)((double)limitSet / (double)bytes);
+			attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+			attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			windowSet = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+			if (!windowSet) cudaGetLastError();
+		}
+	}
 	klatt_f32_sched_kernel<<<grid, kPairBlock, schedSmemBytes(), stream>>>(descs, lite, numStreams, sampleRate, sampleCount, holdTicks, genTicks,
-	                                                                        out, rowStride, scratchRow, noise, ctl, ring, ringCap, holdSms);
+	                                                                        out, rowStride, scratchRow, noise, ctl, ring, ringCap, holdSms, holdMax);
+	if (windowSet) {
+		cudaStreamAttrValue attr;
+		memset(&attr, 0, sizeof attr);
+		attr.accessPolicyWindow.num_bytes = 0;
+		cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+	}
 	// the watchdog's verdict travels to a pinned host word; the engine reads it at its next synchronisation point
 	if (hostFault && (e = cudaMemcpyAsync(hostFault, &ctl->fault, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
 	if (lite) {

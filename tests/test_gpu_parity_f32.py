@@ -180,3 +180,40 @@ def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
     got = res["rounds"][0][s][:len(want)]
     parity.assert_f32_parity(got, want, "drained stream")
     assert not res["rounds"][0][s][len(want):].any()
+
+
+def test_f32_ring_scheduler_long_hold_chunks_bitwise(monkeypatch):
+    """The ring scheduler stretches a hold chunk to the shortest quiet span of its 32 streams (up to NVSP_SCHED_HOLD_MAX
+    ticks): steady vowels next to busy random-frame streams, every cap from "never" to "the whole note", calls that end
+    inside a stretched chunk -- the same bits as the one-thread-per-stream kernel."""
+    sr = 16000
+    vc = workloads.vowel_chart(3, sr)                      # holds of thousands of ticks
+    pick = list(range(0, len(vc.stream_ids), 97))[:40]
+    streams = [vc.stream(s) for s in pick] + [workloads.random_stream(900 + s, 1.5, sr) for s in range(40)]
+    ids = np.concatenate([vc.stream_ids[pick], np.arange(900, 940, dtype=np.uint64)])
+    fb = workloads._concat(sr, streams, ids)
+    n = len(ids)
+    counts = (7001, 640, 12000)
+    res = {}
+    for mode, hold_max in (("single", None), ("cap256", "256"), ("cap576", "576"), ("cap1024", "1024"), ("cap65536", "65536")):
+        monkeypatch.setenv("NVSP_ROUNDS_MIN_STREAMS", "100000000" if mode == "single" else "1")
+        monkeypatch.setenv("NVSP_SCHED", "rings")
+        monkeypatch.setenv("NVSP_SCHED_BLOCKS", "2")
+        monkeypatch.setenv("NVSP_SCHED_HOLD_TICKS", "256")
+        monkeypatch.setenv("NVSP_SCHED_GEN_TICKS", "192")
+        if hold_max:
+            monkeypatch.setenv("NVSP_SCHED_HOLD_MAX", hold_max)
+        b = player.Batch(sr, n, precision=player.PRECISION_FP32, seed=5, stream_ids=fb.stream_ids)
+        b.set_frames_host(fb)
+        parts, written = [], np.zeros(n, dtype=np.int64)
+        for c in counts:
+            o, w = b.synthesize_host(c)
+            parts.append(o)
+            written += w
+        res[mode] = (np.concatenate(parts, axis=1), written, b.last_indices(), b.launch_stats()[0])
+        b.close()
+    assert res["cap1024"][3] == res["single"][3] + 3 * len(counts), "the ring scheduler did not run"
+    assert res["single"][0].any()
+    for mode in ("cap256", "cap576", "cap1024", "cap65536"):
+        for k in range(3):
+            np.testing.assert_array_equal(res["single"][k], res[mode][k], err_msg=mode)

@@ -169,5 +169,47 @@ rl2)  # ring scheduler (compact staged records): chunk-length sweep, streaming o
 	NVSP_LIB=$PWD/tools/_variants/libstream.so NVSP_SCHED_HOLD_TICKS=256 NVSP_SCHED_GEN_TICKS=512 timeout 300 ncu --set full --clock-control none -k regex:klatt_f32_sched_kernel -s 3 -c 1 -f -o $O/prof_sched_stream \
 		python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_sched.log 2>&1; echo "ncu sched rc=$?"
 	;;
+rl3)  # ring scheduler: new defaults (256/384, streaming output stores, hold write-back trim), L2 persistence window on/off
+	timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $O/smoke.log
+	timeout 600 python -m pytest tests -q -m gpu -x -k "parity_f32 or batch_handles or sinks or multibatch" > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -3 $O/pytest_sub.log
+	try "NVSP_L2_PERSIST=1"
+	try "NVSP_L2_PERSIST=0"
+	try "NVSP_L2_PERSIST=1 NVSP_SCHED_HOLD_TICKS=192 NVSP_SCHED_GEN_TICKS=320"
+	try "NVSP_L2_PERSIST=1 NVSP_SCHED_HOLD_TICKS=256 NVSP_SCHED_GEN_TICKS=256"
+	try "NVSP_L2_PERSIST=1 NVSP_SCHED_HOLD_TICKS=128 NVSP_SCHED_GEN_TICKS=256"
+	for pz in 1 0; do
+		NVSP_L2_PERSIST=$pz timeout 300 ncu --set full --clock-control none --import-source on -k regex:klatt_f32_sched_kernel -s 3 -c 1 -f -o $O/prof_sched_p$pz \
+			python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_sched_p$pz.log 2>&1; echo "ncu sched persist=$pz rc=$?"
+	done
+	;;
+rl4)  # ring scheduler: evict-last prefetch of the fade plans on/off (time, DRAM bytes)
+	timeout 300 python -m pytest tests -q -m gpu -x -k "parity_f32 or batch_handles" > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -3 $O/pytest_sub.log
+	try "NVSP_X=default"
+	try "NVSP_LIB=$PWD/tools/_variants/libnopf.so"
+	try "NVSP_X=default"
+	try "NVSP_LIB=$PWD/tools/_variants/libnopf.so"
+	for v in default nopf; do
+		lib=$PWD/nvspeechplayer_b200/libspeechPlayer.so; [ $v = nopf ] && lib=$PWD/tools/_variants/libnopf.so
+		NVSP_LIB=$lib timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:klatt_f32_sched_kernel -s 3 -c 1 \
+			python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_$v.log 2>&1; echo "ncu $v rc=$?"; grep -A8 "klatt_f32_sched_kernel" $O/ncu_$v.log | grep "dram\|duration\|lts" 
+	done
+	;;
+rl5)  # ring scheduler: hold chunks stretched to the shortest quiet span of their 32 streams
+	timeout 300 python -m pytest tests -q -m gpu -x -k "parity_f32 or batch_handles or configs" > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -3 $O/pytest_sub.log
+	for hm in 256 512 1024 2048 4096; do
+		try "NVSP_SCHED_HOLD_MAX=$hm"
+		try "NVSP_SCHED_HOLD_MAX=$hm" --workload vowel
+		try "NVSP_SCHED_HOLD_MAX=$hm" --workload midi
+	done
+	;;
+rl6)  # stretched hold chunks: the fixed test, a few thresholds around the default
+	timeout 300 python -m pytest tests -q -m gpu -x -k "parity_f32" > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -3 $O/pytest_sub.log
+	try "NVSP_SCHED_HOLD_TICKS=192 NVSP_SCHED_GEN_TICKS=384"
+	try "NVSP_SCHED_HOLD_TICKS=128 NVSP_SCHED_GEN_TICKS=384"
+	try "NVSP_SCHED_HOLD_TICKS=256 NVSP_SCHED_GEN_TICKS=320"
+	try "NVSP_SCHED_HOLD_TICKS=128 NVSP_SCHED_GEN_TICKS=256"
+	try "NVSP_SCHED_HOLD_TICKS=192 NVSP_SCHED_GEN_TICKS=384" --workload vowel
+	try "NVSP_SCHED_HOLD_TICKS=128 NVSP_SCHED_GEN_TICKS=384" --workload midi
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
