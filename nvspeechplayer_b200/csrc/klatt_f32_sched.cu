@@ -23,7 +23,7 @@
 // longer needs -dlcm=cg: plans, queues and descriptors are read through the L1 like any read-only data.  After a hold chunk
 // only the first 256 bytes of a record go back (the pole state, the direct parameters and zc do not move in a hold).  The
 // record array sits in a persisting L2 access-policy window and the output leaves with st.global.cs (out_writer.cuh).
-// Measured (config 3): 222 -> 200 ms per step, DRAM traffic of a step 72.1 -> 51.6 GB (algorithmic: 31.8 GB;
+// Measured (config 3): 222 -> 203 ms per step, DRAM traffic of a step 72.1 -> 51.5 GB (algorithmic: 36.6 GB;
 // profiles/r02_sched_ncu_summary.txt).  An evict-last L2 prefetch of the fade plans at the start of
 // a general chunk was tried and made it worse (83 GB: the marked lines crowd the output's write-combining out of the L2).
 #ifndef KLATT_SCHED_LITE
