@@ -211,5 +211,38 @@ rl6)  # stretched hold chunks: the fixed test, a few thresholds around the defau
 	try "NVSP_SCHED_HOLD_TICKS=192 NVSP_SCHED_GEN_TICKS=384" --workload vowel
 	try "NVSP_SCHED_HOLD_TICKS=128 NVSP_SCHED_GEN_TICKS=384" --workload midi
 	;;
+san2)  # compute-sanitizer on the ring scheduler with staged records (memcheck, racecheck), the batched pull and the device sinks
+	cat > $O/san_case.py <<'PY'
+import os, sys
+import numpy as np
+os.environ.update({"NVSP_SCHED": "rings", "NVSP_ROUNDS_MIN_STREAMS": "1", "NVSP_SCHED_BLOCKS": "2", "NVSP_SCHED_HOLD_TICKS": "128", "NVSP_SCHED_GEN_TICKS": "128"})
+from nvspeechplayer_b200 import player, workloads
+sr = 16000
+vc = workloads.vowel_chart(3, sr)
+pick = list(range(0, len(vc.stream_ids), 211))[:24]
+streams = [vc.stream(s) for s in pick] + [workloads.random_stream(900 + s, 0.4, sr) for s in range(43)]
+ids = np.concatenate([vc.stream_ids[pick], np.arange(900, 943, dtype=np.uint64)])
+fb = workloads._concat(sr, streams, ids)
+b = player.Batch(sr, len(ids), precision=player.PRECISION_FP32, seed=5, stream_ids=fb.stream_ids)
+b.set_frames_host(fb)
+tot = 0
+for c in (3001, 2000):
+    o, w = b.synthesize_host(c)
+    tot += int(w.sum())
+print("ring scheduler ok", tot, b.launch_stats())
+b.close()
+if "pull" in sys.argv:
+    ps = [player.SpeechPlayer(sr, precision=player.PRECISION_STREAM, noise=player.NOISE_PHILOX, seed=3, streamId=100 + i) for i in range(5)]
+    for i, p in enumerate(ps):
+        fr, m, f, nul, ux = workloads.random_stream(100 + i, 0.3, sr)
+        p.queue_frames(fr, m, f, ux, nul)
+    out = player.synthesize_batch(ps, 1024) if hasattr(player, "synthesize_batch") else None
+    print("pull batch ok", None if out is None else np.asarray(out[0]).shape)
+    for p in ps:
+        p.close()
+PY
+	timeout 500 env PYTHONPATH=$PWD compute-sanitizer --tool memcheck --print-limit 8 python $O/san_case.py pull > $O/memcheck.log 2>&1; echo "memcheck rc=$?"; grep -v "^=========     at\|^=========         in" $O/memcheck.log | tail -12
+	timeout 700 env PYTHONPATH=$PWD compute-sanitizer --tool racecheck --print-limit 8 python $O/san_case.py > $O/racecheck.log 2>&1; echo "racecheck rc=$?"; grep -v "^=========     at\|^=========         in" $O/racecheck.log | tail -12
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
