@@ -244,5 +244,19 @@ PY
 	timeout 500 env PYTHONPATH=$PWD compute-sanitizer --tool memcheck --print-limit 8 python $O/san_case.py pull > $O/memcheck.log 2>&1; echo "memcheck rc=$?"; grep -v "^=========     at\|^=========         in" $O/memcheck.log | tail -12
 	timeout 700 env PYTHONPATH=$PWD compute-sanitizer --tool racecheck --print-limit 8 python $O/san_case.py > $O/racecheck.log 2>&1; echo "racecheck rc=$?"; grep -v "^=========     at\|^=========         in" $O/racecheck.log | tail -12
 	;;
+rl7)  # ring scheduler: L2 evict-last policy on the plan loads of the general loop, on / off (time, DRAM bytes)
+	timeout 300 python -m pytest tests -q -m gpu -x -k "parity_f32 or batch_handles" > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -3 $O/pytest_sub.log
+	try "NVSP_X=default"
+	try "NVSP_LIB=$PWD/tools/_variants/libnoel.so"
+	try "NVSP_X=default"
+	try "NVSP_LIB=$PWD/tools/_variants/libnoel.so"
+	try "NVSP_X=default" --workload midi
+	try "NVSP_LIB=$PWD/tools/_variants/libnoel.so" --workload midi
+	for v in default noel; do
+		lib=$PWD/nvspeechplayer_b200/libspeechPlayer.so; [ $v = noel ] && lib=$PWD/tools/_variants/libnoel.so
+		NVSP_LIB=$lib timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:klatt_f32_sched_kernel -s 3 -c 1 \
+			python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_$v.log 2>&1; echo "ncu $v rc=$?"; grep "dram__\|gpu__time\|lts__" $O/ncu_$v.log
+	done
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
