@@ -258,5 +258,14 @@ rl7)  # ring scheduler: L2 evict-last policy on the plan loads of the general lo
 			python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_$v.log 2>&1; echo "ncu $v rc=$?"; grep "dram__\|gpu__time\|lts__" $O/ncu_$v.log
 	done
 	;;
+rl8)  # evict-last plan loads with a larger persisting set-aside (records + plan rows)
+	timeout 300 python -m pytest tests -q -m gpu -x -k "parity_f32 or batch_handles" > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -3 $O/pytest_sub.log
+	for mb in 0 16 32 64 max; do
+		e="NVSP_L2_SETASIDE_MB=$mb"; [ $mb = max ] && e="NVSP_X=max"
+		try "$e"
+		env $e NVSP_VERBOSE=1 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:klatt_f32_sched_kernel -s 3 -c 1 \
+			python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_$mb.log 2>&1; echo "ncu $mb rc=$?"; grep "dram__\|gpu__time\|lts__" $O/ncu_$mb.log; grep -m1 "L2: persisting" $O/ncu_$mb.log
+	done
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
