@@ -21,11 +21,10 @@
 // drift-control record zc, every 64 fade ticks) THERE, and the records go back with st.global.cg before the fence and the
 // push.  Everything mutable that crosses SMs moves through those explicit L1-bypassing copies, so the translation unit no
 // longer needs -dlcm=cg: plans, queues and descriptors are read through the L1 like any read-only data.  After a hold chunk
-// only the first 256 bytes of a record go back (the pole state, the direct parameters and zc do not move in a hold).  The
-// record array sits in a persisting L2 access-policy window and the output leaves with st.global.cs (out_writer.cuh).
-// Measured (config 3): 222 -> 203 ms per step, DRAM traffic of a step 72.1 -> 51.5 GB (algorithmic: 36.6 GB;
-// profiles/r02_sched_ncu_summary.txt).  An evict-last L2 prefetch of the fade plans at the start of
-// a general chunk was tried and made it worse (83 GB: the marked lines crowd the output's write-combining out of the L2).
+// only the first 256 bytes of a record go back (the pole state, the direct parameters and zc do not move in a hold); the
+// output leaves with st.global.cs (out_writer.cuh).  Measured (config 3): 222 -> 200.5 ms per step, DRAM traffic of a step
+// 72.1 -> 59.7 GB (algorithmic: 36.6 GB; profiles/r02_sched_ncu_summary.txt, DESIGN.md section 5d, which also has the L2
+// residency controls that were tried -- persisting window on the records, evict-last plan rows -- and why they are off).
 #ifndef KLATT_SCHED_LITE
 #define KLATT_SCHED_LITE 1
 #endif
@@ -442,10 +441,11 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
 	if (lite && (e = launchKlattLiteImport(descs, numStreams, 2 * grid, lite, stream)) != cudaSuccess) return e;
 	klatt_sched_seed_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, lite, numStreams, sampleCount, holdTicks, ctl, ring, ringCap);
 	static const uint32_t holdSms = getenv("NVSP_SCHED_HOLD_SMS") ? (uint32_t)atoi(getenv("NVSP_SCHED_HOLD_SMS")) : 0u;
-	// The records are read and written once per chunk (~800 times per stream and call) while 29 GB of output stream through the
-	// same L2: pin the record array there (persisting access-policy window on the launching stream; the output leaves with
-	// st.global.cs).  NVSP_L2_PERSIST=0 turns it off.
-	static const bool l2Persist = !(getenv("NVSP_L2_PERSIST") && atoi(getenv("NVSP_L2_PERSIST")) == 0);
+	// NVSP_L2_PERSIST=1: pin the record array in the L2 (persisting access-policy window on the launching stream).  Measured
+	// (DESIGN.md section 5d): DRAM traffic of a config-3 step 59.7 -> 51.5 GB, but every workload gets SLOWER in warm
+	// back-to-back steps (config 3 +1.2 %, config 5 +3.3 %, config 2 -- 190 MB of records against a 79 MB set-aside -- +8 %),
+	// so it is off by default.
+	static const bool l2Persist = getenv("NVSP_L2_PERSIST") && atoi(getenv("NVSP_L2_PERSIST")) != 0;
 	bool windowSet = false;
 	if (lite && l2Persist) {
 		int dev = 0, maxPersist = 0, maxWindow = 0;

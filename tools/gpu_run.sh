@@ -267,5 +267,23 @@ rl8)  # evict-last plan loads with a larger persisting set-aside (records + plan
 			python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-parity > $O/ncu_$mb.log 2>&1; echo "ncu $mb rc=$?"; grep "dram__\|gpu__time\|lts__" $O/ncu_$mb.log; grep -m1 "L2: persisting" $O/ncu_$mb.log
 	done
 	;;
+rl9)  # persisting window on the records: warm multi-step time, on / off, alternating
+	for i in 1 2 3; do
+		try "NVSP_L2_PERSIST=1" --steps 5
+		try "NVSP_L2_PERSIST=0" --steps 5
+	done
+	try "NVSP_L2_PERSIST=1" --workload vowel
+	try "NVSP_L2_PERSIST=0" --workload vowel
+	try "NVSP_L2_PERSIST=1" --workload midi
+	try "NVSP_L2_PERSIST=0" --workload midi
+	;;
+rl10)  # streaming (st.global.cs) vs plain output stores on the three workload families, persistence off
+	for w in batch vowel midi; do
+		try "NVSP_X=cs" --workload $w
+		try "NVSP_LIB=$PWD/tools/_variants/libplain.so" --workload $w
+	done
+	try "NVSP_X=cs"
+	try "NVSP_LIB=$PWD/tools/_variants/libplain.so"
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
