@@ -285,5 +285,10 @@ rl10)  # streaming (st.global.cs) vs plain output stores on the three workload f
 	try "NVSP_X=cs"
 	try "NVSP_LIB=$PWD/tools/_variants/libplain.so"
 	;;
+mg2)  # the torchrun bench line only, N GPUs of one box (gpurun --gpus N)
+	N=${1:-8}
+	timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline \
+		> $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err; echo "bench x$N rc=$?"; cut -c1-2500 $O/bench_${N}gpu.json; tail -3 $O/bench_${N}gpu.err
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
