@@ -16,6 +16,8 @@
 #include <chrono>
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +31,7 @@
 #include "glibc_rand.h"
 #include "klatt_common.h"
 #include "pull_manager.h"
+#include "host_pool.h"
 #include "klatt_long_phase.cuh"
 
 namespace klatt {
@@ -791,9 +794,16 @@ void speechPlayer_seedNoise(unsigned int seed) {
 // p->pullSegs (src/frame.cpp:41-80 in closed form); copy the segments into the player's pinned staging, fetch the noise draws,
 // fill the launch context.  The kernel reads the segments from and writes the samples to the pinned staging itself
 // (zero-copy, the default), so a pull is one launch and one synchronize; NVSP_PULL_ZEROCOPY=0 goes through device buffers.
-static int pullStage(Player *p, uint32_t got, PullCtx &X, const PullSeg *&segSrc, int16_t *&pcmOut, bool &zeroCopy, cudaStream_t stream) {
+static bool pullZeroCopy() {
 	static const bool zc = !(getenv("NVSP_PULL_ZEROCOPY") && atoi(getenv("NVSP_PULL_ZEROCOPY")) == 0);
-	zeroCopy = zc;
+	return zc;
+}
+static bool pullDebugPhases() {
+	static const bool dbg = getenv("NVSP_PULL_DEBUG") != nullptr;
+	return dbg;
+}
+static int pullStage(Player *p, uint32_t got, PullCtx &X, const PullSeg *&segSrc, int16_t *&pcmOut, bool &zeroCopy, cudaStream_t stream) {
+	zeroCopy = pullZeroCopy();
 	PullSeg *hSegs = reinterpret_cast<PullSeg *>(p->hPullStage);
 	int32_t *hDraws = reinterpret_cast<int32_t *>(p->hPullStage + Player::kStageSegs + Player::kStagePcm);
 	if (p->noiseMode == kNoiseReplay && p->replayDirty) {
@@ -829,8 +839,7 @@ static int pullStage(Player *p, uint32_t got, PullCtx &X, const PullSeg *&segSrc
 	// 280 k -> 48 k cycles of an 8192-tick launch on B200) unless NVSP_PULL_PHASE=serial asks for the plain loop
 	static const bool phaseSerial = getenv("NVSP_PULL_PHASE") && !strcmp(getenv("NVSP_PULL_PHASE"), "serial");
 	X.phaseMode = phaseSerial ? 0 : 1;
-	static const bool debugPhases = getenv("NVSP_PULL_DEBUG") != nullptr;
-	if (debugPhases && p->dPullDbg.reserve(16 * sizeof(long long))) X.dbg = p->dPullDbg.as<long long>();
+	if (pullDebugPhases() && p->dPullDbg.reserve(16 * sizeof(long long))) X.dbg = p->dPullDbg.as<long long>();
 	return 0;
 }
 
@@ -909,37 +918,65 @@ static long long synthesizePullBatch(std::vector<Player *> &ps, unsigned int sam
 	std::vector<unsigned int> total(n, 0);
 	std::vector<uint32_t> got(n, 0);
 	std::vector<char> done(n, 0), zero(n, 1);
+	// The per-player host work runs on the helper threads when it touches no shared state and makes no CUDA call: zero-copy
+	// staging, no process-global rand() sequence (its draws are handed out in player order), no replay upload pending.
+	bool parallel = pullZeroCopy() && !pullDebugPhases() && n >= 8 && HostPool::get().helpers() > 0;
+	for (size_t i = 0; i < n && parallel; ++i)
+		if (ps[i]->noiseMode == kNoiseGlibc || (ps[i]->noiseMode == kNoiseReplay && ps[i]->replayDirty)) parallel = false;
+	const size_t grain = parallel ? std::max<size_t>(1, n / (4 * (HostPool::get().helpers() + 1))) : n;
+	auto forEach = [&](const std::function<void(size_t)> &fn) {
+		if (parallel) HostPool::get().parallelFor(n, grain, fn);
+		else
+			for (size_t i = 0; i < n; ++i) fn(i);
+	};
 	for (;;) {
-		bool any = false;
-		for (size_t i = 0; i < n; ++i) {
+		std::atomic<int> any{0}, failed{0};
+		auto prepare = [&](size_t i) {
 			Player *p = ps[i];
 			PullBatchItem &it = g_pullItemsHost[i];
 			memset(&it, 0, sizeof it);
 			got[i] = 0;
-			if (done[i] || total[i] >= sampleCount) continue;
+			if (done[i] || total[i] >= sampleCount) return;
 			const uint32_t want = std::min<uint32_t>(sampleCount - total[i], kPullMaxTicks);
 			p->pullSegs.clear();
 			bool drained = false;
 			got[i] = p->pull->advance(want, 0, kPullMaxSegs, p->pullSegs, drained);
 			if (drained) done[i] = 1;
-			if (!got[i]) continue;
+			if (!got[i]) return;
 			bool zc;
-			if (pullStage(p, got[i], it.ctx, it.segSrc, it.pcmOut, zc, stream) != 0) return -1;
+			if (pullStage(p, got[i], it.ctx, it.segSrc, it.pcmOut, zc, stream) != 0) {
+				failed.store(1);
+				return;
+			}
 			zero[i] = zc ? 1 : 0;
-			any = true;
-		}
-		if (!any) break;
+			any.store(1);
+		};
+		static const bool timing = getenv("NVSP_PULL_TIMING") != nullptr;  // host-side phases of a batched pull, one line per launch
+		const auto t0 = std::chrono::steady_clock::now();
+		forEach(prepare);
+		if (failed.load()) return -1;
+		if (!any.load()) break;
+		const auto t1 = std::chrono::steady_clock::now();
 		CU(launchKlattPullBatch(g_pullItemsHost, g_pullItemsDev, (uint32_t)n, stream));
 		for (size_t i = 0; i < n; ++i)
 			if (got[i] && !zero[i])
 				CU(cudaMemcpyAsync(ps[i]->hPullStage + Player::kStageSegs, g_pullItemsHost[i].pcmOut, (size_t)got[i] * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
 		CU(cudaStreamSynchronize(stream));
-		for (size_t i = 0; i < n; ++i) {
-			if (!got[i]) continue;
+		const auto t2 = std::chrono::steady_clock::now();
+		forEach([&](size_t i) {
+			if (!got[i]) return;
 			memcpy(out + i * (size_t)sampleCount + total[i], ps[i]->hPullStage + Player::kStageSegs, (size_t)got[i] * sizeof(int16_t));
 			++ps[i]->pullLaunches;
 			ps[i]->generated += got[i];
 			total[i] += got[i];
+		});
+		if (timing) {
+			const auto t3 = std::chrono::steady_clock::now();
+			auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+				return std::chrono::duration<double, std::micro>(b - a).count();
+			};
+			fprintf(stderr, "[pull batch] %zu players, %s: prepare %.0f us, launch + sync %.0f us, copy out %.0f us\n", n,
+			        parallel ? "helpers" : "serial", us(t0, t1), us(t1, t2), us(t2, t3));
 		}
 	}
 	long long sum = 0;

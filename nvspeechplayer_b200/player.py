@@ -213,15 +213,26 @@ class SpeechPlayer(object):
             pass
 
 
-def synthesize_batch(players, num_samples):
-    """speechPlayer_synthesizeBatch over a list of SpeechPlayer objects -> (int16 [n, num_samples], written[n])."""
+def synthesize_batch(players, num_samples, out=None, written=None, handles=None):
+    """speechPlayer_synthesizeBatch over a list of SpeechPlayer objects -> (int16 [n, num_samples], written[n]).
+    A caller in a loop passes the arrays of its previous call back in (out, written, and handles = batch_handles(players))
+    so that a call costs the library call alone, not fresh pages for the result."""
     L = load_library()
     n = len(players)
-    handles = (ctypes.c_void_p * n)(*[p._speechHandle for p in players])
-    out = np.zeros((n, num_samples), dtype=np.int16)
-    written = np.zeros(n, dtype=np.uint32)
+    if handles is None:
+        handles = batch_handles(players)
+    if out is None:
+        out = np.zeros((n, num_samples), dtype=np.int16)
+    if written is None:
+        written = np.zeros(n, dtype=np.uint32)
+    assert out.shape == (n, num_samples) and out.dtype == np.int16 and out.flags.c_contiguous
     _check(L.speechPlayer_synthesizeBatch(handles, n, num_samples, _ptr(out), _ptr(written)), "speechPlayer_synthesizeBatch")
     return out, written
+
+
+def batch_handles(players):
+    """The handle array speechPlayer_synthesizeBatch takes, for reuse across calls."""
+    return (ctypes.c_void_p * len(players))(*[p._speechHandle for p in players])
 
 
 def synthesize_long(sample_rate, frames, min_dur, fade_dur, is_null=None, seed=0xB200, stream_id=0, chunk_ticks=0,

@@ -393,3 +393,21 @@ extern "C" int hostsim_long_phase(const double *quot, uint64_t n, uint32_t L, do
 	}
 	return ok ? 1 : 0;
 }
+
+
+// ---- the helper threads of the batched pull (nvspeechplayer_b200/csrc/host_pool.h): every index exactly once, any n / grain ----
+#include "../../nvspeechplayer_b200/csrc/host_pool.h"
+extern "C" int hostsim_host_pool(unsigned reps, unsigned maxN, unsigned *helpersOut) {
+	klatt::HostPool &pool = klatt::HostPool::get();
+	if (helpersOut) *helpersOut = (unsigned)pool.helpers();
+	for (unsigned rep = 0; rep < reps; ++rep) {
+		const size_t n = 1 + rep % maxN, grain = 1 + (rep * 7u) % 40u;
+		std::vector<int> hits(n, 0);
+		std::atomic<long long> sum{0};
+		pool.parallelFor(n, grain, [&](size_t i) { hits[i] += 1; sum.fetch_add((long long)i); });
+		for (size_t i = 0; i < n; ++i)
+			if (hits[i] != 1) return -(int)rep - 1;
+		if (sum.load() != (long long)n * (long long)(n - 1) / 2) return -(int)rep - 1;
+	}
+	return 0;
+}

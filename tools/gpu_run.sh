@@ -290,5 +290,19 @@ mg2)  # the torchrun bench line only, N GPUs of one box (gpurun --gpus N)
 	timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline \
 		> $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err; echo "bench x$N rc=$?"; cut -c1-2500 $O/bench_${N}gpu.json; tail -3 $O/bench_${N}gpu.err
 	;;
+pl)  # batched pull with helper threads: tests, bench with and without helpers
+	timeout 400 python -m pytest tests/test_gpu_pull.py tests/test_gpu_batch_handles.py -q -m gpu > $O/pytest_pull.log 2>&1; echo "pull tests rc=$?"; tail -3 $O/pytest_pull.log
+	timeout 300 python bench.py --workload pull > $O/bench_pull.json 2> $O/bench_pull.err; echo "bench pull rc=$?"; python -c "
+import json; d=json.load(open('$O/bench_pull.json')); print(d['ms_per_step'], json.dumps(d.get('batch_of_players') or d['config'].get('batch_of_players') or {k:v for k,v in d.items() if 'batch' in k})[:600])"
+	NVSP_HOST_THREADS=0 timeout 300 python bench.py --workload pull > $O/bench_pull_nohelpers.json 2> $O/bench_pull_nohelpers.err; echo "bench pull (no helpers) rc=$?"; python -c "
+import json; d=json.load(open('$O/bench_pull_nohelpers.json')); print(d['ms_per_step'], json.dumps(d.get('batch_of_players') or d['config'].get('batch_of_players') or {k:v for k,v in d.items() if 'batch' in k})[:600])"
+	;;
+pl2)  # batched pull: host phases (NVSP_PULL_TIMING) with and without helpers, bench
+	NVSP_PULL_TIMING=1 timeout 300 python bench.py --workload pull > $O/bench_pull.json 2> $O/bench_pull.err; echo "bench pull rc=$?"; grep "pull batch" $O/bench_pull.err | tail -4; python -c "
+import json; d=json.load(open('$O/bench_pull.json')); print(d['ms_per_step'], json.dumps(d.get('batch_of_players'))[:600])"
+	NVSP_PULL_TIMING=1 NVSP_HOST_THREADS=0 timeout 300 python bench.py --workload pull > $O/bench_pull_nohelpers.json 2> $O/bench_pull_nohelpers.err; echo "bench pull (no helpers) rc=$?"; grep "pull batch" $O/bench_pull_nohelpers.err | tail -4; python -c "
+import json; d=json.load(open('$O/bench_pull_nohelpers.json')); print(d['ms_per_step'], json.dumps(d.get('batch_of_players'))[:600])"
+	NVSP_PULL_TIMING=1 NVSP_HOST_THREADS=3 timeout 300 python bench.py --workload pull > $O/bench_pull_3.json 2> $O/bench_pull_3.err; echo "bench pull (3 helpers) rc=$?"; grep "pull batch" $O/bench_pull_3.err | tail -3
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
