@@ -51,7 +51,7 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
                                 uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride, uint32_t *samplesWritten,
                                 StreamResult *results, NoiseConfig noise, uint32_t *ring, uint32_t ringCap, void *ctlMem,
                                 int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, void *liteMem, uint32_t holdMax,
-                                cudaStream_t stream, unsigned long long *launchCounter);
+                                uint32_t fadeTicks, uint32_t fadeMax, uint32_t roleSms, cudaStream_t stream, unsigned long long *launchCounter);
 int klattF32SchedBlocksPerSm();
 bool klattF32SchedUsesLite();
 size_t klattF32SchedLiteBytes(uint32_t numStreams, uint32_t numBlocks);
@@ -236,7 +236,7 @@ struct RoundsCtx {
 	bool blockSched = false;
 	uint32_t blockHoldTicks = 128, blockMinStreams = 16384, blockBlocks = 0;
 	uint32_t *hostFault = nullptr;  // pinned: the scheduler watchdog's verdict of the last call
-	uint32_t schedHoldTicks = 256, schedGenTicks = 384, schedHoldMax = 4096, schedBlocks = 0;
+	uint32_t schedHoldTicks = 256, schedGenTicks = 384, schedHoldMax = 4096, schedFadeTicks = 0, schedFadeMax = 512, schedRoleSms = 0, schedBlocks = 0;
 	cudaStream_t lanes[2 * kMaxGroups] = {};
 	cudaEvent_t evStart = nullptr, evFork[kMaxGroups] = {}, evJoin[kMaxGroups] = {};
 	uint32_t holdTicks = 512, genTicks = 256, minStreams = 2048, groups = 4;
@@ -266,6 +266,12 @@ struct RoundsCtx {
 			// a hold chunk whose 32 streams can all hold longer runs up to this many ticks (steady vowels, sung notes; measured
 			// 256 -> 4096: config 2 292 -> 278 ms, config 5 163 -> 155 ms, config 3 unchanged)
 			schedHoldMax = std::max<uint32_t>(envU("NVSP_SCHED_HOLD_MAX", 4096) & ~63u, schedHoldTicks);
+			// the fade class (0: off): streams with this many interior fade ticks ahead on the 64-sample grid take the straight-line
+			// fade loop; chunks stretched up to NVSP_SCHED_FADE_MAX.  NVSP_SCHED_HOLD_SMS / NVSP_SCHED_FADE_SMS: that many SMs take
+			// hold / fade chunks first, the rest general chunks (SM roles: one loop pair per instruction cache)
+			schedFadeTicks = envU("NVSP_SCHED_FADE_TICKS", 0) & ~63u;
+			schedFadeMax = std::min<uint32_t>(std::max<uint32_t>(envU("NVSP_SCHED_FADE_MAX", 512) & ~63u, schedFadeTicks), 4096);
+			schedRoleSms = std::min<uint32_t>(envU("NVSP_SCHED_HOLD_SMS", 0), 255u) | (std::min<uint32_t>(envU("NVSP_SCHED_FADE_SMS", 0), 255u) << 8);
 			int dev = 0, sms = 0;
 			cudaGetDevice(&dev);
 			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -339,13 +345,14 @@ static cudaError_t launchRender(int precision, const StreamDesc *descs, uint32_t
 			*rc->hostFault = 0;
 		}
 		if (*rc->hostFault) return cudaErrorLaunchTimeout;  // an earlier call of this batch tripped the watchdog
-		if (!rc->ring.reserve(sizeof(uint32_t) * 2 * (size_t)cap) || !rc->ctl.reserve(2048) ||
-		    !rc->scratchRow.reserve(sizeof(int16_t) * (size_t)std::max(std::max(rc->schedHoldTicks, rc->schedHoldMax), rc->holdTicks)))
+		if (!rc->ring.reserve(sizeof(uint32_t) * 3 * (size_t)cap) || !rc->ctl.reserve(2048) ||
+		    !rc->scratchRow.reserve(sizeof(int16_t) * (size_t)std::max(std::max(std::max(rc->schedHoldTicks, rc->schedHoldMax), rc->holdTicks), rc->schedFadeMax)))
 			return cudaErrorMemoryAllocation;
 		if (klattF32SchedUsesLite() && !rc->lite.reserve(klattF32SchedLiteBytes(n, rc->schedBlocks))) return cudaErrorMemoryAllocation;
 		return launchKlattF32Sched(descs, n, sampleRate, sampleCount, rc->schedHoldTicks, rc->schedGenTicks, out, rowStride, written,
 		                           results, noise, rc->ring.as<uint32_t>(), cap, rc->ctl.p, rc->scratchRow.as<int16_t>(),
-		                           rc->schedBlocks, rc->hostFault, rc->lite.p, rc->schedHoldMax, stream, launchCounter);
+		                           rc->schedBlocks, rc->hostFault, rc->lite.p, rc->schedHoldMax, rc->schedFadeTicks, rc->schedFadeMax, rc->schedRoleSms, stream,
+		                           launchCounter);
 	}
 	if (rc && planned && rc->init() && n >= rc->minStreams && sampleCount > rc->genTicks) {
 		const uint32_t rounds = (sampleCount + rc->genTicks - 1) / rc->genTicks;

@@ -1079,8 +1079,8 @@ KLATT_HD uint32_t renderGeneralF32(const StreamDesc &desc, int sampleRate, uint3
 // frame-manager event falls inside and that the first tick sits on the 64-sample grid of the drift control, so the coarse
 // re-basing happens before the loop and a tick is pole recurrences -> coefficients -> the DSP with no branch.  The
 // arithmetic of every tick is renderGeneralF32T's, operation for operation: a stream may change between the two (and the
-// hold loop) at any chunk boundary without changing an output bit.  ticks is a multiple of kGroupTicks and at most
-// kCoarseTicks; Philox noise only (pre-queued batches); even `samplesGenerated` follows from the grid condition.
+// hold loop) at any chunk boundary without changing an output bit.  ticks is a multiple of kGroupTicks (any number of
+// kCoarseTicks cells); Philox noise only (pre-queued batches); even `samplesGenerated` follows from the grid condition.
 // ---------------------------------------------------------------------------------------------------
 template <int ROLE, class Out, class Xchg, class FM, class GS>
 KLATT_HD void renderFadeF32T(FM &fm, GS &gs, const StreamDesc &desc, int sampleRate, uint32_t ticks, Out &out, const NoiseConfig &noise,
@@ -1107,71 +1107,77 @@ KLATT_HD void renderFadeF32T(FM &fm, GS &gs, const StreamDesc &desc, int sampleR
 	const bool n0Inv = gs.n0Inv != 0;
 	uint64_t gen = gs.samplesGenerated;
 	const uint64_t streamId = desc.streamId;
-	// the first tick lies on the drift-control grid: its poles come from the coarse recurrence when the previous grid point
-	// of this fade was recorded, from the per-tick one otherwise; either way they become the new record
-	{
-		if (counter + 1u - gs.coarseAt == (uint32_t)kCoarseTicks) {
-#pragma unroll
-			for (int r = T::R0; r < T::R1; ++r) {
-				float zr = gs.zc[r], zi = gs.zc[kNumResonators + r], Wr = plan->Wre[r], Wi = plan->Wim[r];
-				float tr = fmaf(-zr, Wr, Wr);
-				tr = fmaf(zi, Wi, tr);
-				float ti = fmaf(-zr, Wi, Wi);
-				ti = fmaf(-zi, Wr, ti);
-				half(u, r) = -(zr + tr);
-				half(v, r) = -(zi + ti);
-			}
-		} else {
-			stepPoles<ROLE>(u, v, wr, wi);
-		}
-#pragma unroll
-		for (int r = T::R0; r < T::R1; ++r) { gs.zc[r] = -half(u, r); gs.zc[kNumResonators + r] = -half(v, r); }
-	}
-	const uint32_t coarseAt = counter + 1u;
-	for (uint32_t t = 0; t < ticks; t += kGroupTicks) {
-		if (T::hasC && !T::hasP) xc.sync();  // the parallel side has finished this group
+	// A chunk is a sequence of CELLS of kCoarseTicks ticks (the last one may be shorter), each starting on the drift-control
+	// grid: the poles of a cell's first tick come from the coarse recurrence when the previous grid point of this fade was
+	// recorded, from the per-tick one otherwise; either way they become the new record.
+	uint32_t coarseAt = gs.coarseAt;
 #pragma unroll 1
-		for (int k = 0; k < kGroupTicks; k += 2) {
-			Philox4 blk;
-			if (T::hasP) blk = noiseBlock(noise.seed, streamId, (gen + k) >> 1);
+	for (uint32_t c0 = 0; c0 < ticks; c0 += (uint32_t)kCoarseTicks) {
+		const uint32_t cellTicks = ticks - c0 < (uint32_t)kCoarseTicks ? ticks - c0 : (uint32_t)kCoarseTicks;
+		{
+			if (counter + 1u - coarseAt == (uint32_t)kCoarseTicks) {
 #pragma unroll
-			for (int h = 0; h < 2; ++h) {
-				const bool oscHere = T::hasO && !T::hasC;
-				OscChain osc;
-				counter++;
-				kf += 1.0f;
-				if (T::hasO) S.vibInc += vibIncStep;
-				if (t + k + h != 0) stepPoles<ROLE>(u, v, wr, wi);
-				if (oscHere) { osc.seg1(S); osc.seg2(); }
-				CoefF32 C;
-				{
-					F2 dir[kNumDirectPairs];
-					const F2 kf2 = f2s(kf);
+				for (int r = T::R0; r < T::R1; ++r) {
+					float zr = gs.zc[r], zi = gs.zc[kNumResonators + r], Wr = plan->Wre[r], Wi = plan->Wim[r];
+					float tr = fmaf(-zr, Wr, Wr);
+					tr = fmaf(zi, Wi, tr);
+					float ti = fmaf(-zr, Wi, Wi);
+					ti = fmaf(-zi, Wr, ti);
+					half(u, r) = -(zr + tr);
+					half(v, r) = -(zi + ti);
+				}
+			} else {
+				stepPoles<ROLE>(u, v, wr, wi);
+			}
 #pragma unroll
-					for (int q = 0; q < kNumDirectPairs; ++q)
-						if (roleUsesDirectPair<ROLE>(q)) dir[q] = fma2(kf2, dstep[q], dir0[q]);
-					if (oscHere) osc.seg3(S, half(dir, dVibratoPitchOffset));
-					buildCoef<ROLE>(C, u, v, dir, n0Inv);
-				}
-				if (oscHere) osc.seg4(srD, srInv);
-				uint32_t wA = 0;
-				float par = 0.0f, voice = 0.0f;
-				if (T::hasP) {
-					wA = blk.w[2 * h];
-					if (oscHere) osc.seg5(S);
-					par = parallelSide(S, C, blk.w[2 * h + 1]);
-					if (oscHere) voice = osc.seg6();
-					if (!T::hasC) xc.put(t + k + h, wA, par, voice);
-				}
-				if (T::hasC) {
-					if (!T::hasP) xc.get(t + k + h, wA, par, voice);
-					if (T::hasO) voice = oscillatorSide(S, C, srD, srInv);
-					out.push(cascadeSide(S, C, wA, par, voice));
+			for (int r = T::R0; r < T::R1; ++r) { gs.zc[r] = -half(u, r); gs.zc[kNumResonators + r] = -half(v, r); }
+		}
+		coarseAt = counter + 1u;
+		for (uint32_t t = 0; t < cellTicks; t += kGroupTicks) {
+			if (T::hasC && !T::hasP) xc.sync();  // the parallel side has finished this group
+#pragma unroll 1
+			for (int k = 0; k < kGroupTicks; k += 2) {
+				Philox4 blk;
+				if (T::hasP) blk = noiseBlock(noise.seed, streamId, (gen + k) >> 1);
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					const bool oscHere = T::hasO && !T::hasC;
+					OscChain osc;
+					counter++;
+					kf += 1.0f;
+					if (T::hasO) S.vibInc += vibIncStep;
+					if (t + k + h != 0) stepPoles<ROLE>(u, v, wr, wi);
+					if (oscHere) { osc.seg1(S); osc.seg2(); }
+					CoefF32 C;
+					{
+						F2 dir[kNumDirectPairs];
+						const F2 kf2 = f2s(kf);
+#pragma unroll
+						for (int q = 0; q < kNumDirectPairs; ++q)
+							if (roleUsesDirectPair<ROLE>(q)) dir[q] = fma2(kf2, dstep[q], dir0[q]);
+						if (oscHere) osc.seg3(S, half(dir, dVibratoPitchOffset));
+						buildCoef<ROLE>(C, u, v, dir, n0Inv);
+					}
+					if (oscHere) osc.seg4(srD, srInv);
+					uint32_t wA = 0;
+					float par = 0.0f, voice = 0.0f;
+					if (T::hasP) {
+						wA = blk.w[2 * h];
+						if (oscHere) osc.seg5(S);
+						par = parallelSide(S, C, blk.w[2 * h + 1]);
+						if (oscHere) voice = osc.seg6();
+						if (!T::hasC) xc.put(t + k + h, wA, par, voice);
+					}
+					if (T::hasC) {
+						if (!T::hasP) xc.get(t + k + h, wA, par, voice);
+						if (T::hasO) voice = oscillatorSide(S, C, srD, srInv);
+						out.push(cascadeSide(S, C, wA, par, voice));
+					}
 				}
 			}
+			gen += kGroupTicks;
+			if (T::hasP && !T::hasC) xc.sync();  // hand the group over
 		}
-		gen += kGroupTicks;
-		if (T::hasP && !T::hasC) xc.sync();  // hand the group over
 	}
 	storeDspState<ROLE>(gs, S);
 #pragma unroll

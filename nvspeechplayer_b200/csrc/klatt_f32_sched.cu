@@ -72,7 +72,10 @@ cudaError_t launchKlattFinalize(const StreamDesc *descs, uint32_t numStreams, ui
 //                       back to an SM it visited before cannot see a stale line.
 // ---------------------------------------------------------------------------------------------------
 constexpr uint32_t kRingEmpty = 0xffffffffu, kRingAbandoned = 0xfffffffeu;
-constexpr uint32_t kClassHold = 0, kClassGen = 1, kClassExit = 2;
+constexpr uint32_t kClassHold = 0, kClassGen = 1, kClassFade = 2, kClassExit = 3, kNumRings = 3;
+// kClassFade (round 2, on when fadeTicks != 0): streams with fadeTicks INTERIOR fade ticks ahead, starting on the 64-sample
+// grid of the drift control: renderFadeF32T's straight-line loop (pole recurrences, coefficients, DSP; no frame manager, no
+// branch) renders them; the general loop keeps the ticks around pops, landings and swaps.
 
 struct SchedCtl {  // every hot word on its own 128-byte line
 	uint32_t head0, padA[31];
@@ -81,8 +84,10 @@ struct SchedCtl {  // every hot word on its own 128-byte line
 	uint32_t tail1, padD[31];
 	uint32_t remaining, padE[31];  // streams of this call that still have ticks to render
 	uint32_t fault, padF[31];      // set by the watchdog: a worker waited kWatchdogNs for work that never came
-	__device__ __forceinline__ uint32_t *head(uint32_t c) { return c ? &head1 : &head0; }
-	__device__ __forceinline__ uint32_t *tail(uint32_t c) { return c ? &tail1 : &tail0; }
+	uint32_t head2, padG[31];
+	uint32_t tail2, padH[31];
+	__device__ __forceinline__ uint32_t *head(uint32_t c) { return c == 0 ? &head0 : c == 1 ? &head1 : &head2; }
+	__device__ __forceinline__ uint32_t *tail(uint32_t c) { return c == 0 ? &tail0 : c == 1 ? &tail1 : &tail2; }
 };
 
 // A worker that has found both rings empty with streams still unaccounted for, for this long, declares the call
@@ -103,13 +108,15 @@ __device__ __forceinline__ void stVolatile(uint32_t *p, uint32_t v) { *reinterpr
 
 // class of a stream's next chunk, or kClassExit when the call is complete for it
 template <class FM, class GS>
-__device__ __forceinline__ uint32_t classifyNextT(const FM &fm, const GS &gs, uint32_t sampleCount, uint32_t holdTicks) {
+__device__ __forceinline__ uint32_t classifyNextT(const FM &fm, const GS &gs, uint32_t sampleCount, uint32_t holdTicks, uint32_t fadeTicks) {
 	const uint32_t pos = gs.callPos;
 	if (pos >= sampleCount || gs.callDrained != 0) return kClassExit;
-	return (sampleCount - pos >= holdTicks && canHoldF32T(fm, gs, holdTicks)) ? kClassHold : kClassGen;
+	if (sampleCount - pos >= holdTicks && canHoldF32T(fm, gs, holdTicks)) return kClassHold;
+	if (fadeTicks != 0u && sampleCount - pos >= fadeTicks && canFadeF32T(fm, gs, fadeTicks)) return kClassFade;
+	return kClassGen;
 }
 __device__ __forceinline__ uint32_t classifyNext(const StreamState *st, uint32_t sampleCount, uint32_t holdTicks) {
-	return classifyNextT(st->fm, st->gen.f32, sampleCount, holdTicks);
+	return classifyNextT(st->fm, st->gen.f32, sampleCount, holdTicks, 0u);
 }
 constexpr uint32_t kRecPieces = sizeof(StreamStateLite) / 16, kStageStride = sizeof(StreamStateLite) + 8, kStageBytes = 32 * kStageStride;
 constexpr uint32_t kHoldPiecesOut = (uint32_t)(offsetof(StreamStateLite, f32) + offsetof(GenStateF32Lite, zre)) / 16;  // everything before the pole state
@@ -121,18 +128,21 @@ __device__ __forceinline__ void schedPush(SchedCtl *ctl, uint32_t *ring, uint32_
 	const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
 	const unsigned mH = __ballot_sync(0xffffffffu, valid && cls == kClassHold);
 	const unsigned mG = __ballot_sync(0xffffffffu, valid && cls == kClassGen);
+	const unsigned mF = __ballot_sync(0xffffffffu, valid && cls == kClassFade);
 	const unsigned mX = __ballot_sync(0xffffffffu, valid && cls == kClassExit);
-	uint32_t baseH = 0, baseG = 0;
+	uint32_t baseH = 0, baseG = 0, baseF = 0;
 	if (lane == 0) {
 		if (mH) baseH = atomicAdd(ctl->tail(kClassHold), (uint32_t)__popc(mH));
 		if (mG) baseG = atomicAdd(ctl->tail(kClassGen), (uint32_t)__popc(mG));
+		if (mF) baseF = atomicAdd(ctl->tail(kClassFade), (uint32_t)__popc(mF));
 	}
 	baseH = __shfl_sync(0xffffffffu, baseH, 0);
 	baseG = __shfl_sync(0xffffffffu, baseG, 0);
+	baseF = __shfl_sync(0xffffffffu, baseF, 0);
 	const uint32_t mask = ringCap - 1u;
 	if (valid && cls != kClassExit) {
 		uint32_t *r = ring + cls * ringCap;
-		uint32_t idx = cls == kClassHold ? baseH + __popc(mH & below) : baseG + __popc(mG & below);
+		uint32_t idx = cls == kClassHold ? baseH + __popc(mH & below) : cls == kClassGen ? baseG + __popc(mG & below) : baseF + __popc(mF & below);
 		if (SEED) {
 			stVolatile(r + (idx & mask), s);  // nobody holds a ticket yet
 		} else {
@@ -143,20 +153,21 @@ __device__ __forceinline__ void schedPush(SchedCtl *ctl, uint32_t *ring, uint32_
 		}
 	}
 	if (SEED) {  // the seed kernel counts the streams in; the workers count them out
-		if (lane == 0 && (mH | mG)) atomicAdd(&ctl->remaining, (uint32_t)__popc(mH | mG));
+		if (lane == 0 && (mH | mG | mF)) atomicAdd(&ctl->remaining, (uint32_t)__popc(mH | mG | mF));
 	} else {
 		if (lane == 0 && mX) atomicSub(&ctl->remaining, (uint32_t)__popc(mX));
 	}
 }
 
-// All 32 lanes of a worker's cascade warp: take a ticket of 32 slots in the ring with the most work waiting (a general
-// chunk costs about as much as two hold chunks of the same length) and collect the streams.  Returns the class, or
-// kClassExit when the call is complete; s = the lane's stream, or kRingEmpty for a lane that got none.
+// All 32 lanes of a worker's cascade warp: take a ticket of 32 slots in the ring with the most work waiting (a general or
+// a fade chunk costs about as much as two hold chunks) and collect the streams.  Returns the class, or kClassExit when the
+// call is complete; s = the lane's stream, or kRingEmpty for a lane that got none.
 // Tickets are only taken from a ring that shows a backlog, so consumers run ahead of the producers by at most the
 // workers that raced for the same entries; those wait for the next pushes.
-// pref: kClassHold / kClassGen = this SM's workers take that class whenever it has a backlog (SM roles: every warp of an SM
-// then runs the same two loops, which is what its instruction caches hold); kClassExit = no preference.
-__device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, uint32_t ringCap, uint32_t &s, uint32_t pref) {
+// primary: the class this SM's workers take whenever its ring can fill a warp (SM roles with the fade class on: an SM then
+// runs ONE loop pair most of the time, which is what its 32 KB instruction cache holds); other rings only when the primary
+// one cannot fill a warp and another can, or is empty.  kClassExit = no role.
+__device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, uint32_t ringCap, uint32_t &s, uint32_t primary) {
 	const unsigned lane = threadIdx.x & 31u;
 	const uint32_t mask = ringCap - 1u;
 	for (;;) {
@@ -165,13 +176,27 @@ __device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, ui
 			uint32_t backoff = 128;
 			unsigned long long idleSince = 0;
 			for (;;) {
-				const int32_t b0 = (int32_t)(ldVolatile(&ctl->tail0) - ldVolatile(&ctl->head0));
-				const int32_t b1 = (int32_t)(ldVolatile(&ctl->tail1) - ldVolatile(&ctl->head1));
-				if (b0 > 0 || b1 > 0) {
-					cls = (2 * b1 >= b0) ? kClassGen : kClassHold;
-					if (pref != kClassExit) cls = pref;
-					if ((cls == kClassGen ? b1 : b0) < 32 && (cls == kClassGen ? b0 : b1) >= 32) cls ^= 1u;  // a full warp beats the weights
-					if ((cls == kClassGen ? b1 : b0) <= 0) cls ^= 1u;
+				int32_t b0 = (int32_t)(ldVolatile(&ctl->tail0) - ldVolatile(&ctl->head0));
+				int32_t b1 = (int32_t)(ldVolatile(&ctl->tail1) - ldVolatile(&ctl->head1));
+				int32_t b2 = (int32_t)(ldVolatile(&ctl->tail2) - ldVolatile(&ctl->head2));
+				if (b0 > 0 || b1 > 0 || b2 > 0) {
+					// most work waiting (general wins a tie with hold, as before); a full warp beats the weights
+					uint32_t pick = kClassGen;
+					int32_t best = -1;
+					bool bestFull = false;
+					auto consider = [&](uint32_t c, int32_t backlog, int32_t score) {
+						if (backlog <= 0) return;
+						const bool full = backlog >= 32;
+						if (best < 0 || (full && !bestFull) || (full == bestFull && score > best)) { pick = c; best = score; bestFull = full; }
+					};
+					consider(kClassGen, b1, 2 * b1);
+					consider(kClassFade, b2, 2 * b2);
+					consider(kClassHold, b0, b0);
+					if (primary < kNumRings) {
+						const int32_t bp = primary == kClassHold ? b0 : primary == kClassGen ? b1 : b2;
+						if (bp >= 32 || (bp > 0 && !bestFull)) pick = primary;
+					}
+					cls = pick;
 					base = atomicAdd(ctl->head(cls), 32u);
 					break;
 				}
@@ -212,8 +237,11 @@ __device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, ui
 			if (lane == 0) {
 				if (got) quit = spins >= 64u;
 				else if ((spins & 15u) == 15u)
-					quit = ldVolatile(&ctl->remaining) == 0u ||
-					       (int32_t)(ldVolatile(ctl->tail(cls ^ 1u)) - ldVolatile(ctl->head(cls ^ 1u))) >= 32;
+				{
+					quit = ldVolatile(&ctl->remaining) == 0u;
+					for (uint32_t c = 0; c < kNumRings; ++c)
+						if (c != cls && (int32_t)(ldVolatile(ctl->tail(c)) - ldVolatile(ctl->head(c))) >= 32) quit = 1u;
+				}
 			}
 			quit = __shfl_sync(0xffffffffu, quit, 0);
 			if (quit) {
@@ -234,13 +262,13 @@ __device__ __forceinline__ uint32_t schedClaim(SchedCtl *ctl, uint32_t *ring, ui
 // start of a call: reset the per-call cursors of every stream and seed the rings
 __global__ void __launch_bounds__(256)
 klatt_sched_seed_kernel(const StreamDesc *__restrict__ descs, const StreamStateLite *__restrict__ lite, uint32_t numStreams,
-                        uint32_t sampleCount, uint32_t holdTicks, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap) {
+                        uint32_t sampleCount, uint32_t holdTicks, uint32_t fadeTicks, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool valid = s < numStreams;
 	uint32_t cls = kClassExit;
 	if (valid) {
 		if (lite) {  // (the import kernel has reset the per-call cursors)
-			cls = classifyNextT(lite[s].fm, lite[s].f32, sampleCount, holdTicks);
+			cls = classifyNextT(lite[s].fm, lite[s].f32, sampleCount, holdTicks, fadeTicks);
 		} else {
 			StreamState *st = descs[s].state;
 			st->gen.f32.callPos = 0;
@@ -258,7 +286,7 @@ __global__ void __launch_bounds__(kPairBlock, KLATT_SCHED_MINB)
 klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__restrict__ lite, uint32_t numStreams, int sampleRate,
                        uint32_t sampleCount, uint32_t holdTicks, uint32_t genTicks, int16_t *__restrict__ out, size_t rowStride,
                        int16_t *__restrict__ scratchRow, NoiseConfig noise, SchedCtl *ctl, uint32_t *ring, uint32_t ringCap,
-                       uint32_t holdSms, uint32_t holdMax) {
+                       uint32_t roleSms, uint32_t holdMax, uint32_t fadeTicks, uint32_t fadeMax) {
 	// dynamic shared memory: [hand-over buffers: 2 workers x 8 KB][staged records: 2 workers x 32 x 552 B (KLATT_SCHED_LITE)]
 	extern __shared__ uint4 schedSmem[];
 	uint4 (*xbuf)[2 * kGroupTicks * 32] = reinterpret_cast<uint4 (*)[2 * kGroupTicks * 32]>(schedSmem);
@@ -273,20 +301,26 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 	const uint32_t tw = (warp >> 1) * 32u + lane;  // thread of the worker
 #endif
 #ifdef KLATT_SCHED_PROFILE
-	long long tClaim = 0, tHold = 0, tGen = 0, tPush = 0, nHold = 0, nGen = 0, nLanes = 0;
+	long long tClaim = 0, tHold = 0, tGen = 0, tFade = 0, tPush = 0, nHold = 0, nGen = 0, nLanes = 0;
 	long long t0 = clock64();
 #endif
-	uint32_t pref = kClassExit;
-	if (holdSms) {  // SM roles: the first holdSms SMs (spread evenly over the SM ids) prefer hold chunks, the others general chunks
+	uint32_t primary = kClassExit;
+	if (roleSms) {  // SM roles: (roleSms & 0xff) SMs take hold chunks first, (roleSms >> 8) SMs fade chunks, the rest general chunks; each kind spread evenly over the SM ids
 		uint32_t smid, nsm;
 		asm("mov.u32 %0, %%smid;" : "=r"(smid));
 		asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-		pref = ((smid + 1) * holdSms / nsm != smid * holdSms / nsm) ? kClassHold : kClassGen;
+		const uint32_t nH = roleSms & 0xffu, nF = roleSms >> 8;
+		if ((smid + 1) * nH / nsm != smid * nH / nsm) {
+			primary = kClassHold;
+		} else {
+			const uint32_t j = smid - smid * nH / nsm, rest = nsm > nH ? nsm - nH : 1u;
+			primary = ((j + 1) * nF / rest != j * nF / rest) ? kClassFade : kClassGen;
+		}
 	}
 	for (;;) {
 		if (cascade) {
 			uint32_t s = kRingEmpty;
-			const uint32_t cls = schedClaim(ctl, ring, ringCap, s, pref);
+			const uint32_t cls = schedClaim(ctl, ring, ringCap, s, primary);
 			if (s == kRingEmpty) s = numStreams;  // idle lanes run the dummy stream
 			__threadfence();
 			work[pair][lane] = s;
@@ -345,12 +379,40 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 				NullOut no;
 				renderHoldF32T<kRoleParallelOnly>(fm, gs, desc, sampleRate, ticks, no, noise, xc);
 			}
+		} else if (cls == kClassFade) {
+			// every stream here has fadeTicks interior fade ticks ahead on the 64-sample grid; run as many whole 64-tick cells as
+			// the shortest of them allows (canFadeF32T: counter + ticks < newF), up to fadeMax
+			uint32_t ticks = fadeTicks;
+			if (fadeMax > fadeTicks) {
+				uint32_t can = 0xffffffffu;
+				if (valid) {
+					const uint32_t left = sampleCount - gs.callPos, inside = fm.newF - 1u - fm.counter;
+					can = left < inside ? left : inside;
+				}
+				can = __reduce_min_sync(0xffffffffu, can);
+				if (can > fadeMax) can = fadeMax;
+				can &= ~63u;
+				if (can > ticks) ticks = can;
+			}
+			if (cascade) {
+				int16_t *row = valid ? out + (size_t)s * rowStride + gs.callPos : scratchRow;
+				OutWriter ow;
+				ow.init(row, ((reinterpret_cast<uintptr_t>(row) & 15u) == 0));
+				renderFadeF32T<kRoleCascade>(fm, gs, desc, sampleRate, ticks, ow, noise, xc);
+			} else {
+				NullOut no;
+				renderFadeF32T<kRoleParallel>(fm, gs, desc, sampleRate, ticks, no, noise, xc);
+			}
 		} else {
 			const uint32_t pos = gs.callPos;
 			uint32_t ticks = 0;
 			if (valid) {
 				ticks = sampleCount - pos;
 				if (ticks > genTicks) ticks = genTicks;
+				if (fadeTicks != 0u) {  // end on the 64-sample grid of the drift control (the fade class starts there)
+					const uint64_t end = gs.samplesGenerated + ticks, grid = end & ~(uint64_t)(kCoarseTicks - 1);
+					if (grid > gs.samplesGenerated && pos + ticks < sampleCount) ticks = (uint32_t)(grid - gs.samplesGenerated);
+				}
 			}
 			int32_t lastUserIndex;
 			uint32_t qHead;
@@ -368,7 +430,7 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 		}
 #if KLATT_SCHED_LITE
 		xc.sync();  // both halves of every stream of this chunk are in the staged records
-		const uint32_t next = (cascade && valid) ? classifyNextT(fm, gs, sampleCount, holdTicks) : kClassExit;
+		const uint32_t next = (cascade && valid) ? classifyNextT(fm, gs, sampleCount, holdTicks, fadeTicks) : kClassExit;
 		// (a hold chunk only moves the frame-manager counters, the oscillators, the noise memories and the section memories:
 		// the first 256 bytes of a record; the pole state, the direct parameters and the drift-control record are unchanged)
 		const uint32_t piecesOut = cls == kClassHold ? kHoldPiecesOut : kRecPieces;
@@ -386,7 +448,7 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 		__threadfence();
 		xc.sync();  // both halves of every stream of this batch are stored
 #ifdef KLATT_SCHED_PROFILE
-		if (cls == kClassHold) { PROF_LAP(tHold) nHold++; } else { PROF_LAP(tGen) nGen++; }
+		if (cls == kClassHold) { PROF_LAP(tHold) nHold++; } else if (cls == kClassFade) { PROF_LAP(tFade) nGen++; } else { PROF_LAP(tGen) nGen++; }
 		nLanes += __popc(__ballot_sync(0xffffffffu, valid));
 #endif
 		if (cascade) {
@@ -403,7 +465,7 @@ klatt_f32_sched_kernel(const StreamDesc *__restrict__ descs, StreamStateLite *__
 		atomicAdd(p + 0, (unsigned long long)tClaim); atomicAdd(p + 1, (unsigned long long)tHold);
 		atomicAdd(p + 2, (unsigned long long)tGen); atomicAdd(p + 3, (unsigned long long)tPush);
 		atomicAdd(p + 4, (unsigned long long)nHold); atomicAdd(p + 5, (unsigned long long)nGen);
-		atomicAdd(p + 6, (unsigned long long)nLanes);
+		atomicAdd(p + 6, (unsigned long long)nLanes); atomicAdd(p + 7, (unsigned long long)tFade);
 	}
 #endif
 }
@@ -416,13 +478,13 @@ size_t klattF32SchedLiteBytes(uint32_t numStreams, uint32_t numBlocks) {
 	return sizeof(StreamStateLite) * ((size_t)numStreams + 2 * (size_t)numBlocks);
 }
 
-// One call through the stream scheduler: seed the rings, then one persistent launch.  scratch: ring[2 * ringCap]
-// (ringCap a power of two >= 2 * numStreams), ctl, scratchRow[max(holdTicks, holdMax)].  descs holds numStreams + 1 entries.
+// One call through the stream scheduler: seed the rings, then one persistent launch.  scratch: ring[3 * ringCap]
+// (ringCap a power of two >= 2 * numStreams), ctl, scratchRow[max(holdTicks, holdMax, fadeMax)].  descs holds numStreams + 1 entries.
 cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, int sampleRate, uint32_t sampleCount,
                                 uint32_t holdTicks, uint32_t genTicks, int16_t *out, size_t rowStride, uint32_t *samplesWritten,
                                 StreamResult *results, NoiseConfig noise, uint32_t *ring, uint32_t ringCap, void *ctlMem,
                                 int16_t *scratchRow, uint32_t numBlocks, uint32_t *hostFault, void *liteMem, uint32_t holdMax,
-                                cudaStream_t stream, unsigned long long *launchCounter) {
+                                uint32_t fadeTicks, uint32_t fadeMax, uint32_t roleSms, cudaStream_t stream, unsigned long long *launchCounter) {
 	if (numStreams == 0 || sampleCount == 0) return cudaSuccess;
 	SchedCtl *ctl = static_cast<SchedCtl *>(ctlMem);
 	StreamStateLite *lite = KLATT_SCHED_LITE ? static_cast<StreamStateLite *>(liteMem) : nullptr;
@@ -432,15 +494,15 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
 		if (ea != cudaSuccess) return ea;
 		attrSet = true;
 	}
-	cudaError_t e = cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * 2 * (size_t)ringCap, stream);
+	if (!lite) fadeTicks = 0;  // (the fade loop works on the compact records)
+	cudaError_t e = cudaMemsetAsync(ring, 0xff, sizeof(uint32_t) * kNumRings * (size_t)ringCap, stream);
 	if (e != cudaSuccess) return e;
 	if ((e = cudaMemsetAsync(ctl, 0, 2048, stream)) != cudaSuccess) return e;
 	const uint32_t batches = (numStreams + 31) / 32;
 	// paired workers: two warps per batch, two batches per block
 	const uint32_t blocksWanted = (batches + 1) / 2, grid = blocksWanted < numBlocks ? blocksWanted : numBlocks;
 	if (lite && (e = launchKlattLiteImport(descs, numStreams, 2 * grid, lite, stream)) != cudaSuccess) return e;
-	klatt_sched_seed_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, lite, numStreams, sampleCount, holdTicks, ctl, ring, ringCap);
-	static const uint32_t holdSms = getenv("NVSP_SCHED_HOLD_SMS") ? (uint32_t)atoi(getenv("NVSP_SCHED_HOLD_SMS")) : 0u;
+	klatt_sched_seed_kernel<<<(numStreams + 255) / 256, 256, 0, stream>>>(descs, lite, numStreams, sampleCount, holdTicks, fadeTicks, ctl, ring, ringCap);
 	// NVSP_L2_PERSIST=1: pin the record array in the L2 (persisting access-policy window on the launching stream).  Measured
 	// (DESIGN.md section 5d): DRAM traffic of a config-3 step 59.7 -> 51.5 GB, but every workload gets SLOWER in warm
 	// back-to-back steps (config 3 +1.2 %, config 5 +3.3 %, config 2 -- 190 MB of records against a 79 MB set-aside -- +8 %),
@@ -469,7 +531,7 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
 		}
 	}
 	klatt_f32_sched_kernel<<<grid, kPairBlock, schedSmemBytes(), stream>>>(descs, lite, numStreams, sampleRate, sampleCount, holdTicks, genTicks,
-	                                                                        out, rowStride, scratchRow, noise, ctl, ring, ringCap, holdSms, holdMax);
+	                                                                        out, rowStride, scratchRow, noise, ctl, ring, ringCap, roleSms, holdMax, fadeTicks, fadeMax);
 	if (windowSet) {
 		cudaStreamAttrValue attr;
 		memset(&attr, 0, sizeof attr);
@@ -491,8 +553,8 @@ cudaError_t launchKlattF32Sched(const StreamDesc *descs, uint32_t numStreams, in
 		cudaStreamSynchronize(stream);
 		cudaMemcpy(h, reinterpret_cast<unsigned long long *>(ctl) + 128, sizeof(h), cudaMemcpyDeviceToHost);
 		for (int k = 0; k < 2; ++k)
-			fprintf(stderr, "[sched profile] %s warps: claim %.1f  hold %.1f  gen %.1f  push %.1f Mcycles; batches hold %llu gen %llu; lanes/batch %.2f\n",
-			        k ? "parallel" : "cascade ", h[8 * k] / 1e6, h[8 * k + 1] / 1e6, h[8 * k + 2] / 1e6, h[8 * k + 3] / 1e6, h[8 * k + 4], h[8 * k + 5],
+			fprintf(stderr, "[sched profile] %s warps: claim %.1f  hold %.1f  gen %.1f  fade %.1f  push %.1f Mcycles; batches hold %llu gen+fade %llu; lanes/batch %.2f\n",
+			        k ? "parallel" : "cascade ", h[8 * k] / 1e6, h[8 * k + 1] / 1e6, h[8 * k + 2] / 1e6, h[8 * k + 7] / 1e6, h[8 * k + 3] / 1e6, h[8 * k + 4], h[8 * k + 5],
 			        (double)h[8 * k + 6] / (double)(h[8 * k + 4] + h[8 * k + 5]));
 	}
 #endif

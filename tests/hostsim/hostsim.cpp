@@ -89,7 +89,7 @@ extern "C" int hostsim_render_f32(int sampleRate, const double *frames, const ui
 extern "C" int hostsim_render_f32_cells(int sampleRate, const double *frames, const uint32_t *minDur, const uint32_t *fadeDur,
                                         const int32_t *userIndex, const uint8_t *isNull, uint32_t nFrames, uint64_t seed,
                                         uint64_t streamId, uint32_t maxSamples, int16_t *out, uint32_t holdTicks, uint32_t fadeTicks,
-                                        uint32_t *ticksByClass /* [3]: hold, fade, general */, int32_t *lastIndexOut) {
+                                        uint32_t *ticksByClass /* [3]: hold, fade, general */, int32_t *lastIndexOut, uint32_t fadeMax) {
 	StreamStateLite *st = (StreamStateLite *)calloc(1, sizeof(StreamStateLite));
 	st->fm.lastUserIndex = -1;
 	st->fm.curIsNull = 1;
@@ -127,8 +127,17 @@ extern "C" int hostsim_render_f32_cells(int sampleRate, const double *frames, co
 			continue;
 		}
 		if (left >= fadeTicks && canFadeF32T(st->fm, st->f32, fadeTicks)) {
-			renderFadeF32T<kRoleBoth>(st->fm, st->f32, d, sampleRate, fadeTicks, ao, nc, xc);
-			total += fadeTicks; used[1] += fadeTicks;
+			// (the ring scheduler stretches a fade chunk to the interior fade ticks its streams have left, in whole cells)
+			uint32_t ticks = fadeTicks;
+			if (fadeMax > fadeTicks) {
+				uint32_t can = st->fm.newF - 1u - st->fm.counter;
+				if (can > left) can = left;
+				if (can > fadeMax) can = fadeMax;
+				can &= ~63u;
+				if (can > ticks) ticks = can;
+			}
+			renderFadeF32T<kRoleBoth>(st->fm, st->f32, d, sampleRate, ticks, ao, nc, xc);
+			total += ticks; used[1] += ticks;
 			continue;
 		}
 		uint32_t want = (uint32_t)kCoarseTicks - (uint32_t)(st->f32.samplesGenerated & (uint64_t)(kCoarseTicks - 1));

@@ -27,7 +27,7 @@ def lib():
 
 
 def render_f32_cells(sr, frames, min_dur, fade_dur, is_null=None, user_index=None, max_samples=None, seed=0, stream=0,
-                     hold_ticks=128, fade_ticks=64):
+                     hold_ticks=128, fade_ticks=64, fade_max=0):
     """The block scheduler's execution model on one stream: compact state, hold / fade / general cells.  Returns
     (pcm, last_index, [hold ticks, fade ticks, general ticks])."""
     frames = np.ascontiguousarray(frames, dtype=np.float64).reshape(-1, 47)
@@ -44,7 +44,7 @@ def render_f32_cells(sr, frames, min_dur, fade_dur, is_null=None, user_index=Non
     li = ctypes.c_int32(0)
     used = (ctypes.c_uint32 * 3)()
     n = lib().hostsim_render_f32_cells(sr, ptr(frames), ptr(m), ptr(f), ptr(ux), ptr(nul), len(m), seed, stream, max_samples,
-                                       ptr(out), hold_ticks, fade_ticks, used, ctypes.byref(li))
+                                       ptr(out), hold_ticks, fade_ticks, used, ctypes.byref(li), fade_max)
     return out[:n], li.value, list(used)
 
 

@@ -85,3 +85,27 @@ def test_cells_equal_one_shot_bitwise(golden_config1, hold, fade):
         got, _, used = sim.render_f32_cells(16000, fr, m, f, nul, ux, seed=8, stream=s, hold_ticks=hold, fade_ticks=fade)
         np.testing.assert_array_equal(got, one)
         assert used[1] > 0.4 * len(one), used   # 60 % of these ticks are fade ticks
+
+
+@pytest.mark.parametrize("hold,fade,fade_max", [(256, 128, 0), (256, 128, 512), (256, 64, 4096), (256, 192, 320)])
+def test_long_fade_chunks_equal_one_shot_bitwise(hold, fade, fade_max):
+    """The ring scheduler's fade class (klatt_f32_sched.cu): a fade chunk is several 64-tick cells of renderFadeF32T in one
+    call (the coarse re-base at the head of every cell), stretched to the interior fade ticks the stream has left.  Same
+    bits as the one-shot general render."""
+    sr = 22050
+    for sid, secs in ((11, 2.0), (977, 2.5)):
+        fr, m, f, nul, ux = workloads.random_stream(sid, secs, sr)
+        n = int(secs * sr)
+        one, li = sim.render_f32(sr, fr, m, f, nul, ux, max_samples=n, seed=3, stream=sid)
+        got, li2, used = sim.render_f32_cells(sr, fr, m, f, nul, ux, max_samples=n, seed=3, stream=sid, hold_ticks=hold, fade_ticks=fade,
+                                              fade_max=fade_max)
+        np.testing.assert_array_equal(got, one)
+        assert li2 == li and sum(used) == n
+        assert used[1] > 0.05 * n, used
+    fb = workloads.vowel_chart(1, pairs=2)
+    for s in range(fb.num_streams):
+        fr, m, f, nul, ux = fb.stream(s)
+        one, _ = sim.render_f32(16000, fr, m, f, nul, ux, seed=8, stream=s)
+        got, _, used = sim.render_f32_cells(16000, fr, m, f, nul, ux, seed=8, stream=s, hold_ticks=hold, fade_ticks=fade, fade_max=fade_max)
+        np.testing.assert_array_equal(got, one)
+        assert used[1] > 0.4 * len(one), used

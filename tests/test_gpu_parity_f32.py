@@ -144,10 +144,15 @@ def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
     fb = workloads._concat(sr, streams, np.arange(500, 500 + n, dtype=np.uint64))
     count = int(1.0 * sr)
     res = {}
-    for mode, min_streams in (("single", "100000000"), ("rounds", "1"), ("sched", "1"), ("block", "1")):
+    for mode, min_streams in (("single", "100000000"), ("rounds", "1"), ("sched", "1"), ("sched_fade", "1"), ("sched_fade_roles", "1"), ("block", "1")):
         monkeypatch.setenv("NVSP_ROUNDS_MIN_STREAMS", min_streams)
         monkeypatch.setenv("NVSP_GROUPS", "3")
-        monkeypatch.setenv("NVSP_SCHED", {"sched": "rings", "block": "block"}.get(mode, "rounds"))
+        monkeypatch.setenv("NVSP_SCHED", {"sched": "rings", "sched_fade": "rings", "sched_fade_roles": "rings", "block": "block"}.get(mode, "rounds"))
+        # the ring scheduler's fade class (straight-line fade loop on 64-tick cells), with and without SM roles
+        monkeypatch.setenv("NVSP_SCHED_FADE_TICKS", "128" if mode.startswith("sched_fade") else "0")
+        monkeypatch.setenv("NVSP_SCHED_FADE_MAX", "320")
+        monkeypatch.setenv("NVSP_SCHED_FADE_SMS", "40" if mode == "sched_fade_roles" else "0")
+        monkeypatch.setenv("NVSP_SCHED_HOLD_SMS", "30" if mode == "sched_fade_roles" else "0")
         monkeypatch.setenv("NVSP_BLOCK_MIN_STREAMS", "1")
         monkeypatch.setenv("NVSP_BLOCK_BLOCKS", "3")   # 68 streams per block on 8 workers: the queues fill and drain
         monkeypatch.setenv("NVSP_SCHED_BLOCKS", "3")  # fewer workers than stream batches: streams queue up in the rings
@@ -167,6 +172,8 @@ def test_f32_rounds_equal_single_launch_bitwise(monkeypatch, port):
     assert res["block"][3] == res["single"][3] + 2 * 3, "the block scheduler did not run (import + workers + export per call)"
     for k in range(3):
         np.testing.assert_array_equal(res["single"][k], res["sched"][k])
+        np.testing.assert_array_equal(res["single"][k], res["sched_fade"][k])
+        np.testing.assert_array_equal(res["single"][k], res["sched_fade_roles"][k])
         np.testing.assert_array_equal(res["single"][k], res["block"][k])
     np.testing.assert_array_equal(res["single"][1], res["rounds"][1])
     np.testing.assert_array_equal(res["single"][2], res["rounds"][2])
@@ -195,7 +202,8 @@ def test_f32_ring_scheduler_long_hold_chunks_bitwise(monkeypatch):
     n = len(ids)
     counts = (7001, 640, 12000)
     res = {}
-    for mode, hold_max in (("single", None), ("cap256", "256"), ("cap576", "576"), ("cap1024", "1024"), ("cap65536", "65536")):
+    for mode, hold_max in (("single", None), ("cap256", "256"), ("cap576", "576"), ("cap1024", "1024"), ("cap65536", "65536"),
+                           ("fade64", "1024"), ("fade192", "4096")):
         monkeypatch.setenv("NVSP_ROUNDS_MIN_STREAMS", "100000000" if mode == "single" else "1")
         monkeypatch.setenv("NVSP_SCHED", "rings")
         monkeypatch.setenv("NVSP_SCHED_BLOCKS", "2")
@@ -203,6 +211,9 @@ def test_f32_ring_scheduler_long_hold_chunks_bitwise(monkeypatch):
         monkeypatch.setenv("NVSP_SCHED_GEN_TICKS", "192")
         if hold_max:
             monkeypatch.setenv("NVSP_SCHED_HOLD_MAX", hold_max)
+        # (the vowel chart's 400 ms fades: fade chunks of many cells, stretched to the cap)
+        monkeypatch.setenv("NVSP_SCHED_FADE_TICKS", {"fade64": "64", "fade192": "192"}.get(mode, "0"))
+        monkeypatch.setenv("NVSP_SCHED_FADE_MAX", {"fade64": "64", "fade192": "2048"}.get(mode, "512"))
         b = player.Batch(sr, n, precision=player.PRECISION_FP32, seed=5, stream_ids=fb.stream_ids)
         b.set_frames_host(fb)
         parts, written = [], np.zeros(n, dtype=np.int64)
@@ -214,6 +225,6 @@ def test_f32_ring_scheduler_long_hold_chunks_bitwise(monkeypatch):
         b.close()
     assert res["cap1024"][3] == res["single"][3] + 3 * len(counts), "the ring scheduler did not run"
     assert res["single"][0].any()
-    for mode in ("cap256", "cap576", "cap1024", "cap65536"):
+    for mode in ("cap256", "cap576", "cap1024", "cap65536", "fade64", "fade192"):
         for k in range(3):
             np.testing.assert_array_equal(res["single"][k], res[mode][k], err_msg=mode)

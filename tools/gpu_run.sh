@@ -304,5 +304,24 @@ import json; d=json.load(open('$O/bench_pull.json')); print(d['ms_per_step'], js
 import json; d=json.load(open('$O/bench_pull_nohelpers.json')); print(d['ms_per_step'], json.dumps(d.get('batch_of_players'))[:600])"
 	NVSP_PULL_TIMING=1 NVSP_HOST_THREADS=3 timeout 300 python bench.py --workload pull > $O/bench_pull_3.json 2> $O/bench_pull_3.err; echo "bench pull (3 helpers) rc=$?"; grep "pull batch" $O/bench_pull_3.err | tail -3
 	;;
+fd)  # ring scheduler with the fade class: bitwise tests, then fade thresholds / SM roles on config 3
+	timeout 400 python -m pytest tests/test_gpu_parity_f32.py -q -m gpu -x > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -3 $O/pytest_sub.log
+	try "NVSP_SCHED_FADE_TICKS=0"
+	try "NVSP_SCHED_FADE_TICKS=128"
+	try "NVSP_SCHED_FADE_TICKS=128 NVSP_SCHED_FADE_SMS=50"
+	try "NVSP_SCHED_FADE_TICKS=128 NVSP_SCHED_FADE_SMS=74"
+	try "NVSP_SCHED_FADE_TICKS=192 NVSP_SCHED_FADE_SMS=60 NVSP_SCHED_GEN_TICKS=256"
+	try "NVSP_SCHED_FADE_TICKS=64 NVSP_SCHED_FADE_SMS=74 NVSP_SCHED_GEN_TICKS=256"
+	try "NVSP_SCHED_FADE_TICKS=128 NVSP_SCHED_FADE_SMS=60 NVSP_LIB=$PWD/tools/_variants/libprof.so"
+	;;
+fd2)  # fade class with SM roles (a primary class per SM)
+	timeout 400 python -m pytest tests/test_gpu_parity_f32.py -q -m gpu -x -k "rounds_equal or long_hold" > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -3 $O/pytest_sub.log
+	try "NVSP_SCHED_FADE_TICKS=128 NVSP_SCHED_HOLD_SMS=27 NVSP_SCHED_FADE_SMS=30"
+	try "NVSP_SCHED_FADE_TICKS=128 NVSP_SCHED_HOLD_SMS=27 NVSP_SCHED_FADE_SMS=40"
+	try "NVSP_SCHED_FADE_TICKS=128 NVSP_SCHED_HOLD_SMS=20 NVSP_SCHED_FADE_SMS=30"
+	try "NVSP_SCHED_FADE_TICKS=192 NVSP_SCHED_FADE_MAX=1024 NVSP_SCHED_HOLD_SMS=27 NVSP_SCHED_FADE_SMS=30"
+	try "NVSP_SCHED_FADE_TICKS=128 NVSP_SCHED_HOLD_SMS=27 NVSP_SCHED_FADE_SMS=30 NVSP_LIB=$PWD/tools/_variants/libprof.so"
+	try "NVSP_SCHED_FADE_TICKS=0 NVSP_SCHED_HOLD_SMS=28"
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
