@@ -106,14 +106,16 @@ KLATT_HD uint64_t pullVibBefore(const PullSeg &s, uint32_t c) {
 }
 
 // cur.voicePitch on tick (seg, c): stale on the pop tick, the fade (src/utils.h:20-23), the landing value on the landing
-// and the swap tick, then the hold glide (src/frame.cpp:77) as an arithmetic progression
+// and the swap tick, then the hold glide: the reference adds voicePitchInc once per tick (src/frame.cpp:77), and a sum of
+// roundings is not a product -- glideExact (klatt_f32_core.cuh) reproduces the c - F - 1 additions bit for bit.  PullOsc
+// below walks a chunk tick by tick and only seeks this way; from one hold tick to the next it adds, as the reference does.
 KLATT_HD double pullPitchAt(const PullSeg &s, uint32_t c) {
 	if (c == 0) return s.pitchStale;
 	const double o = s.pitchOld, n = s.pitchNew;
 	if (c < s.F) return (n != n) ? o : o + ((n - o) * ((double)c / (double)s.F));
 	const double landing = (n != n) ? o : o + ((n - o) * 1.0);
 	if (c <= s.F + 1) return landing;
-	return landing + (double)(c - s.F - 1) * s.pitchInc;
+	return glideExact(landing, s.pitchInc, (uint64_t)(c - s.F - 1));
 }
 
 KLATT_HD float pullDirAt(const PullSeg &s, int slot, uint32_t c) {
@@ -248,10 +250,23 @@ struct PullSourceSums {
 struct PullOsc {  // vibrato + pitch along the pull
 	PullCursor cur;
 	uint64_t vibPos;
+	double glide;                     // voicePitch on hold tick (glideSeg, glideC)
+	uint32_t glideSeg, glideC;
 	KLATT_HD void seek(const PullCtx &X, uint32_t t) {
 		cur.seek(X, t);
 		const PullSeg &S = X.segs[cur.s];
 		vibPos = S.vibPosAtPop + pullVibBefore(S, cur.c);
+		glide = 0.0; glideSeg = 0xffffffffu; glideC = 0;
+	}
+	// cur.voicePitch on the current tick: pullPitchAt, with the hold glide carried from tick to tick by the reference's own
+	// addition (src/frame.cpp:77)
+	KLATT_HD double pitch(const PullSeg &S) {
+		const uint32_t c = cur.c;
+		if (c <= S.F + 1u) return pullPitchAt(S, c);
+		if (glideSeg == cur.s && glideC + 1u == c) glide = glide + S.pitchInc;
+		else glide = pullPitchAt(S, c);
+		glideSeg = cur.s; glideC = c;
+		return glide;
 	}
 	// what this tick adds to the glottal phase, in cycles: (pitch * vibrato) / sampleRate as the reference rounds it
 	// (src/speechWaveGenerator.cpp:72-74, :55)
@@ -260,7 +275,7 @@ struct PullOsc {  // vibrato + pitch along the pull
 		vibPos += (uint64_t)pullVibInc(S, cur.c);
 		float vph = (float)(int32_t)(uint32_t)(vibPos >> 32) * 2.3283064365386963e-10f;
 		float vib = (sinTurns(vph) * 0.06f) * pullDirAt(S, dVibratoPitchOffset, cur.c);
-		double m = pullPitchAt(S, cur.c) * ((double)vib + 1.0);
+		double m = pitch(S) * ((double)vib + 1.0);
 		return divideBySampleRate(m, srD, srInv);
 	}
 	KLATT_HD void next(const PullCtx &X) {

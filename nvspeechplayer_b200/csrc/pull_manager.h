@@ -112,7 +112,8 @@ private:
 	static double lerp(double o, double nv, double ratio) { return (nv != nv) ? o : o + ((nv - o) * ratio); }  // src/utils.h:20-23
 
 	// Bring curFrame (and the pitch written back into the old request, src/frame.cpp:77-78) to what the reference holds
-	// after the last generated tick.  Only pops and purges look at them, so they are evaluated lazily, in closed form.
+	// after the last generated tick.  Only pops and purges look at them, so they are evaluated lazily (the hold glide as the
+	// reference's repeated addition, seeked with glideExact).
 	void syncToCounter() {
 		if (!inRequest) return;
 		const uint32_t c = counter, F = info.F;
@@ -121,8 +122,8 @@ private:
 		const uint32_t k = c < F ? c : F;
 		const double ratio = (double)k / (double)F;
 		for (int i = 0; i < kNumParams; ++i) cur[i] = lerp(reqOld[i], reqNew[i], ratio);
-		if (c >= F + 2) {
-			cur[kVoicePitch] = cur[kVoicePitch] + (double)(c - F - 1) * info.pitchInc;
+		if (c >= F + 2) {  // the hold glide: c - F - 1 additions of the increment, with the reference's roundings (glideExact)
+			cur[kVoicePitch] = glideExact(cur[kVoicePitch], info.pitchInc, (uint64_t)(c - F - 1));
 			old.frame[kVoicePitch] = cur[kVoicePitch];
 		}
 	}

@@ -420,3 +420,20 @@ extern "C" int hostsim_host_pool(unsigned reps, unsigned maxN, unsigned *helpers
 	}
 	return 0;
 }
+
+
+// ---- voicePitch of the pull path on ticks c0 .. c0+n-1 of one request, as a chunk's PullOsc walks them (seek, then tick by
+// tick): must be the reference's fade formula followed by its repeated addition (src/frame.cpp:49-52, :77), bit for bit ----
+extern "C" void hostsim_pull_pitch_walk(double pitchOld, double pitchNew, double pitchInc, uint32_t F, uint32_t c0, uint32_t n, double *out) {
+	PullSeg seg;
+	memset(&seg, 0, sizeof seg);
+	seg.F = F; seg.pitchOld = pitchOld; seg.pitchNew = pitchNew; seg.pitchInc = pitchInc; seg.pitchStale = pitchOld;
+	PullOsc w;
+	memset(&w, 0, sizeof w);
+	w.glideSeg = 0xffffffffu;
+	w.cur.s = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		w.cur.c = c0 + i;
+		out[i] = w.pitch(seg);
+	}
+}

@@ -323,5 +323,11 @@ fd2)  # fade class with SM roles (a primary class per SM)
 	try "NVSP_SCHED_FADE_TICKS=128 NVSP_SCHED_HOLD_SMS=27 NVSP_SCHED_FADE_SMS=30 NVSP_LIB=$PWD/tools/_variants/libprof.so"
 	try "NVSP_SCHED_FADE_TICKS=0 NVSP_SCHED_HOLD_SMS=28"
 	;;
+pl3)  # exact hold glide in the pull path: pull tests (oracle parity, batch vs solo), smoke, pull bench
+	timeout 400 python -m pytest tests/test_gpu_pull.py tests/test_gpu_batch_handles.py tests/test_gpu_reference_wrapper.py -q -m gpu > $O/pytest_pull.log 2>&1; echo "pull tests rc=$?"; tail -3 $O/pytest_pull.log
+	timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $O/smoke.log
+	timeout 300 python bench.py --workload pull > $O/bench_pull.json 2> $O/bench_pull.err; echo "bench pull rc=$?"; python -c "
+import json; d=json.load(open('$O/bench_pull.json')); print(d['ms_per_step'], json.dumps(d.get('batch_of_players'))[:400], json.dumps(d.get('latency_ms'))[:300])"
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
