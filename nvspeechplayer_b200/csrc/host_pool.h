@@ -10,6 +10,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 
 namespace klatt {
 
@@ -25,7 +26,7 @@ public:
 	}
 	size_t helpers() const { return workers.size(); }
 	void parallelFor(size_t n, size_t grain, const std::function<void(size_t)> &fn) {
-		if (workers.empty() || n <= grain) {
+		if (workers.empty() || n <= grain || getpid() != owner) {  // (a forked child has the pool object but not its threads)
 			for (size_t i = 0; i < n; ++i) fn(i);
 			return;
 		}
@@ -46,7 +47,10 @@ public:
 			stop = true;
 		}
 		cv.notify_all();
-		for (std::thread &t : workers) t.join();
+		for (std::thread &t : workers) {
+			if (getpid() == owner) t.join();
+			else t.detach();
+		}
 	}
 
 private:
@@ -80,6 +84,7 @@ private:
 		}
 	}
 	std::vector<std::thread> workers;
+	const pid_t owner = getpid();
 	std::mutex mu, callMu;
 	std::condition_variable cv, cvDone;
 	const std::function<void(size_t)> *job = nullptr;

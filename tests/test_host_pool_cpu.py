@@ -23,3 +23,16 @@ def test_no_helpers_is_the_serial_loop():
             "rc = L.hostsim_host_pool(200, 50, ctypes.byref(h)); assert rc == 0 and h.value == 0, (rc, h.value)")
     env = dict(os.environ, NVSP_HOST_THREADS="0")
     subprocess.check_call([sys.executable, "-c", code], env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def test_forked_child_runs_serially():
+    """A fork()ed child inherits the pool object without its threads: parallelFor must fall back to the plain loop, not wait for
+    helpers that do not exist."""
+    code = ("import ctypes, os; from tests.hostsim import sim; L = sim.lib(); h = ctypes.c_uint(0); "
+            "assert L.hostsim_host_pool(50, 300, ctypes.byref(h)) == 0; "
+            "pid = os.fork(); "
+            "rc = L.hostsim_host_pool(50, 300, ctypes.byref(h)); "
+            "os._exit(0 if rc == 0 else 3) if pid == 0 else None; "
+            "_, st = os.waitpid(pid, 0); assert os.WIFEXITED(st) and os.WEXITSTATUS(st) == 0, st")
+    subprocess.run([sys.executable, "-c", code], check=True, timeout=60,
+                   cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
