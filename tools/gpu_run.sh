@@ -329,5 +329,12 @@ pl3)  # exact hold glide in the pull path: pull tests (oracle parity, batch vs s
 	timeout 300 python bench.py --workload pull > $O/bench_pull.json 2> $O/bench_pull.err; echo "bench pull rc=$?"; python -c "
 import json; d=json.load(open('$O/bench_pull.json')); print(d['ms_per_step'], json.dumps(d.get('batch_of_players'))[:400], json.dumps(d.get('latency_ms'))[:300])"
 	;;
+si)  # stage-in copy with 6 loads in flight per thread: bitwise tests, tries, the bench line
+	timeout 300 python -m pytest tests/test_gpu_parity_f32.py tests/test_gpu_batch_handles.py -q -m gpu -x > $O/pytest_sub.log 2>&1; echo "gpu subset rc=$?"; tail -2 $O/pytest_sub.log
+	try "NVSP_X=stagein6"
+	try "NVSP_X=stagein6" --workload vowel
+	try "NVSP_X=stagein6" --workload midi
+	timeout 300 python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; cut -c1-330 $O/bench.json
+	;;
 *) echo "unknown stage $stage"; exit 2;;
 esac
